@@ -1,0 +1,134 @@
+"""GPU parity of the tcgen05 GEMM family (through the C-ABI) against plain torch fp32 math on the same bf16 inputs."""
+import ctypes as C
+import math
+
+import pytest
+import torch
+
+from var_b200 import lib as L
+
+pytestmark = pytest.mark.gpu
+
+
+def _gemm(A, W, epi, force_bn=0, **kw):
+    lib = L.load()
+    a = L.GemmArgs()
+    a.A, a.W = A.data_ptr(), W.data_ptr()
+    a.M, a.K = A.shape
+    a.N = W.shape[0]
+    a.epilogue, a.force_bn = epi, force_bn
+    for k, v in kw.items():
+        setattr(a, k, v.data_ptr() if isinstance(v, torch.Tensor) else v)
+    L.check(lib.var_b200_gemm_bf16(C.byref(a), L.current_stream()), "gemm")
+    torch.cuda.synchronize()
+
+
+def _ref(A, W):
+    return A.float() @ W.float().t()
+
+
+@pytest.mark.parametrize("b_mn", [0, 1])
+@pytest.mark.parametrize("N", [64, 128, 256])
+def test_umma_probe(N, b_mn):
+    torch.manual_seed(N + b_mn)
+    lib = L.load()
+    A = torch.randn(128, 64, device="cuda").bfloat16()
+    B = (torch.randn(64, N, device="cuda") if b_mn else torch.randn(N, 64, device="cuda")).bfloat16()
+    D = torch.full((128, N), float("nan"), device="cuda")
+    L.check(lib.var_b200_umma_probe(A.data_ptr(), B.data_ptr(), D.data_ptr(), N, b_mn, L.current_stream()), "probe")
+    torch.cuda.synchronize()
+    ref = A.float() @ (B.float() if b_mn else B.float().t())
+    err = (D - ref).abs().max().item()
+    assert err < 1e-3, f"N={N} b_mn={b_mn} max err {err}"
+
+
+@pytest.mark.parametrize("M,N,K,bn", [
+    (128, 256, 64, 0), (128, 256, 256, 0), (300, 1024, 1024, 0), (5440, 3072, 1024, 0),
+    (680, 1920, 1920, 0), (680, 1920, 1920, 128), (1000, 4096, 1024, 256), (257, 5760, 1920, 0),
+    (4096, 7680, 1920, 0), (128, 1024, 4096, 128),
+])
+def test_gemm_bias_f32(M, N, K, bn):
+    torch.manual_seed(0)
+    A = (torch.randn(M, K, device="cuda") / math.sqrt(K)).bfloat16()
+    W = torch.randn(N, K, device="cuda").bfloat16()
+    bias = torch.randn(N, device="cuda")
+    out = torch.full((M, N), float("nan"), device="cuda")
+    _gemm(A, W, L.EPI_BIAS_F32, force_bn=bn, bias=bias, out=out)
+    ref = _ref(A, W) + bias
+    err = (out - ref).abs().max().item()
+    assert torch.isfinite(out).all()
+    assert err < 2e-3, f"max err {err}"
+
+
+def test_gemm_gelu_bf16():
+    torch.manual_seed(1)
+    M, N, K = 1360, 4096, 1024
+    A = (torch.randn(M, K, device="cuda") / math.sqrt(K)).bfloat16()
+    W = torch.randn(N, K, device="cuda").bfloat16()
+    bias = torch.randn(N, device="cuda")
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    _gemm(A, W, L.EPI_GELU_BF16, bias=bias, out=out)
+    ref = torch.nn.functional.gelu(_ref(A, W) + bias, approximate="tanh")
+    err = (out.float() - ref).abs().max().item()
+    assert err < 3e-2, f"max err {err}"
+
+
+def test_gemm_gate_resid_inplace():
+    torch.manual_seed(2)
+    n_seq, l, N, K = 6, 100, 1024, 4096
+    M = n_seq * l
+    A = (torch.randn(M, K, device="cuda") / math.sqrt(K)).bfloat16()
+    W = torch.randn(N, K, device="cuda").bfloat16()
+    bias = torch.randn(N, device="cuda")
+    x = torch.randn(M, N, device="cuda")
+    ada = torch.randn(n_seq, 6 * N, device="cuda")
+    ref = x + (_ref(A, W) + bias) * ada[:, N:2 * N].repeat_interleave(l, dim=0)
+    _gemm(A, W, L.EPI_GATE_RESID, bias=bias, out=x, resid=x, gate=ada[:, N:], rows_per_seq=l, gate_ld=6 * N)
+    err = (x - ref).abs().max().item()
+    assert err < 5e-3, f"max err {err}"
+
+
+def test_gemm_qkv_scatter():
+    torch.manual_seed(3)
+    n_seq, l, H, Lmax, pos0 = 4, 36, 16, 91, 55
+    Cdim = H * 64
+    M = n_seq * l
+    A = (torch.randn(M, Cdim, device="cuda") / math.sqrt(Cdim)).bfloat16()
+    W = torch.randn(3 * Cdim, Cdim, device="cuda").bfloat16()
+    bias = torch.randn(3 * Cdim, device="cuda")
+    bias[Cdim:2 * Cdim] = 0
+    scale = torch.rand(H, device="cuda") * 5 + 1
+    q = torch.zeros(n_seq, H, l, 64, device="cuda", dtype=torch.bfloat16)
+    kc = torch.zeros(n_seq, H, Lmax, 64, device="cuda", dtype=torch.bfloat16)
+    vc = torch.zeros_like(kc)
+    _gemm(A, W, L.EPI_QKV, bias=bias, q_out=q, k_cache=kc, v_cache=vc, q_scale=scale, C=Cdim, H=H, pos0=pos0, Lmax=Lmax,
+          rows_per_seq=l)
+    qkv = (_ref(A, W) + bias).view(n_seq, l, 3, H, 64).permute(2, 0, 3, 1, 4)
+    qr = torch.nn.functional.normalize(qkv[0], dim=-1) * scale.view(1, H, 1, 1)
+    kr = torch.nn.functional.normalize(qkv[1], dim=-1)
+    vr = qkv[2]
+    assert (q.float() - qr).abs().max().item() < 4e-2
+    assert (kc[:, :, pos0:pos0 + l].float() - kr).abs().max().item() < 1e-2
+    assert (vc[:, :, pos0:pos0 + l].float() - vr).abs().max().item() < 4e-2
+    assert kc[:, :, :pos0].abs().max().item() == 0 and vc[:, :, pos0 + l:].abs().max().item() == 0
+
+
+def test_gemm_score_partials():
+    torch.manual_seed(4)
+    M, N, K = 700, 4096, 1024
+    A = (torch.randn(M, K, device="cuda") / math.sqrt(K)).bfloat16()
+    W = torch.randn(N, K, device="cuda").bfloat16()
+    bias = torch.randn(N, device="cuda")
+    gt = torch.randint(0, N, (M,), device="cuda", dtype=torch.int32)
+    bn = L.load().var_b200_gemm_tile_n(N)
+    nt = (N + bn - 1) // bn
+    part = torch.zeros(M, nt, 2, device="cuda")
+    gl = torch.zeros(M, device="cuda")
+    _gemm(A, W, L.EPI_SCORE, bias=bias, gt=gt, part=part, gt_logit=gl)
+    logits = _ref(A, W) + bias
+    m = part[..., 0].max(dim=1).values
+    lse = m + torch.log((part[..., 1] * torch.exp(part[..., 0] - m[:, None])).sum(1))
+    ref_lse = torch.logsumexp(logits, dim=1)
+    ref_gl = logits.gather(1, gt.long()[:, None])[:, 0]
+    assert (lse - ref_lse).abs().max().item() < 2e-3
+    assert (gl - ref_gl).abs().max().item() < 2e-3

@@ -1,0 +1,29 @@
+// C-ABI wrapper over the GEMM family (declared in include/var_b200.h).
+#include "../../include/var_b200.h"
+#include "gemm.h"
+#include "host.h"
+#include "common.cuh"
+
+extern "C" int var_b200_gemm_bf16(const var_b200_gemm_args_t* a, void* stream) {
+  using namespace vb;
+  VB_REQUIRE(a != nullptr, "gemm: null args");
+  GemmParams p{};
+  p.M = a->M; p.N = a->N; p.K = a->K;
+  p.bias = a->bias;
+  p.out = a->out;
+  p.resid = a->resid;
+  p.gate = a->gate;
+  p.rows_per_seq = a->rows_per_seq;
+  p.gate_ld = a->gate_ld;
+  p.q_out = reinterpret_cast<__nv_bfloat16*>(a->q_out);
+  p.k_cache = reinterpret_cast<__nv_bfloat16*>(a->k_cache);
+  p.v_cache = reinterpret_cast<__nv_bfloat16*>(a->v_cache);
+  p.q_scale = a->q_scale;
+  p.C = a->C; p.H = a->H; p.pos0 = a->pos0; p.Lmax = a->Lmax;
+  p.gt = a->gt;
+  p.part = reinterpret_cast<float2*>(a->part);
+  p.gt_logit = a->gt_logit;
+  return gemm_launch(a->A, a->W, p, a->epilogue, (cudaStream_t)stream, a->force_bn);
+}
+
+extern "C" int var_b200_gemm_tile_n(int N) { return vb::gemm_pick_bn(N); }

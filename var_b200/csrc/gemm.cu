@@ -1,0 +1,97 @@
+// Host launcher for the tcgen05 GEMM family + the raw C-ABI entry used by tests and by the block driver.
+#include "gemm.h"
+
+#include "gemm_sm100.cuh"
+#include "host.h"
+
+namespace vb {
+
+template <int BN, int EPI>
+static int launch_one(const void* A, const void* W, const GemmParams& p, cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.M};
+    uint64_t str[1] = {(uint64_t)p.K * 2};
+    uint32_t box[2] = {GEMM_BK, GEMM_BM};
+    int r = make_tmap_bf16_sw128(&tmA, A, 2, dims, str, box);
+    if (r) return r;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.N};
+    uint64_t str[1] = {(uint64_t)p.K * 2};
+    uint32_t box[2] = {GEMM_BK, (uint32_t)BN};
+    int r = make_tmap_bf16_sw128(&tmB, W, 2, dims, str, box);
+    if (r) return r;
+  }
+  auto kern = gemm_bf16_kernel<BN, EPI>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    VB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int total = m_tiles * n_tiles;
+  const int grid = total < sm_count() ? total : sm_count();
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
+  VB_CUDA_CHECK(cudaGetLastError());
+  return VB_OK;
+}
+
+template <int BN>
+static int launch_bn(const void* A, const void* W, const GemmParams& p, int epi, cudaStream_t st) {
+  switch (epi) {
+    case EPI_BIAS_F32: return launch_one<BN, EPI_BIAS_F32>(A, W, p, st);
+    case EPI_BIAS_BF16: return launch_one<BN, EPI_BIAS_BF16>(A, W, p, st);
+    case EPI_GELU_BF16: return launch_one<BN, EPI_GELU_BF16>(A, W, p, st);
+    case EPI_GATE_RESID: return launch_one<BN, EPI_GATE_RESID>(A, W, p, st);
+    case EPI_QKV: return launch_one<BN, EPI_QKV>(A, W, p, st);
+    case EPI_SCORE: return launch_one<BN, EPI_SCORE>(A, W, p, st);
+  }
+  set_error("gemm: unknown epilogue %d", epi);
+  return VB_ERR_ARG;
+}
+
+int gemm_pick_bn(int N) {
+  // smallest padded N wins; ties go to the wider tile (fewer A re-reads)
+  int best = 256, best_pad = ((N + 255) / 256) * 256;
+  const int cands[2] = {192, 128};
+  for (int bn : cands) {
+    int pad = ((N + bn - 1) / bn) * bn;
+    if (pad < best_pad) { best = bn; best_pad = pad; }
+  }
+  return best;
+}
+
+int gemm_launch(const void* A, const void* W, const GemmParams& p, int epi, cudaStream_t st, int force_bn) {
+  VB_REQUIRE(A && W, "gemm: null operand");
+  VB_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
+  VB_REQUIRE(p.K % GEMM_BK == 0, "gemm: K=%d must be a multiple of %d", p.K, GEMM_BK);
+  VB_REQUIRE(p.N % 64 == 0, "gemm: N=%d must be a multiple of 64", p.N);
+  VB_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0, "gemm: operands must be 16-byte aligned");
+  if (epi == EPI_QKV) {
+    VB_REQUIRE(p.N == 3 * p.C && p.C % 64 == 0 && p.H * 64 == p.C, "gemm/qkv: N=%d C=%d H=%d inconsistent", p.N, p.C, p.H);
+    VB_REQUIRE(p.q_out && p.k_cache && p.v_cache && p.q_scale && p.bias, "gemm/qkv: null pointer");
+    VB_REQUIRE(p.rows_per_seq > 0 && p.M % p.rows_per_seq == 0, "gemm/qkv: M=%d not a multiple of rows_per_seq=%d", p.M,
+               p.rows_per_seq);
+    VB_REQUIRE(p.pos0 >= 0 && p.pos0 + p.rows_per_seq <= p.Lmax, "gemm/qkv: cache overflow pos0=%d l=%d Lmax=%d", p.pos0,
+               p.rows_per_seq, p.Lmax);
+  } else if (epi == EPI_SCORE) {
+    VB_REQUIRE(p.gt && p.part && p.gt_logit && p.bias, "gemm/score: null pointer");
+  } else {
+    VB_REQUIRE(p.out, "gemm: null output");
+    if (epi == EPI_GATE_RESID)
+      VB_REQUIRE(p.resid && p.gate && p.rows_per_seq > 0, "gemm/gate: null pointer or rows_per_seq=%d", p.rows_per_seq);
+  }
+  const int bn = force_bn ? force_bn : gemm_pick_bn(p.N);
+  switch (bn) {
+    case 256: return launch_bn<256>(A, W, p, epi, st);
+    case 192: return launch_bn<192>(A, W, p, epi, st);
+    case 128: return launch_bn<128>(A, W, p, epi, st);
+  }
+  set_error("gemm: unsupported tile width %d", bn);
+  return VB_ERR_ARG;
+}
+
+}  // namespace vb

@@ -1,0 +1,43 @@
+// GEMM family interface shared by the host-side drivers (no device code here).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace vb {
+
+enum EpiMode : int {
+  EPI_BIAS_F32 = 0,    // out fp32 = acc + bias                                  (head: models/var.py:124)
+  EPI_BIAS_BF16 = 1,   // out bf16 = acc + bias
+  EPI_GELU_BF16 = 2,   // out bf16 = gelu_tanh(acc + bias)                        (fc1: models/basic_var.py:52)
+  EPI_GATE_RESID = 3,  // out fp32 = resid + gate[seq] * (acc + bias)             (proj/fc2: basic_var.py:157-158)
+  EPI_QKV = 4,         // q,k L2-norm per head, q*scale, scatter to q / K-cache / V-cache (basic_var.py:93-109)
+  EPI_SCORE = 5,       // per-row partial log-sum-exp + logit at the ground-truth token (eval_prob.py:446-452)
+};
+
+struct GemmParams {
+  int M, N, K;
+  const float* bias;  // [N] (may be null)
+  void* out;          // [M,N] fp32 or bf16, row stride N
+  // EPI_GATE_RESID
+  const float* resid;  // [M,N] fp32 (may alias out)
+  const float* gate;   // gate[(m / rows_per_seq) * gate_ld + n]
+  int rows_per_seq;
+  int gate_ld;
+  // EPI_QKV  (N == 3*C): rows are (seq, t) with t in [0, rows_per_seq)
+  __nv_bfloat16* q_out;    // [n_seq, H, rows_per_seq, 64]
+  __nv_bfloat16* k_cache;  // [n_seq, H, Lmax, 64]   written at position pos0 + t
+  __nv_bfloat16* v_cache;  // [n_seq, H, Lmax, 64]
+  const float* q_scale;    // [H] = exp(min(scale_mul, ln 100))
+  int C, H, pos0, Lmax;
+  // EPI_SCORE
+  const int* gt;    // [M] ground-truth token per row
+  float2* part;     // [M, n_tiles] (max, sum exp(x - max)) over the tile's columns
+  float* gt_logit;  // [M]
+};
+
+// Tile width the launcher will use for a given N (needed to size EPI_SCORE partials: n_tiles = ceil(N / bn)).
+int gemm_pick_bn(int N);
+// A: [M,K] bf16 row-major, W: [N,K] bf16 row-major (nn.Linear layout). force_bn: 0 = auto, else 128/192/256.
+int gemm_launch(const void* A, const void* W, const GemmParams& p, int epi, cudaStream_t st, int force_bn = 0);
+
+}  // namespace vb

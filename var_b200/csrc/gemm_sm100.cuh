@@ -1,0 +1,274 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a:  D[M,N] = A[M,K] * W[N,K]^T  (fp32 accumulate in TMEM)
+//   * A and W are K-major (row-major activations, nn.Linear weight layout) and arrive through TMA
+//     (128B-swizzled 64-column boxes) into a multi-stage smem ring
+//   * one elected thread issues tcgen05.mma (UMMA 128 x BN x 16, cta_group::1)
+//   * accumulators are double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps
+//     the main loop of tile i+1
+//   * four epilogue warps read TMEM with tcgen05.ld (one accumulator row per thread) and apply the
+//     fused epilogue of the VAR block (reference semantics cited per mode below)
+#pragma once
+#include "common.cuh"
+#include "gemm.h"
+
+namespace vb {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 192;  // warp0: TMA, warp1: MMA + TMEM owner, warps 2-5: epilogue
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 192 ? 5 : 6);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // +1024: manual alignment slack
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bars[2 * STAGES + 4];
+  __shared__ uint32_t tmem_base_smem;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  auto full_bar = [&](int s) { return smem_u32(&bars[s]); };
+  auto empty_bar = [&](int s) { return smem_u32(&bars[STAGES + s]); };
+  auto tfull_bar = [&](int s) { return smem_u32(&bars[2 * STAGES + s]); };
+  auto tempty_bar = [&](int s) { return smem_u32(&bars[2 * STAGES + 2 + s]); };
+
+  const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int total_tiles = m_tiles * n_tiles;
+  const int num_kb = p.K / GEMM_BK;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_smem), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          tma_load_2d(&tmA, full_bar(stage), sa, kb * GEMM_BK, m_blk * GEMM_BM);
+          tma_load_2d(&tmB, full_bar(stage), sa + Cfg::A_BYTES, kb * GEMM_BK, n_blk * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(tempty_bar(as), aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * 256;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint64_t adesc = umma_desc_k_sw128(sa);
+          const uint64_t bdesc = umma_desc_k_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the 128B swizzle atom: +2 in the (addr>>4) field
+            umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar(as));  // accumulator complete
+      }
+    }
+  } else {
+    // ------------------------------ epilogue warps ------------------------------
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const int row = m_blk * GEMM_BM + quarter * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t taddr = tmem_base + as * 256 + ((uint32_t)(quarter * 32) << 16);
+      const int n_base = n_blk * BN;
+
+      if constexpr (EPI == EPI_QKV) {
+        const int seq = row / p.rows_per_seq;
+        const int t = row - seq * p.rows_per_seq;
+#pragma unroll 1
+        for (int c = 0; c < BN / 64; ++c) {
+          const int n0 = n_base + c * 64;
+          if (n0 >= p.N) break;
+          float v[64];
+          __syncwarp();
+          tmem_ld_32x32(taddr + c * 64, v);
+          tmem_ld_32x32(taddr + c * 64 + 32, v + 32);
+          tmem_ld_wait();
+          const int which = n0 / p.C;  // 0 q, 1 k, 2 v
+          const int head = (n0 - which * p.C) >> 6;
+          float ss = 0.f;
+#pragma unroll
+          for (int j = 0; j < 64; ++j) {
+            v[j] += __ldg(p.bias + n0 + j);
+            ss += v[j] * v[j];
+          }
+          float mul = 1.f;
+          if (which < 2) {
+            mul = 1.f / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize(dim=-1), eps 1e-12
+            if (which == 0) mul *= __ldg(p.q_scale + head);
+          }
+          if (row_ok) {
+            __nv_bfloat16* dst;
+            if (which == 0)
+              dst = p.q_out + (((size_t)seq * p.H + head) * p.rows_per_seq + t) * 64;
+            else
+              dst = (which == 1 ? p.k_cache : p.v_cache) + (((size_t)seq * p.H + head) * p.Lmax + p.pos0 + t) * 64;
+            uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              uint4 o;
+              o.x = pack_bf16x2(v[8 * j + 0] * mul, v[8 * j + 1] * mul);
+              o.y = pack_bf16x2(v[8 * j + 2] * mul, v[8 * j + 3] * mul);
+              o.z = pack_bf16x2(v[8 * j + 4] * mul, v[8 * j + 5] * mul);
+              o.w = pack_bf16x2(v[8 * j + 6] * mul, v[8 * j + 7] * mul);
+              d4[j] = o;
+            }
+          }
+        }
+      } else if constexpr (EPI == EPI_SCORE) {
+        float run_max = -INFINITY, run_sum = 0.f;
+        const int gt = row_ok ? __ldg(p.gt + row) : -1;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          const int n0 = n_base + c * 32;
+          if (n0 >= p.N) break;
+          float v[32];
+          __syncwarp();
+          tmem_ld_32x32(taddr + c * 32, v);
+          tmem_ld_wait();
+          float cmax = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            v[j] += __ldg(p.bias + n0 + j);
+            cmax = fmaxf(cmax, v[j]);
+          }
+          if (gt >= n0 && gt < n0 + 32) {
+            float g = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) g = (gt - n0 == j) ? v[j] : g;
+            p.gt_logit[row] = g;
+          }
+          const float new_max = fmaxf(run_max, cmax);
+          float s = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) s += __expf(v[j] - new_max);
+          run_sum = run_sum * __expf(run_max - new_max) + s;
+          run_max = new_max;
+        }
+        if (row_ok) p.part[(size_t)row * n_tiles + n_blk] = make_float2(run_max, run_sum);
+      } else {
+        int seq = 0;
+        if constexpr (EPI == EPI_GATE_RESID) seq = row / p.rows_per_seq;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          const int n0 = n_base + c * 32;
+          if (n0 >= p.N) break;
+          float v[32];
+          __syncwarp();
+          tmem_ld_32x32(taddr + c * 32, v);
+          tmem_ld_wait();
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+            }
+          }
+          if (!row_ok) {
+            // nothing to store for rows beyond M (the TMEM load above stays warp-convergent)
+          } else if constexpr (EPI == EPI_BIAS_F32) {
+            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)row * p.N + n0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else if constexpr (EPI == EPI_GATE_RESID) {
+            const float4* g4 = reinterpret_cast<const float4*>(p.gate + (size_t)seq * p.gate_ld + n0);
+            const float4* r4 = reinterpret_cast<const float4*>(p.resid + (size_t)row * p.N + n0);
+            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)row * p.N + n0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 g = __ldg(g4 + j);
+              const float4 r = r4[j];
+              o[j] = make_float4(fmaf(v[4 * j], g.x, r.x), fmaf(v[4 * j + 1], g.y, r.y), fmaf(v[4 * j + 2], g.z, r.z),
+                                 fmaf(v[4 * j + 3], g.w, r.w));
+            }
+          } else {  // EPI_BIAS_BF16 / EPI_GELU_BF16
+            if constexpr (EPI == EPI_GELU_BF16) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
+            }
+            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.N + n0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 w;
+              w.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+              w.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+              w.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+              w.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+              o[j] = w;
+            }
+          }
+        }
+      }
+      // release this accumulator stage back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace vb
