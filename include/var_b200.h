@@ -69,7 +69,8 @@ typedef struct var_b200_gemm_args {
   const float* q_scale; /* [H] exp(min(scale_mul, ln 100)) */
   int C, H, pos0, Lmax;
   /* SCORE */
-  const int32_t* gt; /* [M] */
+  const int32_t* gt; /* row m uses gt[m % gt_mod] */
+  int gt_mod;        /* 0 = M */
   float* part;       /* [M, ceil(N / var_b200_gemm_tile_n(N)), 2] (max, sumexp) */
   float* gt_logit;   /* [M] */
 } var_b200_gemm_args_t;
@@ -81,6 +82,126 @@ VAR_B200_API int var_b200_gemm_tile_n(int N);
 /* Hardware probe used by the test-suite to pin UMMA shared-memory descriptor encodings:
  * D[128,N] = A[128,64] * B, B = [N,64] (K-major) or [64,N] (MN-major). */
 VAR_B200_API int var_b200_umma_probe(const void* A, const void* B, float* D, int N, int b_mn_major, void* stream);
+
+
+/* ------------------------------------------------------------------------------------------------
+ * Block-causal attention (models/basic_var.py:98-117, mask of models/var.py:107-112), tcgen05/TMEM.
+ * q: bf16 [n_seq,H,Lq,64], k/v: bf16 [n_seq,H,Lmax,64] (the preallocated KV cache), out: bf16 [n_seq,Lq,H*64].
+ * A query at absolute position q_pos0 + i of pyramid level s attends keys [0, level_end[s]).
+ * ---------------------------------------------------------------------------------------------- */
+#define VAR_B200_MAX_SCALES 16
+VAR_B200_API int var_b200_attention(const void* q, const void* k, const void* v, void* out, int n_seq, int H, int Lq,
+                                    int Lmax, int q_pos0, int n_scales, const int* level_end /* host */, void* stream);
+
+/* LN(x)*(1+scale[seq])+shift[seq] -> bf16 (models/basic_var.py:157-158,174). scale/shift: row stride ada_ld. */
+VAR_B200_API int var_b200_ln_modulate(const float* x, const float* scale, const float* shift, int ada_ld,
+                                      int rows_per_seq, void* out_bf16, int M, int C, float eps, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-scale residual quantizer (models/quant.py). All tensors device fp32 NCHW unless noted; idx is int64.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct var_b200_quant {
+  int Cvae, V, n_scales;                 /* Cvae must be 32 */
+  int ph[VAR_B200_MAX_SCALES], pw[VAR_B200_MAX_SCALES]; /* patch grid per scale; last = latent H,W */
+  int phi_of_scale[VAR_B200_MAX_SCALES]; /* Phi conv used by each scale (quant.py:218-243) */
+  int n_phi;
+  float resi;                            /* |quant_resi| (quant.py:204) */
+  const float* codebook;                 /* [V,Cvae] embedding.weight */
+  const float* phi_w;                    /* [n_phi,Cvae,Cvae,3,3] */
+  const float* phi_b;                    /* [n_phi,Cvae] */
+} var_b200_quant_t;
+
+/* f_to_idxBl_or_fhat (quant.py:135-166). idx_out: int64, scale blocks [B, ph*pw] concatenated.
+ * fhat_list: NULL or [S,B,Cvae,H,W] (the to_fhat=True list). work: 2*B*Cvae*H*W floats. */
+VAR_B200_API int var_b200_quant_encode(const var_b200_quant_t* qz, const float* f, int B, int64_t* idx_out,
+                                       float* fhat_list, float* work, void* stream);
+/* idxBl_to_var_input (quant.py:169-184) and embed_to_fhat(all_to_max_scale=True) (quant.py:107-121) in one pass.
+ * var_input: NULL or [B, L - l_0, Cvae]; fhat_list: NULL or [S,B,Cvae,H,W]; fhat_last: [B,Cvae,H,W] (required). */
+VAR_B200_API int var_b200_quant_decode(const var_b200_quant_t* qz, const int64_t* idx, int B, float* var_input,
+                                       float* fhat_list, float* fhat_last, void* stream);
+/* get_next_autoregressive_input (quant.py:187-196) with h = codebook[idx]: f_hat updated in place;
+ * next_tokens: NULL or [B, l_{si+1}, Cvae] (token-major word_embed input); next_nchw: NULL or [B,Cvae,ph,pw]. */
+VAR_B200_API int var_b200_quant_next_input(const var_b200_quant_t* qz, int si, float* f_hat, const int64_t* idx_si, int B,
+                                           float* next_tokens, float* next_nchw, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * CFG mix + top-k/top-p + sampling from caller-supplied Exp(1) noise (models/var.py:172-175, helpers.py:6-19).
+ * logits: [2B,l,V] (cond then uncond) when use_cfg, else [B,l,V]. q: [B*l,V]. idx_out: int64 [B,l].
+ * ---------------------------------------------------------------------------------------------- */
+VAR_B200_API int var_b200_cfg_topk_sample(const float* logits, int B, int l, int V, int use_cfg, double t, const float* q,
+                                          int top_k, float top_p, int64_t* idx_out, float* mixed_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * VAR transformer (models/var.py, models/basic_var.py). Weights are caller-owned device buffers packed once:
+ * GEMM weights bf16 in nn.Linear layout [out,in], everything else fp32.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct var_b200_block_weights {
+  const void* w_qkv;    /* bf16 [3C,C]   attn.mat_qkv.weight */
+  const float* b_qkv;   /* [3C] = cat(q_bias, 0, v_bias)            basic_var.py:93 */
+  const float* q_scale; /* [H]  = exp(min(scale_mul_1H11, ln 100))   basic_var.py:101 */
+  const void* w_proj;   /* bf16 [C,C] */
+  const float* b_proj;  /* [C] */
+  const void* w_fc1;    /* bf16 [4C,C] */
+  const float* b_fc1;   /* [4C] */
+  const void* w_fc2;    /* bf16 [C,4C] */
+  const float* b_fc2;   /* [C] */
+} var_b200_block_weights_t;
+
+typedef struct var_b200_model {
+  int depth, C, H, V, Cvae, n_scales, num_classes, shared_aln;
+  float norm_eps;
+  int patch_nums[VAR_B200_MAX_SCALES];
+  const var_b200_block_weights_t* blocks; /* HOST array [depth] */
+  /* adaLN linears stacked along the output dimension. shared_aln=0: rows = [blocks.0.ada_lin (6C) ... blocks.{d-1}
+   * (6C), head_nm.ada_lin (2C)]; shared_aln=1: rows = [shared_ada_lin (6C), head_nm.ada_lin (2C)]. */
+  const void* w_ada;     /* bf16 [ada_rows, C] */
+  const float* b_ada;    /* [ada_rows] */
+  int ada_rows;
+  const float* ada_gss;  /* shared_aln only: [depth,6,C] (blocks.i.ada_gss), else NULL */
+  const void* w_head;    /* bf16 [V,C] */
+  const float* b_head;   /* [V] */
+  const float* w_word;   /* [C,Cvae] word_embed.weight */
+  const float* b_word;   /* [C] */
+  const float* class_emb; /* [num_classes+1, C] */
+  const float* pos_start; /* [first_l, C] */
+  const float* lvl_pos;   /* [L, C] = lvl_embed[lvl_1L] + pos_1LC   (var.py:153,207) */
+} var_b200_model_t;
+
+/* Row stride (floats) of the per-sequence adaLN parameter table: (6*depth + 2) * C.
+ * Column layout: block i -> [gamma1,gamma2,scale1,scale2,shift1,shift2] at 6*i*C (basic_var.py:156);
+ * head_nm -> [scale, shift] at 6*depth*C (basic_var.py:173). */
+VAR_B200_API int var_b200_ada_ld(const var_b200_model_t* m);
+/* ada_out[n_seq, ada_ld] = Linear(SiLU(class_emb[labels])) for every block and the head (loop-invariant over the
+ * 10 AR scales; the reference recomputes it per block per call, basic_var.py:156). work: var_b200_ada_workspace(). */
+VAR_B200_API size_t var_b200_ada_workspace(const var_b200_model_t* m, int n_seq);
+VAR_B200_API int var_b200_ada_params(const var_b200_model_t* m, const int32_t* labels, int n_seq, float* ada_out,
+                                     void* work, size_t work_bytes, void* stream);
+
+/* Token embedding (var.py:200-207 / :153-154,185-187): rows t < first_rows are start tokens
+ * (class_emb[label] + pos_start[t]), the rest word_embed(x_in[seq % n_x, t - first_rows]); + lvl_pos[pos0 + t]. */
+VAR_B200_API int var_b200_embed(const var_b200_model_t* m, const float* x_in, int n_x, int l_in, const int32_t* labels,
+                                int n_seq, int l, int first_rows, int pos0, float* x_out, void* stream);
+
+/* depth x AdaLNSelfAttn.forward (basic_var.py:152-159) on x[n_seq, l, C] in place.
+ * Teacher-forced: l = L, pos0 = 0, kv = scratch [2][n_seq,H,L,64] shared by all layers (kv_layer_stride = 0).
+ * KV-cached step: l = pn^2, pos0 = tokens already cached, kv = [depth][2][n_seq,H,Lmax,64]
+ * (kv_layer_stride = 2*n_seq*H*Lmax*64 elements). x_dump: NULL or [depth, n_seq*l, C] copies of x after each block. */
+VAR_B200_API size_t var_b200_blocks_workspace(const var_b200_model_t* m, int n_seq, int l);
+VAR_B200_API int var_b200_blocks(const var_b200_model_t* m, float* x, const float* ada, int n_seq, int l, int pos0,
+                                 void* kv, size_t kv_layer_stride, int Lmax, float* x_dump, void* work,
+                                 size_t work_bytes, void* stream);
+
+/* get_logits (var.py:118-124): logits[n_seq*l, V] fp32 = head(LN(x)*(1+scale)+shift). work: blocks workspace. */
+VAR_B200_API int var_b200_head_logits(const var_b200_model_t* m, const float* x, const float* ada, int n_seq, int l,
+                                      float* logits, void* work, size_t work_bytes, void* stream);
+/* Fused head + log-softmax + gather + per-sequence sum (eval_prob.py:441-463) without materialising logits.
+ * gt: int32 [gt_rows] with gt_rows dividing n_seq*L; row r uses gt[r % gt_rows] (the token pyramid of the image is
+ * shared by every candidate class). scores[n_seq] = sum_{t >= first_pos} log p(gt_t); per_scale: NULL or [n_seq,S];
+ * tok_logp: NULL or [n_seq*L]. work: var_b200_score_workspace(). */
+VAR_B200_API size_t var_b200_score_workspace(const var_b200_model_t* m, int n_seq, int l);
+VAR_B200_API int var_b200_head_score(const var_b200_model_t* m, const float* x, const float* ada, int n_seq, int l,
+                                     const int32_t* gt, int gt_rows, int first_pos, float* scores, float* per_scale,
+                                     float* tok_logp, void* work, size_t work_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,111 @@
+"""CPU tier: pin the oracle (oracle/) to the reference through the committed golden vectors, and check the host-side
+contracts (state_dict keys, C-ABI symbols). No GPU, no /root/reference needed."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import (GOLDEN, PATCH_NUMS, golden, quant_oracle_of, replay_noise, sd_cpu, seeded_models, split_scales,
+                     var_cfg_of)
+from oracle import var_oracle as VO
+
+
+def test_state_dict_keys_and_shapes_match_reference():
+    ref = json.loads((GOLDEN / "state_dict_shapes.json").read_text())
+    for shared in (False, True):
+        vae, var = seeded_models(depth=2, shared_aln=shared)
+        ours = {k: list(v.shape) for k, v in var.state_dict().items()}
+        assert ours == ref[f"var_d2_shared{int(shared)}"]
+    ours = {k: list(v.shape) for k, v in vae.state_dict().items()}
+    assert ours == ref["vqvae"]
+
+
+def test_capi_exports_every_declared_symbol():
+    from var_b200 import lib as L
+    lib = L.load()
+    syms = L.exported_symbols()
+    assert len(syms) >= 19
+    for s in syms:
+        assert hasattr(lib, s), s
+    assert lib.var_b200_last_error() is not None
+    assert lib.var_b200_gemm_tile_n(1920) == 192 and lib.var_b200_gemm_tile_n(4096) == 256
+
+
+def test_quant_oracle_indices_match_reference_golden():
+    g = golden("quant_forward_d2.npz")
+    vae, _ = seeded_models()
+    qo = quant_oracle_of(vae)
+    idx = qo.f_to_idxBl_or_fhat(g["f"], to_fhat=False)
+    got = np.concatenate(idx, axis=1)
+    mism = np.argwhere(got != g["idx"].astype(np.int64))
+    assert mism.size == 0, f"{len(mism)} index mismatches vs reference, first at {mism[:5].tolist()}"
+    fh = qo.f_to_idxBl_or_fhat(g["f"], to_fhat=True)
+    assert np.abs(fh[-1] - g["fhat_last"]).max() < 2e-5
+    assert np.abs(fh[3] - g["fhat_s3"]).max() < 2e-5
+
+
+def test_quant_oracle_nonsquare_patch_grid():
+    g = golden("quant_forward_d2.npz")
+    vae, _ = seeded_models()
+    vpn = [(1, 1), (2, 3), (4, 4), (5, 8), (16, 16)]
+    idx = quant_oracle_of(vae).f_to_idxBl_or_fhat(g["f"][:2], to_fhat=False, v_patch_nums=vpn)
+    assert np.array_equal(np.concatenate(idx, axis=1), g["idx_nonsquare"].astype(np.int64))
+    with pytest.raises(AssertionError):
+        quant_oracle_of(vae).f_to_idxBl_or_fhat(g["f"][:2], to_fhat=False, v_patch_nums=[1, 2, 8])
+
+
+def test_quant_oracle_var_input_and_fhat_decode():
+    g = golden("quant_forward_d2.npz")
+    vae, _ = seeded_models()
+    qo = quant_oracle_of(vae)
+    idx = split_scales(g["idx"])
+    assert np.abs(qo.idxBl_to_var_input(idx) - g["var_input"]).max() < 2e-5
+    assert np.abs(qo.idxBl_to_fhat(idx, last_one=True) - g["fhat_last"]).max() < 2e-5
+    # step-wise decode == whole decode (quant.py:187-196 vs :169-184)
+    f_hat = np.zeros_like(g["fhat_last"])
+    nxts = []
+    for si in range(len(PATCH_NUMS)):
+        nxt = qo.get_next_autoregressive_input(si, f_hat, idx[si])
+        if nxt is not None:
+            nxts.append(nxt.reshape(nxt.shape[0], 32, -1).transpose(0, 2, 1))
+    assert np.array_equal(np.concatenate(nxts, axis=1), qo.idxBl_to_var_input(idx))
+    assert np.array_equal(f_hat, qo.idxBl_to_fhat(idx, last_one=True))
+
+
+def test_var_oracle_forward_matches_reference_golden():
+    g = golden("quant_forward_d2.npz")
+    _, var = seeded_models()
+    sd, cfg = sd_cpu(var), var_cfg_of(var)
+    logits, acts = VO.var_forward(sd, cfg, torch.from_numpy(g["labels"]), torch.from_numpy(g["var_input"]), return_blocks=True)
+    assert (logits[:, ::23, ::29] - torch.from_numpy(g["logits_sub"])).abs().max() < 5e-4
+    assert (torch.logsumexp(logits, -1) - torch.from_numpy(g["lse"])).abs().max() < 5e-4
+    gt = torch.from_numpy(g["idx"].astype(np.int64))
+    logp = VO.token_log_probs(logits, gt)
+    assert (logp - torch.from_numpy(g["logp"])).abs().max() < 1e-3
+    assert (logp.sum(1) - torch.from_numpy(g["scores"])).abs().max() < 2e-2
+    for i, a in enumerate(acts):
+        ref = torch.from_numpy(g["block_sub"][i])
+        assert (a[:, ::23, ::7] - ref).abs().max() < 1e-3 * max(1.0, ref.abs().max().item()), f"block {i}"
+    # the golden weights are dense: the transformer body must matter
+    assert float(np.abs(g["block_sub"][1] - g["block_sub"][0]).max()) > 0.1
+
+
+def test_sampler_oracle_matches_reference_golden():
+    g = golden("sampler.npz")
+    lg, q = torch.from_numpy(g["logits"]), torch.from_numpy(g["q"])
+    for name, (k, p) in dict(k900=(900, 0.0), k900p95=(900, 0.95), k0=(0, 0.0), p50=(0, 0.5)).items():
+        tok = VO.sample_top_k_top_p(lg, q, top_k=k, top_p=p)
+        assert torch.equal(tok, torch.from_numpy(g["tok_" + name].astype(np.int64))), name
+
+
+def test_ar_oracle_matches_reference_golden():
+    g = golden("ar_d2.npz")
+    vae, var = seeded_models()
+    sd, cfg = sd_cpu(var), var_cfg_of(var)
+    noise = replay_noise(123, B=2)
+    out = VO.ar_infer(sd, cfg, quant_oracle_of(vae), torch.from_numpy(g["labels"]), noise, cfg_scale=1.5, top_k=900)
+    got = torch.cat(out["idx"], dim=1).numpy()
+    ref = g["idx"].astype(np.int64)
+    assert (got != ref).sum() == 0, f"{(got != ref).sum()} sampled tokens differ from the reference"
+    assert (out["f_hat"] - torch.from_numpy(g["f_hat"])).abs().max() < 5e-5

@@ -1,0 +1,141 @@
+"""CNN encoder / decoder of the VQVAE (PyTorch, cuDNN): boundary helpers, not hand-written kernels.
+
+`north_star` keeps these dense convolutions outside the hot path; they exist here
+because the drop-in boundary functions VQVAE.img_to_idxBl / fhat_to_img call them (models/vqvae.py:62-67). The
+module tree reproduces the reference's state_dict keys (models/basic_vae.py:99-226) so `vae_ch160v4096z32.pth`
+loads with strict=True.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+def _gn(ch: int) -> nn.GroupNorm:
+    return nn.GroupNorm(32, ch, eps=1e-6, affine=True)
+
+
+class ResnetBlock(nn.Module):
+    """GN-SiLU-conv3x3 twice plus a (1x1-projected) skip (models/basic_vae.py:40-60)."""
+
+    def __init__(self, cin: int, cout: int):
+        super().__init__()
+        self.norm1, self.conv1 = _gn(cin), nn.Conv2d(cin, cout, 3, 1, 1)
+        self.norm2, self.conv2 = _gn(cout), nn.Conv2d(cout, cout, 3, 1, 1)
+        self.nin_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else nn.Identity()
+
+    def forward(self, x):
+        y = self.conv1(F.silu(self.norm1(x)))
+        y = self.conv2(F.silu(self.norm2(y)))
+        return self.nin_shortcut(x) + y
+
+
+class AttnBlock(nn.Module):
+    """Single-head spatial self-attention with scale C^-0.5 (models/basic_vae.py:63-92)."""
+
+    def __init__(self, ch: int):
+        super().__init__()
+        self.C = ch
+        self.norm = _gn(ch)
+        self.qkv = nn.Conv2d(ch, 3 * ch, 1)
+        self.proj_out = nn.Conv2d(ch, ch, 1)
+
+    def forward(self, x):
+        B, C, H, W = x.shape
+        q, k, v = self.qkv(self.norm(x)).view(B, 3, C, H * W).transpose(2, 3).unbind(1)  # each [B, HW, C]
+        o = F.scaled_dot_product_attention(q, k, v, scale=float(C) ** -0.5)
+        return x + self.proj_out(o.transpose(1, 2).reshape(B, C, H, W))
+
+
+class _Resample(nn.Module):
+    def __init__(self, ch: int, down: bool):
+        super().__init__()
+        self.down = down
+        self.conv = nn.Conv2d(ch, ch, 3, 2 if down else 1, 0 if down else 1)
+
+    def forward(self, x):
+        if self.down:  # asymmetric pad then stride-2 conv (models/basic_vae.py:31-37)
+            return self.conv(F.pad(x, (0, 1, 0, 1)))
+        return self.conv(F.interpolate(x, scale_factor=2, mode="nearest"))  # models/basic_vae.py:22-28
+
+
+class _Level(nn.Module):
+    def __init__(self, cin: int, cout: int, n_blocks: int, with_attn: bool, resample: str | None):
+        super().__init__()
+        self.block = nn.ModuleList()
+        self.attn = nn.ModuleList()
+        for _ in range(n_blocks):
+            self.block.append(ResnetBlock(cin, cout))
+            cin = cout
+            if with_attn:
+                self.attn.append(AttnBlock(cout))
+        if resample == "down":
+            self.downsample = _Resample(cout, True)
+        elif resample == "up":
+            self.upsample = _Resample(cout, False)
+
+    def run(self, h):
+        for i, blk in enumerate(self.block):
+            h = blk(h)
+            if len(self.attn):
+                h = self.attn[i](h)
+        return h
+
+
+class _Mid(nn.Module):
+    def __init__(self, ch: int):
+        super().__init__()
+        self.block_1, self.attn_1, self.block_2 = ResnetBlock(ch, ch), AttnBlock(ch), ResnetBlock(ch, ch)
+
+    def forward(self, h):
+        return self.block_2(self.attn_1(self.block_1(h)))
+
+
+class Encoder(nn.Module):
+    def __init__(self, ch=160, ch_mult=(1, 1, 2, 2, 4), num_res_blocks=2, in_channels=3, z_channels=32):
+        super().__init__()
+        n = len(ch_mult)
+        self.conv_in = nn.Conv2d(in_channels, ch, 3, 1, 1)
+        mults = (1,) + tuple(ch_mult)
+        self.down = nn.ModuleList(
+            _Level(ch * mults[i], ch * ch_mult[i], num_res_blocks, with_attn=(i == n - 1),
+                   resample=("down" if i != n - 1 else None)) for i in range(n))
+        top = ch * ch_mult[-1]
+        self.mid = _Mid(top)
+        self.norm_out = _gn(top)
+        self.conv_out = nn.Conv2d(top, z_channels, 3, 1, 1)
+
+    def forward(self, x):
+        h = self.conv_in(x)
+        for lvl in self.down:
+            h = lvl.run(h)
+            if hasattr(lvl, "downsample"):
+                h = lvl.downsample(h)
+        return self.conv_out(F.silu(self.norm_out(self.mid(h))))
+
+
+class Decoder(nn.Module):
+    def __init__(self, ch=160, ch_mult=(1, 1, 2, 2, 4), num_res_blocks=2, in_channels=3, z_channels=32):
+        super().__init__()
+        n = len(ch_mult)
+        top = ch * ch_mult[-1]
+        self.conv_in = nn.Conv2d(z_channels, top, 3, 1, 1)
+        self.mid = _Mid(top)
+        levels, cin = [], top
+        for i in reversed(range(n)):
+            cout = ch * ch_mult[i]
+            levels.insert(0, _Level(cin, cout, num_res_blocks + 1, with_attn=(i == n - 1),
+                                    resample=("up" if i != 0 else None)))
+            cin = cout
+        self.up = nn.ModuleList(levels)
+        self.norm_out = _gn(cin)
+        self.conv_out = nn.Conv2d(cin, in_channels, 3, 1, 1)
+
+    def forward(self, z):
+        h = self.mid(self.conv_in(z))
+        for lvl in reversed(self.up):
+            h = lvl.run(h)
+            if hasattr(lvl, "upsample"):
+                h = lvl.upsample(h)
+        return self.conv_out(F.silu(self.norm_out(h)))

@@ -1,0 +1,22 @@
+// Block-causal attention launcher interface (no device code).
+#pragma once
+#include <cuda_runtime.h>
+
+#define VB_MAX_SCALES 16
+
+namespace vb {
+
+struct AttnArgs {
+  const void* q;  // bf16 [n_seq, H, Lq, 64]   (L2-normalised, scaled)
+  const void* k;  // bf16 [n_seq, H, Lmax, 64] (L2-normalised) ; rows >= visible range must be finite
+  const void* v;  // bf16 [n_seq, H, Lmax, 64]
+  void* out;      // bf16 [n_seq, Lq, H*64]
+  int n_seq, H, Lq, Lmax;
+  int q_pos0;                    // absolute sequence position of query row 0
+  int n_scales;                  // pyramid levels
+  int level_end[VB_MAX_SCALES];  // cumulative token count after each level
+};
+
+int attn_launch(const AttnArgs& a, cudaStream_t st);
+
+}  // namespace vb

@@ -21,6 +21,7 @@ extern "C" int var_b200_gemm_bf16(const var_b200_gemm_args_t* a, void* stream) {
   p.q_scale = a->q_scale;
   p.C = a->C; p.H = a->H; p.pos0 = a->pos0; p.Lmax = a->Lmax;
   p.gt = a->gt;
+  p.gt_mod = a->gt_mod > 0 ? a->gt_mod : a->M;
   p.part = reinterpret_cast<float2*>(a->part);
   p.gt_logit = a->gt_logit;
   return gemm_launch(a->A, a->W, p, a->epilogue, (cudaStream_t)stream, a->force_bn);

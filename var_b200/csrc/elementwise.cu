@@ -1,0 +1,215 @@
+// HBM-bound helper kernels of the VAR block: adaLN LayerNorm-modulate (A-operand producer for the QKV / FC1 / head
+// GEMMs), token embedding, class-condition activation, and the likelihood-score reduction.
+#include "elementwise.h"
+
+#include "common.cuh"
+#include "host.h"
+
+namespace vb {
+
+// ------------------------------------------------------------------------------------------------
+// LN(x) * (1 + scale[seq]) + shift[seq] -> bf16        (basic_var.py:157-158,174; LayerNorm without affine)
+// one warp per row; the row lives in registers between the statistics and the normalisation pass
+// ------------------------------------------------------------------------------------------------
+constexpr int LN_MAXV = 20;  // float4 per lane: supports C <= 2560
+
+__global__ void __launch_bounds__(256)
+ln_modulate_kernel(const float* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
+                   int ada_ld, int rows_per_seq, __nv_bfloat16* __restrict__ out, int M, int C, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= M) return;
+  const int nvec = C >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * C);
+  float4 v[LN_MAXV];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nvec) {
+      v[i] = xr[idx];
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float mean = warp_sum(sum) / (float)C;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nvec) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      sq += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float rstd = 1.f / sqrtf(warp_sum(sq) / (float)C + eps);
+  const int seq = row / rows_per_seq;
+  const float4* sc = reinterpret_cast<const float4*>(scale + (size_t)seq * ada_ld);
+  const float4* sh = reinterpret_cast<const float4*>(shift + (size_t)seq * ada_ld);
+  uint2* o = reinterpret_cast<uint2*>(out + (size_t)row * C);
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nvec) {
+      const float4 s = __ldg(sc + idx), h = __ldg(sh + idx);
+      const float a = (v[i].x - mean) * rstd * (1.f + s.x) + h.x;
+      const float b = (v[i].y - mean) * rstd * (1.f + s.y) + h.y;
+      const float c = (v[i].z - mean) * rstd * (1.f + s.z) + h.z;
+      const float d = (v[i].w - mean) * rstd * (1.f + s.w) + h.w;
+      o[idx] = make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d));
+    }
+  }
+}
+
+int ln_modulate(const float* x, const float* scale, const float* shift, int ada_ld, int rows_per_seq, void* out, int M,
+                int C, float eps, cudaStream_t st) {
+  VB_REQUIRE(x && scale && shift && out, "ln_modulate: null pointer");
+  VB_REQUIRE(C % 4 == 0 && C <= LN_MAXV * 128, "ln_modulate: C=%d unsupported", C);
+  VB_REQUIRE(M > 0 && rows_per_seq > 0, "ln_modulate: bad M=%d rows_per_seq=%d", M, rows_per_seq);
+  const int wpb = 8;
+  ln_modulate_kernel<<<(M + wpb - 1) / wpb, wpb * 32, 0, st>>>(x, scale, shift, ada_ld, rows_per_seq,
+                                                               reinterpret_cast<__nv_bfloat16*>(out), M, C, eps);
+  VB_CUDA_CHECK(cudaGetLastError());
+  return VB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// cond = class_emb[label] ; A = bf16(SiLU(cond))      (basic_var.py:146-147 input of every ada_lin)
+// ------------------------------------------------------------------------------------------------
+__global__ void cond_silu_kernel(const float* __restrict__ class_emb, const int* __restrict__ labels,
+                                 __nv_bfloat16* __restrict__ out, int n_seq, int C) {
+  const int s = blockIdx.x;
+  const float* e = class_emb + (size_t)__ldg(labels + s) * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float v = e[c];
+    out[(size_t)s * C + c] = __float2bfloat16(v / (1.f + expf(-v)));
+  }
+}
+
+int cond_silu(const float* class_emb, const int* labels, void* out, int n_seq, int C, cudaStream_t st) {
+  VB_REQUIRE(class_emb && labels && out && n_seq > 0, "cond_silu: bad arguments");
+  cond_silu_kernel<<<n_seq, 256, 0, st>>>(class_emb, labels, reinterpret_cast<__nv_bfloat16*>(out), n_seq, C);
+  VB_CUDA_CHECK(cudaGetLastError());
+  return VB_OK;
+}
+
+// shared_aln (models/var.py:15-18,80; basic_var.py:153-154): ada[s, blk*6C + j] = gss[blk, j] + shared[s, j]
+__global__ void expand_shared_aln_kernel(const float* __restrict__ shared, int shared_ld, const float* __restrict__ gss,
+                                         float* __restrict__ ada, int ada_ld, int depth, int sixC) {
+  const int s = blockIdx.y, blk = blockIdx.x;
+  for (int j = threadIdx.x; j < sixC; j += blockDim.x)
+    ada[(size_t)s * ada_ld + (size_t)blk * sixC + j] = gss[(size_t)blk * sixC + j] + shared[(size_t)s * shared_ld + j];
+}
+
+int expand_shared_aln(const float* shared, int shared_ld, const float* gss, float* ada, int ada_ld, int depth, int C,
+                      int n_seq, cudaStream_t st) {
+  expand_shared_aln_kernel<<<dim3(depth, n_seq), 256, 0, st>>>(shared, shared_ld, gss, ada, ada_ld, depth, 6 * C);
+  VB_CUDA_CHECK(cudaGetLastError());
+  return VB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// token embedding (models/var.py:200-207 teacher forced; :153-154,185-187 autoregressive)
+//   row t <  first_rows : class_emb[label] + pos_start[t] + lvl_pos[pos0 + t]
+//   row t >= first_rows : word_embed(x_in[seq % n_x, t - first_rows, :]) + lvl_pos[pos0 + t]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+embed_kernel(const float* __restrict__ x_in, int n_x, int l_in, const int* __restrict__ labels,
+             const float* __restrict__ class_emb, const float* __restrict__ pos_start,
+             const float* __restrict__ lvl_pos, const float* __restrict__ w_word, const float* __restrict__ b_word,
+             float* __restrict__ out, int l, int first_rows, int pos0, int C, int Cv) {
+  __shared__ float xin[64];
+  const int t = blockIdx.x, s = blockIdx.y;
+  float* o = out + ((size_t)s * l + t) * C;
+  const float* lp = lvl_pos + (size_t)(pos0 + t) * C;
+  if (t < first_rows) {
+    const float* e = class_emb + (size_t)__ldg(labels + s) * C;
+    const float* ps = pos_start + (size_t)t * C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) o[c] = (e[c] + ps[c]) + lp[c];
+    return;
+  }
+  const float* xi = x_in + ((size_t)(s % n_x) * l_in + (t - first_rows)) * Cv;
+  if (threadIdx.x < Cv) xin[threadIdx.x] = xi[threadIdx.x];
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float* w = w_word + (size_t)c * Cv;
+    float acc = 0.f;
+    for (int k = 0; k < Cv; ++k) acc = fmaf(xin[k], __ldg(w + k), acc);
+    o[c] = (acc + b_word[c]) + lp[c];
+  }
+}
+
+int embed_tokens(const float* x_in, int n_x, int l_in, const int* labels, const float* class_emb,
+                 const float* pos_start, const float* lvl_pos, const float* w_word, const float* b_word, float* out,
+                 int n_seq, int l, int first_rows, int pos0, int C, int Cv, cudaStream_t st) {
+  VB_REQUIRE(out && labels && class_emb && pos_start && lvl_pos && w_word && b_word, "embed: null pointer");
+  VB_REQUIRE(Cv <= 64 && n_seq > 0 && l > 0 && n_seq <= 65535, "embed: bad shape Cv=%d n_seq=%d l=%d", Cv, n_seq, l);
+  VB_REQUIRE(first_rows >= l || (x_in && n_x > 0), "embed: x_in required");
+  embed_kernel<<<dim3(l, n_seq), 256, 0, st>>>(x_in, n_x > 0 ? n_x : 1, l_in, labels, class_emb, pos_start, lvl_pos,
+                                               w_word, b_word, out, l, first_rows, pos0, C, Cv);
+  VB_CUDA_CHECK(cudaGetLastError());
+  return VB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// likelihood score (eval_prob.py:446-463): log p(gt_t) = gt_logit_t - logsumexp_t ; summed per pyramid level.
+// part[row, tile] = (max, sum exp(x - max)) from the head GEMM's EPI_SCORE epilogue.
+// One CTA per sequence, fixed reduction order (deterministic).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+score_finalize_kernel(const float2* __restrict__ part, int n_tiles, const float* __restrict__ gt_logit, int L,
+                      AttnLevelsPOD lv, float* __restrict__ tok_logp, float* __restrict__ per_scale,
+                      float* __restrict__ total, int first_pos) {
+  __shared__ float red[VB_MAX_SCALES][8];
+  const int s = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float acc[VB_MAX_SCALES];
+#pragma unroll
+  for (int i = 0; i < VB_MAX_SCALES; ++i) acc[i] = 0.f;
+  for (int t = threadIdx.x; t < L; t += blockDim.x) {
+    const size_t row = (size_t)s * L + t;
+    const float2* p = part + row * n_tiles;
+    float m = -INFINITY;
+    for (int i = 0; i < n_tiles; ++i) m = fmaxf(m, p[i].x);
+    float sum = 0.f;
+    for (int i = 0; i < n_tiles; ++i) sum += p[i].y * expf(p[i].x - m);
+    const float lp = gt_logit[row] - (m + logf(sum));
+    if (tok_logp) tok_logp[row] = lp;
+    int level = 0;
+    while (level < lv.n - 1 && t >= lv.end[level]) ++level;
+#pragma unroll
+    for (int i = 0; i < VB_MAX_SCALES; ++i)
+      if (i == level && t >= first_pos) acc[i] += lp;
+  }
+#pragma unroll
+  for (int i = 0; i < VB_MAX_SCALES; ++i) {
+    const float v = warp_sum(acc[i]);
+    if (lane == 0) red[i][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int i = 0; i < lv.n; ++i) {
+      float v = 0.f;
+      for (int w = 0; w < 8; ++w) v += red[i][w];
+      if (per_scale) per_scale[(size_t)s * lv.n + i] = v;
+      tot += v;
+    }
+    total[s] = tot;
+  }
+}
+
+int score_finalize(const void* part, int n_tiles, const float* gt_logit, int n_seq, int L, int n_scales,
+                   const int* level_end, float* tok_logp, float* per_scale, float* total, int first_pos,
+                   cudaStream_t st) {
+  VB_REQUIRE(part && gt_logit && total && n_seq > 0 && L > 0, "score_finalize: bad arguments");
+  VB_REQUIRE(n_scales > 0 && n_scales <= VB_MAX_SCALES, "score_finalize: n_scales=%d", n_scales);
+  AttnLevelsPOD lv;
+  lv.n = n_scales;
+  for (int i = 0; i < VB_MAX_SCALES; ++i) lv.end[i] = level_end[i < n_scales ? i : n_scales - 1];
+  score_finalize_kernel<<<n_seq, 256, 0, st>>>(reinterpret_cast<const float2*>(part), n_tiles, gt_logit, L, lv, tok_logp,
+                                               per_scale, total, first_pos);
+  VB_CUDA_CHECK(cudaGetLastError());
+  return VB_OK;
+}
+
+}  // namespace vb

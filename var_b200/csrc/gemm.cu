@@ -78,7 +78,7 @@ int gemm_launch(const void* A, const void* W, const GemmParams& p, int epi, cuda
     VB_REQUIRE(p.pos0 >= 0 && p.pos0 + p.rows_per_seq <= p.Lmax, "gemm/qkv: cache overflow pos0=%d l=%d Lmax=%d", p.pos0,
                p.rows_per_seq, p.Lmax);
   } else if (epi == EPI_SCORE) {
-    VB_REQUIRE(p.gt && p.part && p.gt_logit && p.bias, "gemm/score: null pointer");
+    VB_REQUIRE(p.gt && p.part && p.gt_logit && p.bias && p.gt_mod > 0, "gemm/score: null pointer or gt_mod=%d", p.gt_mod);
   } else {
     VB_REQUIRE(p.out, "gemm: null output");
     if (epi == EPI_GATE_RESID)

@@ -30,7 +30,8 @@ struct GemmParams {
   const float* q_scale;    // [H] = exp(min(scale_mul, ln 100))
   int C, H, pos0, Lmax;
   // EPI_SCORE
-  const int* gt;    // [M] ground-truth token per row
+  const int* gt;    // ground-truth token of row m = gt[m % gt_mod]
+  int gt_mod;
   float2* part;     // [M, n_tiles] (max, sum exp(x - max)) over the tile's columns
   float* gt_logit;  // [M]
 };

@@ -174,7 +174,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       } else if constexpr (EPI == EPI_SCORE) {
         float run_max = -INFINITY, run_sum = 0.f;
-        const int gt = row_ok ? __ldg(p.gt + row) : -1;
+        const int gt = row_ok ? __ldg(p.gt + (row % p.gt_mod)) : -1;
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           const int n0 = n_base + c * 32;

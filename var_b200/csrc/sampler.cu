@@ -1,0 +1,197 @@
+// Classifier-free-guidance logit mixing fused with top-k (+top-p) filtering and sampling from caller-supplied
+// Exp(1) noise. One CTA per (image, position) row of V logits held in shared memory.
+//
+// Reference semantics: models/var.py:172-175 and models/helpers.py:6-19:
+//   x = (1+t)*cond - t*uncond                      (two rounded products and a subtraction, no FMA)
+//   top-k: thr = k-th largest; x < thr -> -inf      (ties with thr are kept)
+//   top-p: ascending sort, softmax, cumsum <= 1-p removed, the largest is always kept
+//   p = softmax(x); idx = argmax_v(p_v / q_v)       == torch.multinomial(p, 1) with q ~ Exp(1)
+#include "sampler.h"
+
+#include "common.cuh"
+#include "host.h"
+
+namespace vb {
+
+constexpr int ST = 256;
+
+__device__ __forceinline__ uint32_t f2key(float f) {  // order-preserving float -> uint
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+__device__ float block_max(float v, float* red) {
+  v = warp_max(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = red[0];
+  for (int i = 1; i < ST / 32; ++i) r = fmaxf(r, red[i]);
+  __syncthreads();
+  return r;
+}
+__device__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = red[0];
+  for (int i = 1; i < ST / 32; ++i) r += red[i];
+  __syncthreads();
+  return r;
+}
+
+// In-place ascending bitonic sort of (key, payload) pairs in shared memory; n is a power of two.
+__device__ void bitonic_sort(float* key, int* val, int n) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n; i += ST) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const bool up = (i & k) == 0;
+          const float a = key[i], b = key[ixj];
+          const int va = val[i], vb2 = val[ixj];
+          // total order: by key, ties by original index (stable, like torch.sort)
+          const bool gt = (a > b) || (a == b && va > vb2);
+          if (gt == up) { key[i] = b; key[ixj] = a; val[i] = vb2; val[ixj] = va; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(ST)
+sample_kernel(const float* __restrict__ logits, int B, int l, int V, int use_cfg, float one_plus_t, float t,
+              const float* __restrict__ q, int top_k, float top_p, float p_lim, long long* __restrict__ idx_out,
+              float* __restrict__ mixed_out, int Vpow2) {
+  extern __shared__ float sm[];
+  float* xs = sm;                                   // [V]
+  float* sk = xs + V;                               // [Vpow2] sort keys (top-p only)
+  int* sv = reinterpret_cast<int*>(sk + Vpow2);     // [Vpow2] sort payload (top-p only)
+  __shared__ float red[ST / 32];
+  __shared__ int hist[256];
+  __shared__ uint32_t sel_prefix;
+  __shared__ int sel_k;
+  __shared__ float bval[ST / 32];
+  __shared__ int bidx[ST / 32];
+  const int r = blockIdx.x;  // row = b*l + pos
+  const int tid = threadIdx.x;
+  const float* lc = logits + (size_t)r * V;
+  const float* lu = logits + ((size_t)B * l + r) * V;
+  for (int v = tid; v < V; v += ST) {
+    float x = lc[v];
+    if (use_cfg) x = __fsub_rn(__fmul_rn(one_plus_t, x), __fmul_rn(t, lu[v]));
+    xs[v] = x;
+    if (mixed_out) mixed_out[(size_t)r * V + v] = x;
+  }
+  __syncthreads();
+
+  if (top_k > 0 && top_k < V) {
+    // exact k-th largest by 4-pass radix select on order-preserving keys
+    if (tid == 0) { sel_prefix = 0; sel_k = top_k; }
+    for (int pass = 0; pass < 4; ++pass) {
+      const int shift = 24 - 8 * pass;
+      hist[tid] = 0;
+      __syncthreads();
+      const uint32_t prefix = sel_prefix;
+      const uint32_t mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+      for (int v = tid; v < V; v += ST) {
+        const uint32_t k = f2key(xs[v]);
+        if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 255], 1);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int need = sel_k, bin = 255;
+        for (; bin > 0; --bin) {
+          if (hist[bin] >= need) break;
+          need -= hist[bin];
+        }
+        sel_k = need;
+        sel_prefix = prefix | ((uint32_t)bin << shift);
+      }
+      __syncthreads();
+    }
+    const float thr = key2f(sel_prefix);
+    for (int v = tid; v < V; v += ST)
+      if (xs[v] < thr) xs[v] = -INFINITY;
+    __syncthreads();
+  }
+
+  if (top_p > 0.f) {
+    // helpers.py:11-15. Ascending stable sort, softmax over the sorted row, inclusive cumsum (double accumulator as
+    // ATen's CPU cumsum), remove entries with cumsum <= 1-p except the last (largest).
+    for (int i = tid; i < Vpow2; i += ST) {
+      sk[i] = i < V ? xs[i] : INFINITY;
+      sv[i] = i;
+    }
+    __syncthreads();
+    bitonic_sort(sk, sv, Vpow2);
+    float m = -INFINITY;
+    for (int i = tid; i < V; i += ST) m = fmaxf(m, sk[i]);
+    m = block_max(m, red);
+    float ps = 0.f;
+    for (int i = tid; i < V; i += ST) ps += expf(sk[i] - m);
+    const float sum = block_sum(ps, red);
+    if (tid == 0) {
+      double c = 0.0;
+      const float lim = p_lim;
+      for (int i = 0; i < V - 1; ++i) {
+        c += (double)(expf(sk[i] - m) / sum);
+        if ((float)c <= lim) xs[sv[i]] = -INFINITY; else break;  // cumsum is monotone: nothing later is removed
+      }
+    }
+    __syncthreads();
+  }
+
+  float m = -INFINITY;
+  for (int v = tid; v < V; v += ST) m = fmaxf(m, xs[v]);
+  m = block_max(m, red);
+  float ps = 0.f;
+  for (int v = tid; v < V; v += ST) ps += expf(xs[v] - m);
+  const float sum = block_sum(ps, red);
+  const float* qr = q + (size_t)r * V;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int v = tid; v < V; v += ST) {
+    const float ratio = (expf(xs[v] - m) / sum) / qr[v];
+    if (ratio > best) { best = ratio; bi = v; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+  }
+  if ((tid & 31) == 0) { bval[tid >> 5] = best; bidx[tid >> 5] = bi; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < ST / 32; ++w)
+      if (bval[w] > best || (bval[w] == best && bidx[w] < bi)) { best = bval[w]; bi = bidx[w]; }
+    idx_out[r] = bi == 0x7fffffff ? 0 : bi;
+  }
+}
+
+int sample_launch(const SampleArgs& a, cudaStream_t st) {
+  VB_REQUIRE(a.logits && a.q && a.idx_out, "sample: null pointer");
+  VB_REQUIRE(a.B > 0 && a.l > 0 && a.V > 0, "sample: bad shape B=%d l=%d V=%d", a.B, a.l, a.V);
+  VB_REQUIRE(a.top_k >= 0 && a.top_p >= 0.f && a.top_p <= 1.f, "sample: bad top_k=%d top_p=%f", a.top_k, a.top_p);
+  int vp2 = 1;
+  while (vp2 < a.V) vp2 <<= 1;
+  const bool use_p = a.top_p > 0.f;
+  const size_t smem = (size_t)a.V * 4 + (use_p ? (size_t)vp2 * 8 : 0);
+  VB_REQUIRE(smem <= 200 * 1024, "sample: V=%d too large for the shared-memory sampler", a.V);
+  static size_t attr = 0;
+  if (smem > attr && smem > 48 * 1024) {
+    VB_CUDA_CHECK(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  const float opt = (float)(1.0 + a.t), tf = (float)a.t;
+  sample_kernel<<<a.B * a.l, ST, smem, st>>>(a.logits, a.B, a.l, a.V, a.use_cfg, opt, tf, a.q, a.top_k, a.top_p, (float)(1.0 - (double)a.top_p),
+                                             reinterpret_cast<long long*>(a.idx_out), a.mixed_out, use_p ? vp2 : 0);
+  VB_CUDA_CHECK(cudaGetLastError());
+  return VB_OK;
+}
+
+}  // namespace vb

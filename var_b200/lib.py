@@ -27,7 +27,36 @@ class GemmArgs(C.Structure):
         ("resid", C.c_void_p), ("gate", C.c_void_p), ("rows_per_seq", C.c_int), ("gate_ld", C.c_int),
         ("q_out", C.c_void_p), ("k_cache", C.c_void_p), ("v_cache", C.c_void_p), ("q_scale", C.c_void_p),
         ("C", C.c_int), ("H", C.c_int), ("pos0", C.c_int), ("Lmax", C.c_int),
-        ("gt", C.c_void_p), ("part", C.c_void_p), ("gt_logit", C.c_void_p),
+        ("gt", C.c_void_p), ("gt_mod", C.c_int), ("part", C.c_void_p), ("gt_logit", C.c_void_p),
+    ]
+
+
+MAX_SCALES = 16
+
+
+class QuantDesc(C.Structure):
+    _fields_ = [
+        ("Cvae", C.c_int), ("V", C.c_int), ("n_scales", C.c_int),
+        ("ph", C.c_int * MAX_SCALES), ("pw", C.c_int * MAX_SCALES), ("phi_of_scale", C.c_int * MAX_SCALES),
+        ("n_phi", C.c_int), ("resi", C.c_float),
+        ("codebook", C.c_void_p), ("phi_w", C.c_void_p), ("phi_b", C.c_void_p),
+    ]
+
+
+class BlockWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in
+                ("w_qkv", "b_qkv", "q_scale", "w_proj", "b_proj", "w_fc1", "b_fc1", "w_fc2", "b_fc2")]
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [
+        ("depth", C.c_int), ("C", C.c_int), ("H", C.c_int), ("V", C.c_int), ("Cvae", C.c_int), ("n_scales", C.c_int),
+        ("num_classes", C.c_int), ("shared_aln", C.c_int), ("norm_eps", C.c_float),
+        ("patch_nums", C.c_int * MAX_SCALES),
+        ("blocks", C.POINTER(BlockWeights)),
+        ("w_ada", C.c_void_p), ("b_ada", C.c_void_p), ("ada_rows", C.c_int), ("ada_gss", C.c_void_p),
+        ("w_head", C.c_void_p), ("b_head", C.c_void_p), ("w_word", C.c_void_p), ("b_word", C.c_void_p),
+        ("class_emb", C.c_void_p), ("pos_start", C.c_void_p), ("lvl_pos", C.c_void_p),
     ]
 
 
@@ -64,10 +93,35 @@ def _declare(lib: C.CDLL) -> None:
         fn = getattr(lib, name)  # AttributeError here = header/library mismatch
         fn.argtypes = argtypes
         fn.restype = i32
+    for name in ("var_b200_ada_workspace", "var_b200_blocks_workspace", "var_b200_score_workspace"):
+        fn = getattr(lib, name)
+        fn.argtypes = [C.POINTER(ModelDesc), i32] if name == "var_b200_ada_workspace" else [C.POINTER(ModelDesc), i32, i32]
+        fn.restype = C.c_size_t
+
+
+def exported_symbols():
+    """Every symbol include/var_b200.h declares (used by the CPU-only ABI test)."""
+    import re
+    hdr = (Path(__file__).resolve().parent.parent / "include" / "var_b200.h").read_text()
+    return sorted(set(re.findall(r"VAR_B200_API[^;(]*?\b(var_b200_\w+)\s*\(", hdr)))
 
 
 def _EXTRA_SIGS(vp, i32, i64, f32):
-    return {}
+    sz, dbl = C.c_size_t, C.c_double
+    return {
+        "var_b200_attention": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, C.POINTER(C.c_int), vp],
+        "var_b200_ln_modulate": [vp, vp, vp, i32, i32, vp, i32, i32, f32, vp],
+        "var_b200_quant_encode": [C.POINTER(QuantDesc), vp, i32, vp, vp, vp, vp],
+        "var_b200_quant_decode": [C.POINTER(QuantDesc), vp, i32, vp, vp, vp, vp],
+        "var_b200_quant_next_input": [C.POINTER(QuantDesc), i32, vp, vp, i32, vp, vp, vp],
+        "var_b200_cfg_topk_sample": [vp, i32, i32, i32, i32, dbl, vp, i32, f32, vp, vp, vp],
+        "var_b200_ada_ld": [C.POINTER(ModelDesc)],
+        "var_b200_ada_params": [C.POINTER(ModelDesc), vp, i32, vp, vp, sz, vp],
+        "var_b200_embed": [C.POINTER(ModelDesc), vp, i32, i32, vp, i32, i32, i32, i32, vp, vp],
+        "var_b200_blocks": [C.POINTER(ModelDesc), vp, vp, i32, i32, i32, vp, sz, i32, vp, vp, sz, vp],
+        "var_b200_head_logits": [C.POINTER(ModelDesc), vp, vp, i32, i32, vp, vp, sz, vp],
+        "var_b200_head_score": [C.POINTER(ModelDesc), vp, vp, i32, i32, vp, i32, i32, vp, vp, vp, vp, sz, vp],
+    }
 
 
 def check(rc: int, what: str = "") -> None:

@@ -1,0 +1,408 @@
+"""Host-side mirror of VAR (/root/reference/models/var.py, models/basic_var.py) over the sm_100a kernels.
+
+Same constructor, public methods (`forward`, `autoregressive_infer_cfg`, `get_logits`) and state_dict keys/shapes as
+the reference, so `var_d{16,20,24,30,36}.pth` load with strict=True. The nn.Module tree only *holds* parameters;
+all arithmetic runs in libvar_b200.so through the C-ABI (include/var_b200.h). There is no PyTorch fallback: calling
+the model with CPU parameters, or without the built library, raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import List, Optional, Sequence, Tuple, Union
+
+import torch
+import torch.nn as nn
+
+from . import lib as L
+from .vqvae import VQVAE
+
+
+# --------------------------------------------------------------------------------------------------
+# parameter containers (names follow models/basic_var.py so the state_dict keys match)
+# --------------------------------------------------------------------------------------------------
+class _SelfAttention(nn.Module):
+    def __init__(self, C: int, H: int, attn_l2_norm: bool):
+        super().__init__()
+        self.num_heads, self.head_dim, self.attn_l2_norm = H, C // H, attn_l2_norm
+        if attn_l2_norm:
+            self.scale_mul_1H11 = nn.Parameter(torch.full((1, H, 1, 1), 4.0).log())
+            self.max_scale_mul = math.log(100)
+        self.mat_qkv = nn.Linear(C, 3 * C, bias=False)
+        self.q_bias, self.v_bias = nn.Parameter(torch.zeros(C)), nn.Parameter(torch.zeros(C))
+        self.register_buffer("zero_k_bias", torch.zeros(C))
+        self.proj = nn.Linear(C, C)
+
+    def kv_caching(self, enable: bool):  # the cache lives in VAR._kv (preallocated), kept for API compatibility
+        pass
+
+
+class _FFN(nn.Module):
+    def __init__(self, C: int, hidden: int):
+        super().__init__()
+        self.fc1, self.fc2 = nn.Linear(C, hidden), nn.Linear(hidden, C)
+
+
+class _AdaLNBlock(nn.Module):
+    def __init__(self, C: int, D: int, H: int, mlp_ratio: float, shared_aln: bool, attn_l2_norm: bool):
+        super().__init__()
+        self.attn = _SelfAttention(C, H, attn_l2_norm)
+        self.ffn = _FFN(C, round(C * mlp_ratio))
+        self.shared_aln = shared_aln
+        if shared_aln:
+            self.ada_gss = nn.Parameter(torch.randn(1, 1, 6, C) / C ** 0.5)
+        else:
+            self.ada_lin = nn.Sequential(nn.SiLU(inplace=False), nn.Linear(D, 6 * C))
+
+
+class _AdaLNBeforeHead(nn.Module):
+    def __init__(self, C: int, D: int):
+        super().__init__()
+        self.ada_lin = nn.Sequential(nn.SiLU(inplace=False), nn.Linear(D, 2 * C))
+
+
+class VAR(nn.Module):
+    def __init__(self, vae_local: VQVAE, num_classes=1000, depth=16, embed_dim=1024, num_heads=16, mlp_ratio=4.,
+                 drop_rate=0., attn_drop_rate=0., drop_path_rate=0., norm_eps=1e-6, shared_aln=False, cond_drop_rate=0.1,
+                 attn_l2_norm=False, patch_nums=(1, 2, 3, 4, 5, 6, 8, 10, 13, 16), flash_if_available=True,
+                 fused_if_available=True):
+        super().__init__()
+        assert embed_dim % num_heads == 0
+        if not attn_l2_norm:
+            raise NotImplementedError("attn_l2_norm=False (basic_var.py:72) is not built: every reference script uses "
+                                      "the build_vae_var default attn_l2_norm=True (models/__init__.py:15)")
+        if embed_dim // num_heads != 64:
+            raise NotImplementedError("the attention kernel is specialised for head_dim 64 (models/__init__.py:19-20)")
+        if mlp_ratio != 4.:
+            raise NotImplementedError("mlp_ratio must be 4")
+        if len(patch_nums) > L.MAX_SCALES:
+            raise ValueError(f"at most {L.MAX_SCALES} scales")
+        self.Cvae, self.V = vae_local.Cvae, vae_local.vocab_size
+        self.depth, self.C, self.D, self.num_heads = depth, embed_dim, embed_dim, num_heads
+        self.cond_drop_rate = cond_drop_rate
+        self.drop_path_rate = drop_path_rate
+        self.prog_si = -1
+        self.norm_eps = norm_eps
+        self.shared_aln = shared_aln
+        self.patch_nums: Tuple[int, ...] = tuple(patch_nums)
+        self.L = sum(pn ** 2 for pn in self.patch_nums)
+        self.first_l = self.patch_nums[0] ** 2
+        self.begin_ends, cur = [], 0
+        for pn in self.patch_nums:
+            self.begin_ends.append((cur, cur + pn * pn))
+            cur += pn * pn
+        self.num_stages_minus_1 = len(self.patch_nums) - 1
+        self._rng: Optional[torch.Generator] = None
+
+        self.vae_proxy: Tuple[VQVAE] = (vae_local,)
+        self.vae_quant_proxy = (vae_local.quantize,)
+        self.word_embed = nn.Linear(self.Cvae, self.C)
+
+        init_std = math.sqrt(1 / self.C / 3)
+        self.num_classes = num_classes
+        self.class_emb = nn.Embedding(num_classes + 1, self.C)
+        nn.init.trunc_normal_(self.class_emb.weight.data, mean=0, std=init_std)
+        self.pos_start = nn.Parameter(torch.empty(1, self.first_l, self.C))
+        nn.init.trunc_normal_(self.pos_start.data, mean=0, std=init_std)
+        self.pos_1LC = nn.Parameter(torch.empty(1, self.L, self.C))
+        nn.init.trunc_normal_(self.pos_1LC.data, mean=0, std=init_std)
+        self.lvl_embed = nn.Embedding(len(self.patch_nums), self.C)
+        nn.init.trunc_normal_(self.lvl_embed.weight.data, mean=0, std=init_std)
+
+        self.shared_ada_lin = (nn.Sequential(nn.SiLU(inplace=False), nn.Linear(self.D, 6 * self.C)) if shared_aln
+                               else nn.Identity())
+        self.blocks = nn.ModuleList(_AdaLNBlock(self.C, self.D, num_heads, mlp_ratio, shared_aln, attn_l2_norm)
+                                    for _ in range(depth))
+
+        d = torch.cat([torch.full((pn * pn,), i) for i, pn in enumerate(self.patch_nums)]).view(1, self.L, 1)
+        dT = d.transpose(1, 2)
+        self.register_buffer("lvl_1L", dT[:, 0].contiguous())
+        # kept only for state_dict compatibility (var.py:111-112): the kernels compute the mask from level ends
+        self.register_buffer("attn_bias_for_masking",
+                             torch.where(d >= dT, 0., -torch.inf).reshape(1, 1, self.L, self.L).contiguous())
+
+        self.head_nm = _AdaLNBeforeHead(self.C, self.D)
+        self.head = nn.Linear(self.C, self.V)
+        self._pack_key = None
+        self._packed = None
+
+    # ------------------------------------------------------------------ reference-compatible helpers
+    @property
+    def rng(self) -> torch.Generator:
+        dev = self.lvl_1L.device
+        if self._rng is None or self._rng.device != dev:
+            self._rng = torch.Generator(device=dev)
+        return self._rng
+
+    def init_weights(self, init_adaln=0.5, init_adaln_gamma=1e-5, init_head=0.02, init_std=0.02, conv_std_or_gain=0.02):
+        """models/var.py:577-627 (same distributions; used by build_vae_var)."""
+        if init_std < 0:
+            init_std = (1 / self.C / 3) ** 0.5
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.trunc_normal_(m.weight.data, std=init_std)
+                if m.bias is not None:
+                    m.bias.data.zero_()
+            elif isinstance(m, nn.Embedding):
+                nn.init.trunc_normal_(m.weight.data, std=init_std)
+        if init_head >= 0:
+            self.head.weight.data.mul_(init_head)
+            self.head.bias.data.zero_()
+        self.head_nm.ada_lin[-1].weight.data.mul_(init_adaln)
+        self.head_nm.ada_lin[-1].bias.data.zero_()
+        depth = len(self.blocks)
+        for b in self.blocks:
+            b.attn.proj.weight.data.div_(math.sqrt(2 * depth))
+            b.ffn.fc2.weight.data.div_(math.sqrt(2 * depth))
+            if hasattr(b, "ada_lin"):
+                b.ada_lin[-1].weight.data[2 * self.C:].mul_(init_adaln)
+                b.ada_lin[-1].weight.data[:2 * self.C].mul_(init_adaln_gamma)
+                b.ada_lin[-1].bias.data.zero_()
+            else:
+                b.ada_gss.data[:, :, 2:].mul_(init_adaln)
+                b.ada_gss.data[:, :, :2].mul_(init_adaln_gamma)
+
+    # ------------------------------------------------------------------ weight packing for the C-ABI
+    def _version_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def repack(self):
+        self._pack_key = None
+
+    def _model(self) -> "PackedModel":
+        key = self._version_key()
+        if key != self._pack_key:
+            self._packed = PackedModel(self)
+            self._pack_key = key
+        return self._packed
+
+    # ------------------------------------------------------------------ forward passes
+    def _labels_i32(self, label_B: torch.Tensor, n: int) -> torch.Tensor:
+        lab = label_B.reshape(-1).to(device=self.lvl_1L.device, dtype=torch.int32)
+        if lab.numel() == 1 and n > 1:
+            lab = lab.expand(n)
+        if lab.numel() != n:
+            raise RuntimeError(f"label_B has {lab.numel()} entries but the batch is {n} (models/var.py:199-203)")
+        return lab.contiguous()
+
+    @torch.no_grad()
+    def get_logits(self, h_or_h_and_residual, cond_BD=None, *, labels: Optional[torch.Tensor] = None):
+        """models/var.py:118-124. The kernel path is driven by labels (cond_BD = class_emb(label))."""
+        raise NotImplementedError("get_logits is fused into forward/autoregressive_infer_cfg (var_b200_head_logits)")
+
+    @torch.no_grad()
+    def forward(self, label_B: torch.LongTensor, x_BLCv_wo_first_l: torch.Tensor, *, return_blocks: bool = False):
+        """models/var.py:192-234: teacher-forced logits [B, L, V] fp32."""
+        if self.prog_si >= 0:
+            raise NotImplementedError("progressive training (prog_si >= 0) is not supported (inference hot path)")
+        if self.training and self.drop_path_rate > 0:
+            raise RuntimeError("var_b200 implements the inference path: call .eval() first (drop_path is training only)")
+        pm = self._model()
+        B = x_BLCv_wo_first_l.shape[0]
+        dev = self.lvl_1L.device
+        label_B = label_B.to(dev)
+        # same RNG side effect and label dropout as the reference (var.py:201)
+        label_B = torch.where(torch.rand(B, device=dev) < self.cond_drop_rate, self.num_classes, label_B)
+        labels = self._labels_i32(label_B, B)
+        x_in = x_BLCv_wo_first_l.to(dev).float().contiguous()
+        x = pm.embed(x_in, B, labels, B, self.L, self.first_l, 0)
+        ada = pm.ada_params(labels)
+        dump = torch.empty((self.depth, B * self.L, self.C), device=dev) if return_blocks else None
+        pm.blocks_teacher(x, ada, B, dump)
+        logits = pm.head_logits(x, ada, B, self.L)
+        if return_blocks:
+            return logits, [dump[i].view(B, self.L, self.C) for i in range(self.depth)]
+        return logits
+
+    @torch.no_grad()
+    def autoregressive_infer_cfg(self, B: int, label_B: Optional[Union[int, torch.LongTensor]], g_seed: Optional[int] = None,
+                                 cfg=1.5, top_k=0, top_p=0.0, more_smooth=False, *, forced_idx=None, return_trace=False,
+                                 decode=True):
+        """models/var.py:126-190: KV-cached CFG sampling; returns images [B,3,H,W] in [0,1].
+        Extras (keyword-only, for the parity harness): forced_idx = tokens to feed instead of the sampled ones,
+        return_trace = also return dict(idx, logits, f_hat); decode=False skips the CNN decoder (returns f_hat)."""
+        if more_smooth:
+            raise NotImplementedError("more_smooth (Gumbel-softmax visualisation path, var.py:178-180) is out of scope")
+        pm = self._model()
+        dev = self.lvl_1L.device
+        if g_seed is None:
+            rng = None
+        else:
+            self.rng.manual_seed(g_seed)
+            rng = self.rng
+        if label_B is None:
+            uniform = torch.full((1, self.num_classes), 1.0 / self.num_classes, dtype=torch.float32, device=dev)
+            label_B = torch.multinomial(uniform, num_samples=B, replacement=True, generator=rng).reshape(B)
+        elif isinstance(label_B, int):
+            label_B = torch.full((B,), fill_value=self.num_classes if label_B < 0 else label_B, device=dev)
+        label_B = label_B.to(dev)
+        labels = self._labels_i32(torch.cat((label_B, torch.full_like(label_B, self.num_classes))), 2 * B)
+        quant = self.vae_quant_proxy[0]
+        S = len(self.patch_nums)
+        ada = pm.ada_params(labels)
+        kv = pm.kv_cache(2 * B)
+        H = W = self.patch_nums[-1]
+        f_hat = torch.zeros((B, self.Cvae, H, W), dtype=torch.float32, device=dev)
+        trace = dict(idx=[], logits=[]) if return_trace else None
+        cur, nxt = 0, None
+        for si, pn in enumerate(self.patch_nums):
+            l = pn * pn
+            if si == 0:
+                x = pm.embed(None, 0, labels, 2 * B, l, self.first_l, 0)
+            else:
+                x = pm.embed(nxt, B, labels, 2 * B, l, 0, cur)
+            pm.blocks_cached(x, ada, 2 * B, l, cur, kv)
+            logits = pm.head_logits(x, ada, 2 * B, l)
+            q = torch.empty((B * l, self.V), dtype=torch.float32, device=dev).exponential_(1.0, generator=rng)
+            t = cfg * (si / self.num_stages_minus_1) if self.num_stages_minus_1 > 0 else 0.0
+            mixed = torch.empty((B, l, self.V), dtype=torch.float32, device=dev) if return_trace else None
+            idx = pm.sample(logits, B, l, t, q, top_k, top_p, mixed)
+            if forced_idx is not None:
+                idx = forced_idx[si].to(dev).to(torch.int64).contiguous()
+            if return_trace:
+                trace["idx"].append(idx)
+                trace["logits"].append(mixed)
+            _, nxt = quant.get_next_autoregressive_input(si, S, f_hat, idx_Bl=idx, token_major=True)
+            cur += l
+        if return_trace:
+            trace["f_hat"] = f_hat
+        img = self.vae_proxy[0].fhat_to_img(f_hat).add_(1).mul_(0.5) if decode else f_hat
+        return (img, trace) if return_trace else img
+
+    def extra_repr(self):
+        return f"depth={self.depth}, C={self.C}, shared_aln={self.shared_aln}, drop_path_rate={self.drop_path_rate:g}"
+
+
+# --------------------------------------------------------------------------------------------------
+# packed weights + thin typed wrappers over the C-ABI
+# --------------------------------------------------------------------------------------------------
+class PackedModel:
+    """bf16/fp32 copies of the parameters in the layout var_b200_model_t expects, plus call wrappers."""
+
+    def __init__(self, var: VAR):
+        p0 = var.head.weight
+        if not p0.is_cuda:
+            raise L.VarB200Error("var_b200.VAR needs its parameters on a CUDA device: there is no CPU fallback path")
+        self.lib = L.load()
+        self.dev = p0.device
+        self.var_cfg = (var.depth, var.C, var.num_heads, var.V, var.Cvae, var.L, var.first_l)
+        C_, depth = var.C, var.depth
+        bf = lambda t: t.detach().to(torch.bfloat16).contiguous()
+        f32 = lambda t: t.detach().float().contiguous()
+        keep: List[torch.Tensor] = []
+        self.blocks_arr = (L.BlockWeights * depth)()
+        for i, b in enumerate(var.blocks):
+            a = b.attn
+            ts = dict(
+                w_qkv=bf(a.mat_qkv.weight),
+                b_qkv=f32(torch.cat((a.q_bias, torch.zeros_like(a.q_bias), a.v_bias))),
+                q_scale=f32(a.scale_mul_1H11.clamp_max(a.max_scale_mul).exp().reshape(-1)),
+                w_proj=bf(a.proj.weight), b_proj=f32(a.proj.bias),
+                w_fc1=bf(b.ffn.fc1.weight), b_fc1=f32(b.ffn.fc1.bias),
+                w_fc2=bf(b.ffn.fc2.weight), b_fc2=f32(b.ffn.fc2.bias))
+            for k, t in ts.items():
+                setattr(self.blocks_arr[i], k, t.data_ptr())
+                keep.append(t)
+        if var.shared_aln:
+            w_ada = torch.cat((var.shared_ada_lin[1].weight, var.head_nm.ada_lin[1].weight))
+            b_ada = torch.cat((var.shared_ada_lin[1].bias, var.head_nm.ada_lin[1].bias))
+            gss = f32(torch.cat([b.ada_gss.reshape(1, 6 * C_) for b in var.blocks]))
+        else:
+            w_ada = torch.cat([b.ada_lin[1].weight for b in var.blocks] + [var.head_nm.ada_lin[1].weight])
+            b_ada = torch.cat([b.ada_lin[1].bias for b in var.blocks] + [var.head_nm.ada_lin[1].bias])
+            gss = None
+        t = dict(w_ada=bf(w_ada), b_ada=f32(b_ada), w_head=bf(var.head.weight), b_head=f32(var.head.bias),
+                 w_word=f32(var.word_embed.weight), b_word=f32(var.word_embed.bias), class_emb=f32(var.class_emb.weight),
+                 pos_start=f32(var.pos_start.reshape(var.first_l, C_)),
+                 lvl_pos=f32(var.lvl_embed.weight[var.lvl_1L.reshape(-1)] + var.pos_1LC.reshape(var.L, C_)))
+        m = L.ModelDesc()
+        m.depth, m.C, m.H, m.V, m.Cvae = depth, C_, var.num_heads, var.V, var.Cvae
+        m.n_scales, m.num_classes, m.shared_aln, m.norm_eps = len(var.patch_nums), var.num_classes, int(var.shared_aln), var.norm_eps
+        for i, pn in enumerate(var.patch_nums):
+            m.patch_nums[i] = pn
+        m.blocks = C.cast(self.blocks_arr, C.POINTER(L.BlockWeights))
+        for k, v in t.items():
+            setattr(m, k, v.data_ptr())
+            keep.append(v)
+        m.ada_rows = w_ada.shape[0]
+        m.ada_gss = gss.data_ptr() if gss is not None else None
+        if gss is not None:
+            keep.append(gss)
+        self.m, self._keep = m, keep
+        self.depth, self.C, self.H, self.V, self.Cvae, self.L, self.first_l = self.var_cfg
+        self.ada_ld = self.lib.var_b200_ada_ld(C.byref(m))
+        self._ws = {}
+
+    # ---- scratch management: buffers are cached per (tag) and grown on demand
+    def _buf(self, tag: str, nbytes: int) -> torch.Tensor:
+        b = self._ws.get(tag)
+        if b is None or b.numel() < nbytes:
+            b = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=self.dev)
+            self._ws[tag] = b
+        return b
+
+    def ada_params(self, labels_i32: torch.Tensor) -> torch.Tensor:
+        n = labels_i32.numel()
+        out = torch.empty((n, self.ada_ld), dtype=torch.float32, device=self.dev)
+        wsb = self.lib.var_b200_ada_workspace(C.byref(self.m), n)
+        ws = self._buf("ada", wsb)
+        L.check(self.lib.var_b200_ada_params(C.byref(self.m), labels_i32.data_ptr(), n, out.data_ptr(), ws.data_ptr(),
+                                             ws.numel(), L.current_stream()), "ada_params")
+        return out
+
+    def embed(self, x_in, n_x, labels_i32, n_seq, l, first_rows, pos0) -> torch.Tensor:
+        out = torch.empty((n_seq, l, self.C), dtype=torch.float32, device=self.dev)
+        l_in = x_in.shape[1] if x_in is not None else 0
+        L.check(self.lib.var_b200_embed(C.byref(self.m), L.ptr(x_in), n_x, l_in, labels_i32.data_ptr(), n_seq, l,
+                                        first_rows, pos0, out.data_ptr(), L.current_stream()), "embed")
+        return out
+
+    def _blocks_ws(self, n_seq, l, score=False):
+        fn = self.lib.var_b200_score_workspace if score else self.lib.var_b200_blocks_workspace
+        return self._buf("blocks", fn(C.byref(self.m), n_seq, l))
+
+    def blocks_teacher(self, x, ada, n_seq, dump=None):
+        ws = self._blocks_ws(n_seq, self.L)
+        kv = self._buf("kv_scratch", 2 * n_seq * self.C * self.L * 2)
+        L.check(self.lib.var_b200_blocks(C.byref(self.m), x.data_ptr(), ada.data_ptr(), n_seq, self.L, 0, kv.data_ptr(), 0,
+                                         self.L, L.ptr(dump), ws.data_ptr(), ws.numel(), L.current_stream()), "blocks")
+
+    def kv_cache(self, n_seq: int) -> torch.Tensor:
+        """Preallocated zero-initialised cache [depth][2][n_seq,H,L,64] bf16 (replaces torch.cat, basic_var.py:107-109)."""
+        n = self.depth * 2 * n_seq * self.C * self.L
+        kv = self._ws.get("kv_cache")
+        if kv is None or kv.numel() != n:
+            self._ws["kv_cache"] = None
+            kv = torch.zeros(n, dtype=torch.bfloat16, device=self.dev)
+            self._ws["kv_cache"] = kv
+        return kv
+
+    def blocks_cached(self, x, ada, n_seq, l, pos0, kv):
+        ws = self._blocks_ws(n_seq, l)
+        stride = 2 * n_seq * self.C * self.L
+        L.check(self.lib.var_b200_blocks(C.byref(self.m), x.data_ptr(), ada.data_ptr(), n_seq, l, pos0, kv.data_ptr(),
+                                         stride, self.L, None, ws.data_ptr(), ws.numel(), L.current_stream()), "blocks")
+
+    def head_logits(self, x, ada, n_seq, l) -> torch.Tensor:
+        ws = self._blocks_ws(n_seq, l)
+        out = torch.empty((n_seq, l, self.V), dtype=torch.float32, device=self.dev)
+        L.check(self.lib.var_b200_head_logits(C.byref(self.m), x.data_ptr(), ada.data_ptr(), n_seq, l, out.data_ptr(),
+                                              ws.data_ptr(), ws.numel(), L.current_stream()), "head_logits")
+        return out
+
+    def head_score(self, x, ada, n_seq, gt_i32, first_pos=0, per_scale=False, tok_logp=False):
+        ws = self._blocks_ws(n_seq, self.L, score=True)
+        scores = torch.empty(n_seq, dtype=torch.float32, device=self.dev)
+        ps = torch.empty((n_seq, self.m.n_scales), dtype=torch.float32, device=self.dev) if per_scale else None
+        tl = torch.empty((n_seq, self.L), dtype=torch.float32, device=self.dev) if tok_logp else None
+        L.check(self.lib.var_b200_head_score(C.byref(self.m), x.data_ptr(), ada.data_ptr(), n_seq, self.L,
+                                             gt_i32.data_ptr(), gt_i32.numel(), first_pos, scores.data_ptr(), L.ptr(ps),
+                                             L.ptr(tl), ws.data_ptr(), ws.numel(), L.current_stream()), "head_score")
+        return scores, ps, tl
+
+    def sample(self, logits, B, l, t, q, top_k, top_p, mixed=None, use_cfg=True) -> torch.Tensor:
+        idx = torch.empty((B, l), dtype=torch.int64, device=self.dev)
+        L.check(self.lib.var_b200_cfg_topk_sample(logits.data_ptr(), B, l, self.V, int(use_cfg), float(t), q.data_ptr(),
+                                                  int(top_k), float(top_p), idx.data_ptr(), L.ptr(mixed),
+                                                  L.current_stream()), "cfg_topk_sample")
+        return idx
