@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the VAR next-scale-prediction hot path on B200 (contract: task statement ④).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload sample_d30|score_d16|sample_d16] [--impl reference]
+
+One "step" = one pass of the hot path over one batch of synthetic input:
+  sample_d30 (default, BASELINE.json configs[4]): VAR-d30 autoregressive_infer_cfg, 256 px, B=256 per GPU, cfg=1.5,
+              top_k=900, bf16 GEMMs / fp32 residual, preallocated KV cache. Metric: images/sec.
+  score_d16  (configs[3]): VAR-d16 1000-class likelihood scoring of one image per step per GPU... (classes sharded
+              over the ranks with one all-gather when N > 1). Metric: images/sec.
+  sample_d16 (configs[2]): VAR-d16 sampling, B=64.
+The JSON line carries `value` (device-timed, inputs resident, to f_hat), `e2e` (public API with host labels in, images
+out, CNN decoder under bf16 autocast), `roofline` (dominant kernel = the tcgen05 GEMM, timed live at the step's
+largest shape), `cpu_baseline` (the oracle port on this box's host cores, bounded sample) and `secondary` (the other
+headline workload). `--impl reference` times the CPU oracle port only (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+PATCH_NUMS = (1, 2, 3, 4, 5, 6, 8, 10, 13, 16)
+L_SEQ = sum(p * p for p in PATCH_NUMS)
+V, CVAE = 4096, 32
+
+
+def flops_per_seq(depth: int) -> float:
+    """Algorithmic FLOPs of one 680-token sequence; attention counted on visible pairs only."""
+    C = 64 * depth
+    vis, cum = 0, 0
+    for p in PATCH_NUMS:
+        cum += p * p
+        vis += p * p * cum
+    return (24 * C * C * depth * L_SEQ + 4 * C * depth * vis + 2 * C * V * L_SEQ + (12 * C * C * depth + 4 * C * C)
+            + 2 * CVAE * C * (L_SEQ - 1))
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(burst=d["bf16_tflops"], sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), hbm=d["hbm_gbs"],
+                    src="measured")
+    return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = max([int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()] or [0])
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=mx or None, reasons=reasons)
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm (oracle port)
+def cpu_sampling_step(depth: int, n_img: int, threads: int):
+    """One bounded CPU sample of the same workload through the oracle port: n_img images, all 10 scales."""
+    from oracle import var_oracle as VO
+    from oracle.quant_oracle import QuantOracle
+    torch.set_num_threads(threads)
+    cfg = VO.VarCfg(depth=depth)
+    sd, quant = _cpu_state(depth)
+    g = torch.Generator().manual_seed(0)
+    labels = torch.randint(0, 1000, (n_img,), generator=g)
+    noise = [torch.empty(n_img * p * p, V).exponential_(1, generator=g) for p in PATCH_NUMS]
+    t0 = time.perf_counter()
+    VO.ar_infer(sd, cfg, quant, labels, noise, cfg_scale=1.5, top_k=900)
+    return time.perf_counter() - t0
+
+
+def cpu_scoring_step(depth: int, n_cls: int, threads: int):
+    from oracle import var_oracle as VO
+    torch.set_num_threads(threads)
+    cfg = VO.VarCfg(depth=depth)
+    sd, quant = _cpu_state(depth)
+    g = torch.Generator().manual_seed(0)
+    idx = [torch.randint(0, V, (1, p * p), generator=g).numpy() for p in PATCH_NUMS]
+    t0 = time.perf_counter()
+    vin = torch.from_numpy(quant.idxBl_to_var_input(idx))
+    logits = VO.var_forward(sd, cfg, torch.arange(n_cls), vin.expand(n_cls, -1, -1))
+    VO.class_scores(logits, torch.from_numpy(__import__("numpy").concatenate(idx, axis=1)))
+    return time.perf_counter() - t0
+
+
+_CPU_STATE = {}
+
+
+def _cpu_state(depth: int):
+    if depth not in _CPU_STATE:
+        from oracle.quant_oracle import QuantOracle
+        from var_b200 import build_vae_var
+        from var_b200.init_utils import dense_init_
+        import numpy as np
+        # VQVAE quantizer weights only (the CNN is outside the hot path): tiny ch to keep construction cheap
+        vae, var = build_vae_var("cpu", depth=depth, ch=32)
+        dense_init_(var, seed=2)
+        dense_init_(vae.quantize, seed=1)
+        sd = {k: v.detach() for k, v in var.state_dict().items()}
+        phis = vae.quantize.quant_resi.phis()
+        quant = QuantOracle(vae.quantize.embedding.weight.detach().numpy(), np.stack([p.weight.detach().numpy() for p in phis]),
+                            np.stack([p.bias.detach().numpy() for p in phis]), PATCH_NUMS)
+        _CPU_STATE[depth] = (sd, quant)
+    return _CPU_STATE[depth]
+
+
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference_arm(args, workload):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the Python reference itself
+    cannot travel to the GPU box) on a bounded sample, all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = host_threads()
+    depth = workload["depth"]
+    if workload["kind"] == "sample":
+        n_img, unit_per_step = 1, 1.0
+        fn = lambda: cpu_sampling_step(depth, n_img, threads)
+        sample = f"{n_img} image(s), all 10 scales, cfg=1.5, top_k=900, fp32, oracle port of autoregressive_infer_cfg to f_hat"
+    else:
+        n_cls = 4
+        unit_per_step = n_cls / 1000.0
+        fn = lambda: cpu_scoring_step(depth, n_cls, threads)
+        sample = f"{n_cls} of 1000 classes of one image, fp32 oracle port of VAR.forward + log-softmax/gather/sum"
+    for _ in range(args.warmup):
+        fn()
+    ts = [fn() for _ in range(args.steps)]
+    total = sum(ts)
+    value = unit_per_step * args.steps / total
+    line = dict(impl="reference", metric=workload["metric"], value=value, unit="images/sec", n_gpus=args.gpus,
+                steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * total / args.steps, higher_is_better=True,
+                scaling=workload["scaling"], vs_baseline=None, dtype="f32", data="synthetic", config=workload["config"],
+                cpu_baseline=dict(value=value, unit="images/sec", cores=threads, kind="port", sample=sample),
+                e2e=dict(value=value, unit="images/sec", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def time_gemm(M, N, K, epi, reps=20):
+    """Live CUDA-event timing of the dominant kernel (tcgen05 GEMM) at the step's largest shape."""
+    import ctypes as C
+    from var_b200 import lib as L
+    lib = L.load()
+    dev = "cuda"
+    A = (torch.randn(M, K, device=dev) * 0.05).bfloat16()
+    W = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
+    bias = torch.zeros(N, device=dev)
+    out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    a = L.GemmArgs()
+    a.A, a.W, a.M, a.N, a.K, a.epilogue = A.data_ptr(), W.data_ptr(), M, N, K, epi
+    a.bias, a.out = bias.data_ptr(), out.data_ptr()
+    st = torch.cuda.current_stream()
+    for _ in range(3):
+        L.check(lib.var_b200_gemm_bf16(C.byref(a), st.cuda_stream))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(st)
+    for _ in range(reps):
+        L.check(lib.var_b200_gemm_bf16(C.byref(a), st.cuda_stream))
+    e1.record(st)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e-3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="var_b200")
+    ap.add_argument("--workload", default="sample_d30", choices=["sample_d30", "sample_d16", "score_d16"])
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (sampling) / classes (scoring)")
+    ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+
+    wl = dict(
+        sample_d30=dict(kind="sample", depth=30, batch=256,
+                        metric="images/sec: VAR-d30 256px CFG sampling (autoregressive_infer_cfg, cfg=1.5, top_k=900)"),
+        sample_d16=dict(kind="sample", depth=16, batch=64,
+                        metric="images/sec: VAR-d16 256px CFG sampling (autoregressive_infer_cfg, cfg=1.5, top_k=900)"),
+        score_d16=dict(kind="score", depth=16, batch=1000,
+                       metric="images/sec: VAR-d16 1000-class likelihood scoring (eval_prob bayesian)"),
+    )[args.workload]
+    if args.batch:
+        wl["batch"] = args.batch
+    # sampling: per-GPU batch fixed (weak); scoring: the 1000 classes of one image are split over the ranks (strong)
+    wl["scaling"] = "weak" if wl["kind"] == "sample" else "strong"
+    wl["config"] = dict(workload=args.workload, depth=wl["depth"], px=256, tokens=L_SEQ,
+                        per_gpu_batch=wl["batch"] if wl["kind"] == "sample" else 1,
+                        classes=1000 if wl["kind"] == "score" else None,
+                        sampler="cfg=1.5,top_k=900,top_p=0" if wl["kind"] == "sample" else None,
+                        l2="activations per step >> 126 MB L2 (inputs larger than L2)", parallelism=f"dp{args.gpus}")
+
+    if args.impl == "reference":
+        run_reference_arm(args, wl)
+        return
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from var_b200 import build_vae_var, lib as L
+    from var_b200.init_utils import dense_init_
+    lib = L.load()
+    pk = peaks()
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item())
+
+    def build(depth):
+        vae, var = build_vae_var(dev, depth=depth)
+        dense_init_(var, seed=2)
+        dense_init_(vae, seed=1)
+        var.eval(); vae.eval(); var.cond_drop_rate = 0
+        return vae, var
+
+    def sampling_runner(vae, var, B):
+        g = torch.Generator(device="cpu").manual_seed(rank)
+        labels_host = torch.randint(0, 1000, (B,), generator=g).pin_memory()
+        labels_dev = labels_host.to(dev)
+
+        def step_hot():  # inputs resident, hot path to f_hat
+            var.autoregressive_infer_cfg(B, labels_dev, g_seed=0, cfg=1.5, top_k=900, top_p=0.0, decode=False)
+
+        def step_e2e():  # public API: host labels in, images out; CNN decoder in bf16 like the reference's autocast
+            lab = labels_host.to(dev, non_blocking=True)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                img = var.autoregressive_infer_cfg(B, lab, g_seed=0, cfg=1.5, top_k=900, top_p=0.0)
+            return img.to("cpu", non_blocking=False)
+        return step_hot, step_e2e, B, labels_host.numel() * 8, B * 3 * 256 * 256 * 4
+
+    def scoring_runner(vae, var, K):
+        from var_b200.scoring import class_log_likelihoods, gather_class_scores, shard_range
+        g = torch.Generator(device="cpu").manual_seed(0)
+        img_host = (torch.rand(1, 3, 256, 256, generator=g) * 2 - 1).pin_memory()
+        lo, hi = shard_range(K, rank, world)
+        labels = torch.arange(lo, hi, device=dev)
+        gt_idx = vae.img_to_idxBl(img_host.to(dev))
+
+        def step_hot():  # tokens resident; class-sharded forward + fused score + all-gather
+            local_scores = class_log_likelihoods(var, gt_idx, labels, class_batch=125)
+            return gather_class_scores(local_scores, K, rank, world)
+
+        def step_e2e():  # image on the host -> encoder -> tokens -> scores -> prediction on the host
+            img = img_host.to(dev, non_blocking=True)
+            idx = vae.img_to_idxBl(img)
+            s = gather_class_scores(class_log_likelihoods(var, idx, labels, class_batch=125), K, rank, world)
+            return int(torch.argmax(s).item())
+        return step_hot, step_e2e, 1.0 / world, img_host.numel() * 4, 8
+
+    def measure(step, steps, warmup):
+        for _ in range(warmup):
+            step()
+        barrier()
+        st = torch.cuda.current_stream()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = lib.var_b200_launch_count()
+        e0.record(st)
+        for _ in range(steps):
+            step()
+        e1.record(st)
+        barrier()
+        launches = lib.var_b200_launch_count() - n0
+        return max_over_ranks(e0.elapsed_time(e1) * 1e-3), launches
+
+    vae, var = build(wl["depth"])
+    if wl["kind"] == "sample":
+        hot, e2e, units, h2d, d2h = sampling_runner(vae, var, wl["batch"])
+    else:
+        hot, e2e, units, h2d, d2h = scoring_runner(vae, var, wl["batch"])
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    t_hot, launches = measure(hot, args.steps, max(args.warmup, 3))
+    clk = clocks.stop() if rank == 0 else None
+    t_e2e, _ = measure(e2e, args.steps, 1)
+    value = units * world * args.steps / t_hot
+    value_e2e = units * world * args.steps / t_e2e
+
+    # roofline of the dominant kernel (GEMM family = 96 % of the FLOPs): fc1 at the largest per-step shape
+    depth = wl["depth"]
+    C_ = 64 * depth
+    M_big = (2 * wl["batch"] * 256) if wl["kind"] == "sample" else 125 * L_SEQ
+    t_g = time_gemm(M_big, 4 * C_, C_, L.EPI_GELU_BF16)
+    gemm_tf = 2.0 * M_big * 4 * C_ * C_ / t_g / 1e12
+    fl_img = (2 if wl["kind"] == "sample" else 1000) * flops_per_seq(depth)
+    step_tf = value / world * fl_img / 1e12
+    roofline = dict(bound="tensor", kernel=f"gemm_bf16_kernel<BN,GELU> M={M_big} N={4 * C_} K={C_}", achieved=gemm_tf,
+                    peak=pk["burst"], unit="TFLOP/s", frac=gemm_tf / pk["burst"], traffic=None,
+                    peak_source=f"{pk['src']} MEASURED_PEAKS.json bf16_tflops (burst: kernel timed alone)",
+                    step_achieved=step_tf, step_peak=pk["sustained"], step_frac=step_tf / pk["sustained"],
+                    step_note="whole-step algorithmic FLOPs (SURVEY §8d, both CFG branches) / step time vs sustained peak")
+
+    line = dict(metric=wl["metric"], value=value, unit="images/sec", n_gpus=world, steps=args.steps,
+                warmup=max(args.warmup, 3), ms_per_step=1e3 * t_hot / args.steps, higher_is_better=True, scaling=wl["scaling"],
+                vs_baseline=None, dtype="bf16", data="synthetic (random labels/images, seeded dense random-init weights)",
+                config=wl["config"], clocks=clk,
+                e2e=dict(value=value_e2e, unit="images/sec", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                         note="public API call incl. CNN decoder (cuDNN, bf16 autocast) and host copies"),
+                gpu_launches=int(launches), roofline=roofline)
+
+    if rank == 0 and world == 1 and not args.no_secondary and args.workload == "sample_d30":
+        # the other headline metric, measured in the same run (d16 1000-class scoring, one image per step)
+        del var, vae, hot, e2e
+        torch.cuda.empty_cache()
+        vae2, var2 = build(16)
+        hot2, e2e2, units2, _, _ = scoring_runner(vae2, var2, 1000)
+        t2, _ = measure(hot2, 2, 1)
+        t2e, _ = measure(e2e2, 2, 1)
+        v2 = units2 * 2 / t2
+        line["secondary"] = dict(metric="images/sec: VAR-d16 1000-class likelihood scoring", value=v2, unit="images/sec",
+                                 e2e=units2 * 2 / t2e, pairs_per_sec=v2 * 1000,
+                                 step_frac=v2 * 1000 * flops_per_seq(16) / 1e12 / pk["sustained"])
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = host_threads()
+        if wl["kind"] == "sample":
+            t_cpu = cpu_sampling_step(wl["depth"], 1, threads)
+            line["cpu_baseline"] = dict(value=1.0 / t_cpu, unit="images/sec", cores=threads, kind="port",
+                                        sample="1 image, all 10 scales, fp32 oracle port of autoregressive_infer_cfg to f_hat")
+        else:
+            t_cpu = cpu_scoring_step(wl["depth"], 4, threads)
+            line["cpu_baseline"] = dict(value=4 / 1000.0 / t_cpu, unit="images/sec", cores=threads, kind="port",
+                                        sample="4 of 1000 classes of one image, fp32 oracle port of VAR.forward + score")
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -33,6 +33,8 @@ extern "C" {
 
 /* Message describing the most recent error on the calling thread (never NULL). */
 VAR_B200_API const char* var_b200_last_error(void);
+/* Number of kernels this library has launched so far in the process. */
+VAR_B200_API long long var_b200_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * GEMM family:  D[M,N] = A[M,K] * W[N,K]^T, bf16 operands, fp32 accumulation on tcgen05/TMEM.

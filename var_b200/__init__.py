@@ -27,7 +27,16 @@ def build_vae_var(
 ) -> Tuple[VQVAE, VAR]:
     """Drop-in for models/__init__.py:9-39 (heads = depth, width = 64*depth, dpr = 0.1*depth/24).
     Unlike the reference this does not monkey-patch reset_parameters process-wide."""
+    import torch
     heads, width, dpr = depth, depth * 64, 0.1 * depth / 24
+    with torch.device(device):  # parameters are created (and initialised) directly on the target device
+        return _build(device, patch_nums, V, Cvae, ch, share_quant_resi, num_classes, depth, shared_aln, attn_l2_norm,
+                      flash_if_available, fused_if_available, init_adaln, init_adaln_gamma, init_head, init_std, heads,
+                      width, dpr)
+
+
+def _build(device, patch_nums, V, Cvae, ch, share_quant_resi, num_classes, depth, shared_aln, attn_l2_norm,
+           flash_if_available, fused_if_available, init_adaln, init_adaln_gamma, init_head, init_std, heads, width, dpr):
     vae_local = VQVAE(vocab_size=V, z_channels=Cvae, ch=ch, test_mode=True, share_quant_resi=share_quant_resi,
                       v_patch_nums=patch_nums).to(device)
     var_wo_ddp = VAR(vae_local=vae_local, num_classes=num_classes, depth=depth, embed_dim=width, num_heads=heads,

@@ -280,6 +280,7 @@ int attn_launch(const AttnArgs& a, cudaStream_t st) {
   attn_kernel<<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, reinterpret_cast<__nv_bfloat16*>(a.out), a.Lq, a.H,
                                                    a.q_pos0, lv);
   VB_CUDA_CHECK(cudaGetLastError());
+  vb::count_launch();
   return VB_OK;
 }
 

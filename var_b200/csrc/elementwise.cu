@@ -69,6 +69,7 @@ int ln_modulate(const float* x, const float* scale, const float* shift, int ada_
   ln_modulate_kernel<<<(M + wpb - 1) / wpb, wpb * 32, 0, st>>>(x, scale, shift, ada_ld, rows_per_seq,
                                                                reinterpret_cast<__nv_bfloat16*>(out), M, C, eps);
   VB_CUDA_CHECK(cudaGetLastError());
+  vb::count_launch();
   return VB_OK;
 }
 
@@ -89,6 +90,7 @@ int cond_silu(const float* class_emb, const int* labels, void* out, int n_seq, i
   VB_REQUIRE(class_emb && labels && out && n_seq > 0, "cond_silu: bad arguments");
   cond_silu_kernel<<<n_seq, 256, 0, st>>>(class_emb, labels, reinterpret_cast<__nv_bfloat16*>(out), n_seq, C);
   VB_CUDA_CHECK(cudaGetLastError());
+  vb::count_launch();
   return VB_OK;
 }
 
@@ -104,6 +106,7 @@ int expand_shared_aln(const float* shared, int shared_ld, const float* gss, floa
                       int n_seq, cudaStream_t st) {
   expand_shared_aln_kernel<<<dim3(depth, n_seq), 256, 0, st>>>(shared, shared_ld, gss, ada, ada_ld, depth, 6 * C);
   VB_CUDA_CHECK(cudaGetLastError());
+  vb::count_launch();
   return VB_OK;
 }
 
@@ -147,6 +150,7 @@ int embed_tokens(const float* x_in, int n_x, int l_in, const int* labels, const 
   embed_kernel<<<dim3(l, n_seq), 256, 0, st>>>(x_in, n_x > 0 ? n_x : 1, l_in, labels, class_emb, pos_start, lvl_pos,
                                                w_word, b_word, out, l, first_rows, pos0, C, Cv);
   VB_CUDA_CHECK(cudaGetLastError());
+  vb::count_launch();
   return VB_OK;
 }
 
@@ -209,6 +213,7 @@ int score_finalize(const void* part, int n_tiles, const float* gt_logit, int n_s
   score_finalize_kernel<<<n_seq, 256, 0, st>>>(reinterpret_cast<const float2*>(part), n_tiles, gt_logit, L, lv, tok_logp,
                                                per_scale, total, first_pos);
   VB_CUDA_CHECK(cudaGetLastError());
+  vb::count_launch();
   return VB_OK;
 }
 

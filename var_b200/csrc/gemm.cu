@@ -36,6 +36,7 @@ static int launch_one(const void* A, const void* W, const GemmParams& p, cudaStr
   const int grid = total < sm_count() ? total : sm_count();
   kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
   VB_CUDA_CHECK(cudaGetLastError());
+  vb::count_launch();
   return VB_OK;
 }
 

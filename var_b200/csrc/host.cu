@@ -6,7 +6,10 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <atomic>
 #include <mutex>
+#include <string>
+#include <unordered_map>
 
 #include "common.cuh"
 
@@ -38,8 +41,33 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
+// Descriptor cache: the block driver re-encodes the same (pointer, shape, box) maps on every call (weights and
+// workspace buffers keep their addresses), and cuTensorMapEncodeTiled costs microseconds of host time each.
+struct TmapKey {
+  uint64_t w[12];
+};
+static std::unordered_map<std::string, CUtensorMap> g_tmaps;
+static std::mutex g_tmaps_mu;
+
 int make_tmap_bf16_sw128(CUtensorMap* out, const void* gptr, int rank, const uint64_t* dims,
                          const uint64_t* strides_bytes, const uint32_t* box) {
+  TmapKey key{};
+  key.w[0] = reinterpret_cast<uint64_t>(gptr);
+  key.w[1] = (uint64_t)rank;
+  for (int i = 0; i < rank; ++i) {
+    key.w[2 + i] = dims[i];
+    key.w[6 + i] = box[i];
+    if (i + 1 < rank) key.w[9 + i] = strides_bytes[i];
+  }
+  const std::string ks(reinterpret_cast<const char*>(&key), sizeof(key));
+  {
+    std::lock_guard<std::mutex> lk(g_tmaps_mu);
+    auto it = g_tmaps.find(ks);
+    if (it != g_tmaps.end()) {
+      *out = it->second;
+      return VB_OK;
+    }
+  }
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled driver entry point unavailable (no CUDA driver?)");
@@ -64,8 +92,16 @@ int make_tmap_bf16_sw128(CUtensorMap* out, const void* gptr, int rank, const uin
               (unsigned long long)(rank > 2 ? dims[2] : 0), box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, gptr);
     return VB_ERR_DRIVER;
   }
+  {
+    std::lock_guard<std::mutex> lk(g_tmaps_mu);
+    if (g_tmaps.size() > 65536) g_tmaps.clear();
+    g_tmaps.emplace(ks, *out);
+  }
   return VB_OK;
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int sm_count() {
   static int n = 0;
@@ -80,3 +116,4 @@ int sm_count() {
 }  // namespace vb
 
 extern "C" const char* var_b200_last_error(void) { return vb::get_error(); }
+extern "C" long long var_b200_launch_count(void) { return vb::g_launches.load(); }

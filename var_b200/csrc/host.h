@@ -15,6 +15,8 @@ int make_tmap_bf16_sw128(CUtensorMap* out, const void* gptr, int rank, const uin
                          const uint64_t* strides_bytes, const uint32_t* box);
 
 int sm_count();
+// number of kernels this library has launched in the process (bench.py's gpu_launches claim)
+void count_launch(int n = 1);
 
 #define VB_CUDA_CHECK(expr)                                                                  \
   do {                                                                                       \

@@ -108,5 +108,6 @@ extern "C" int var_b200_umma_probe(const void* A, const void* B, float* D, int N
   VB_CUDA_CHECK(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   umma_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(tmA, tmB, D, N, b_mn_major);
   VB_CUDA_CHECK(cudaGetLastError());
+  vb::count_launch();
   return VB_OK;
 }

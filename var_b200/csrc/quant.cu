@@ -348,6 +348,7 @@ int quant_launch(const QuantArgs& a, cudaStream_t st) {
   }
   quant_kernel<<<a.B, QT, smem, st>>>(p);
   VB_CUDA_CHECK(cudaGetLastError());
+  vb::count_launch();
   return VB_OK;
 }
 

@@ -183,7 +183,7 @@ int sample_launch(const SampleArgs& a, cudaStream_t st) {
   const size_t smem = (size_t)a.V * 4 + (use_p ? (size_t)vp2 * 8 : 0);
   VB_REQUIRE(smem <= 200 * 1024, "sample: V=%d too large for the shared-memory sampler", a.V);
   static size_t attr = 0;
-  if (smem > attr && smem > 48 * 1024) {
+  if (smem > attr && smem > 40 * 1024) {  // static smem (~1.2 KB) counts against the 48 KB default limit
     VB_CUDA_CHECK(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
@@ -191,6 +191,7 @@ int sample_launch(const SampleArgs& a, cudaStream_t st) {
   sample_kernel<<<a.B * a.l, ST, smem, st>>>(a.logits, a.B, a.l, a.V, a.use_cfg, opt, tf, a.q, a.top_k, a.top_p, (float)(1.0 - (double)a.top_p),
                                              reinterpret_cast<long long*>(a.idx_out), a.mixed_out, use_p ? vp2 : 0);
   VB_CUDA_CHECK(cudaGetLastError());
+  vb::count_launch();
   return VB_OK;
 }
 

@@ -76,6 +76,8 @@ def load() -> C.CDLL:
     lib = C.CDLL(str(_LIB_PATH))
     lib.var_b200_last_error.restype = C.c_char_p
     lib.var_b200_last_error.argtypes = []
+    lib.var_b200_launch_count.restype = C.c_longlong
+    lib.var_b200_launch_count.argtypes = []
     _declare(lib)
     _lib = lib
     return lib
