@@ -162,7 +162,7 @@ typedef struct var_b200_model {
   const float* ada_gss;  /* shared_aln only: [depth,6,C] (blocks.i.ada_gss), else NULL */
   const void* w_head;    /* bf16 [V,C] */
   const float* b_head;   /* [V] */
-  const float* w_word;   /* [C,Cvae] word_embed.weight */
+  const float* w_word;   /* [Cvae,C] word_embed.weight TRANSPOSED (coalesced per-channel loads) */
   const float* b_word;   /* [C] */
   const float* class_emb; /* [num_classes+1, C] */
   const float* pos_start; /* [first_l, C] */

@@ -123,6 +123,28 @@ def test_attention_block_causal(n_seq, H, si):
     assert torch.isfinite(out.float()).all() and err < 3e-2, f"max err {err}"
 
 
+def test_attention_reference_rebase_path():
+    """Rows whose later key tiles exceed the first tile's maximum by > 2^80 force the in-TMEM rescale of the
+    accumulator (only reachable with per-head scales > 27; the clamp allows up to 100, basic_var.py:101)."""
+    torch.manual_seed(11)
+    n_seq, H, Lq, Lmax = 2, 3, 680, 680
+    ends = list(np.cumsum([p * p for p in PATCH_NUMS]))
+    u = torch.nn.functional.normalize(torch.randn(n_seq, H, 1, 64, device=DEV), dim=-1)
+    q = torch.nn.functional.normalize(u + 0.05 * torch.randn(n_seq, H, Lq, 64, device=DEV), dim=-1) * 90.0
+    k = torch.nn.functional.normalize(u + 0.3 * torch.randn(n_seq, H, Lmax, 64, device=DEV), dim=-1)
+    k[:, :, :64] = torch.nn.functional.normalize(-u + 0.3 * torch.randn(n_seq, H, 64, 64, device=DEV), dim=-1)
+    v = torch.randn(n_seq, H, Lmax, 64, device=DEV)
+    qb, kb, vb = q.bfloat16(), k.bfloat16(), v.bfloat16()
+    out = torch.full((n_seq, Lq, H * 64), float("nan"), device=DEV, dtype=torch.bfloat16)
+    arr = (C.c_int * 10)(*[int(e) for e in ends])
+    L.check(L.load().var_b200_attention(qb.data_ptr(), kb.data_ptr(), vb.data_ptr(), out.data_ptr(), n_seq, H, Lq, Lmax,
+                                        0, 10, arr, L.current_stream()), "attention")
+    torch.cuda.synchronize()
+    ref = _attn_ref(qb, kb, vb, 0, ends)
+    assert torch.isfinite(out.float()).all()
+    assert (out.float() - ref).abs().max().item() < 5e-2
+
+
 def test_ln_modulate():
     torch.manual_seed(8)
     for C_ in (128, 1024, 1920):

@@ -9,10 +9,13 @@
 //
 // One CTA = 128 query rows of one (sequence, head). Warps 0-3: softmax (one row per thread == one TMEM lane),
 // warp 4: TMA producer + UMMA issuer (one elected thread).
-//   S = Q K^T   : UMMA 128x64x16 x4, Q and K tiles K-major SW128 in smem, S in TMEM columns [0,64)
-//   P = exp2(..) : registers -> bf16 -> smem (K-major SW128, A operand of the second MMA)
-//   O_j = P V   : UMMA 128x64x16 x4, V tile in its natural [key, d] layout = MN-major B operand, TMEM [64,128)
-//   running output is kept in registers and rescaled on-line (flash-attention recurrence).
+//   S_j = Q K_j^T : UMMA 128x64x16 x4, Q and K tiles K-major SW128 in smem, S double-buffered in TMEM [0,64),[64,128)
+//   P_j = exp2(..): registers -> bf16 -> smem (K-major SW128, A operand of the second MMA), double-buffered
+//   O  += P_j V_j : UMMA 128x64x16 x4, V tile in its natural [key, d] layout = MN-major B operand, TMEM [128,192)
+// The output accumulates in TMEM across key tiles against a per-row reference maximum fixed at the first tile
+// (q_hat.k_hat is bounded by the per-head scale <= 100, basic_var.py:101): softmax warps never wait for P V and the
+// tensor pipe runs QK_{j+1} under softmax_j. If a later tile exceeds the reference by more than 2^80 (only possible
+// for scales > 27) the accumulator is rescaled in TMEM (tcgen05.ld / st), which is exact like the usual recurrence.
 #include "attn.h"
 #include "common.cuh"
 #include "host.h"
@@ -23,10 +26,13 @@ constexpr int ATT_BM = 128;  // query rows per CTA
 constexpr int ATT_BN = 64;   // keys per tile
 constexpr int ATT_D = 64;    // head dim
 constexpr int ATT_THREADS = 160;
+constexpr int ATT_KST = 3;                        // K / V ring depth
 constexpr int ATT_Q_BYTES = ATT_BM * ATT_D * 2;   // 16 KB
 constexpr int ATT_KV_BYTES = ATT_BN * ATT_D * 2;  // 8 KB
 constexpr int ATT_P_BYTES = ATT_BM * ATT_BN * 2;  // 16 KB
-constexpr int ATT_SMEM = ATT_Q_BYTES + 4 * ATT_KV_BYTES + ATT_P_BYTES + 1024;
+constexpr int ATT_SMEM = ATT_Q_BYTES + 2 * ATT_KST * ATT_KV_BYTES + 2 * ATT_P_BYTES + 1024;
+constexpr int ATT_OSTG_LD = 144;  // bytes per staged output row (128 + 16 pad)
+constexpr float ATT_RESCALE_LOG2 = 80.f;
 
 struct AttnLevels {
   int n;
@@ -48,20 +54,22 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
             const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, int Lq, int H, int q_pos0,
             const AttnLevels lv) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t bars[8];  // 0:q 1,2:k[2] 3,4:v[2] 5:s 6:p 7:o
+  __shared__ uint64_t bars[1 + 2 * ATT_KST + 6];  // q | k[3] | v[3] | s[2] | p[2] | pv[2]
   __shared__ uint32_t tmem_base_smem;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = base;
   const uint32_t sK = sQ + ATT_Q_BYTES;
-  const uint32_t sV = sK + 2 * ATT_KV_BYTES;
-  const uint32_t sP = sV + 2 * ATT_KV_BYTES;
+  const uint32_t sV = sK + ATT_KST * ATT_KV_BYTES;
+  const uint32_t sP = sV + ATT_KST * ATT_KV_BYTES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q_tile = blockIdx.x, head = blockIdx.y, seq = blockIdx.z;
   const int bh = seq * H + head;
-  const uint32_t bar_q = smem_u32(&bars[0]), bar_s = smem_u32(&bars[5]), bar_p = smem_u32(&bars[6]),
-                 bar_o = smem_u32(&bars[7]);
+  const uint32_t bar_q = smem_u32(&bars[0]);
   auto bar_k = [&](int s) { return smem_u32(&bars[1 + s]); };
-  auto bar_v = [&](int s) { return smem_u32(&bars[3 + s]); };
+  auto bar_v = [&](int s) { return smem_u32(&bars[1 + ATT_KST + s]); };
+  auto bar_s = [&](int s) { return smem_u32(&bars[1 + 2 * ATT_KST + s]); };
+  auto bar_p = [&](int s) { return smem_u32(&bars[3 + 2 * ATT_KST + s]); };
+  auto bar_pv = [&](int s) { return smem_u32(&bars[5 + 2 * ATT_KST + s]); };
 
   // visible keys for the rows of this tile
   const int row0 = q_tile * ATT_BM;
@@ -78,17 +86,16 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
 
   if (threadIdx.x == 0) {
     mbar_init(bar_q, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(bar_k(s), 1); mbar_init(bar_v(s), 1); }
-    mbar_init(bar_s, 1);
-    mbar_init(bar_p, 128);
-    mbar_init(bar_o, 1);
+    for (int s = 0; s < ATT_KST; ++s) { mbar_init(bar_k(s), 1); mbar_init(bar_v(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(bar_s(s), 1); mbar_init(bar_p(s), 128); mbar_init(bar_pv(s), 1); }
     mbar_fence_init();
   }
-  if (warp == 4) tmem_alloc(smem_u32(&tmem_base_smem), 128);
+  if (warp == 4) tmem_alloc(smem_u32(&tmem_base_smem), 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_smem;
+  const uint32_t tmem_o = tmem + 128;
 
   if (warp == 4) {
     if (lane == 0) {
@@ -96,50 +103,51 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BM, ATT_D) | (1u << 16);  // B (V) is MN-major
       mbar_expect_tx(bar_q, ATT_Q_BYTES);
       tma_load_3d(&tmQ, bar_q, sQ, 0, row0, bh);
-      for (int j = 0; j < 2 && j < n_kt; ++j) {
+      for (int j = 0; j < ATT_KST && j < n_kt; ++j) {
         mbar_expect_tx(bar_k(j), ATT_KV_BYTES);
         tma_load_3d(&tmK, bar_k(j), sK + j * ATT_KV_BYTES, 0, j * ATT_BN, bh);
         mbar_expect_tx(bar_v(j), ATT_KV_BYTES);
         tma_load_3d(&tmV, bar_v(j), sV + j * ATT_KV_BYTES, 0, j * ATT_BN, bh);
       }
-      mbar_wait(bar_q, 0);
-      for (int j = 0; j < n_kt; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        // ---- S = Q K_j^T ----
-        mbar_wait(bar_k(st), ph);
+      const uint64_t qd = umma_desc_k_sw128(sQ);
+      auto issue_qk = [&](int j) {
+        const int st = j % ATT_KST;
+        mbar_wait(bar_k(st), (j / ATT_KST) & 1);
         tc_fence_after();
-        {
-          const uint64_t qd = umma_desc_k_sw128(sQ);
-          const uint64_t kd = umma_desc_k_sw128(sK + st * ATT_KV_BYTES);
+        const uint64_t kd = umma_desc_k_sw128(sK + st * ATT_KV_BYTES);
 #pragma unroll
-          for (int k = 0; k < ATT_D / 16; ++k) umma_bf16_ss(tmem, qd + 2 * k, kd + 2 * k, idesc_qk, k != 0);
-        }
-        umma_commit(bar_s);
-        // ---- O_j = P_j V_j ----
-        mbar_wait(bar_p, j & 1);  // softmax wrote P_j (and finished reading S_j, O_{j-1})
+        for (int k = 0; k < ATT_D / 16; ++k) umma_bf16_ss(tmem + (j & 1) * 64, qd + 2 * k, kd + 2 * k, idesc_qk, k != 0);
+        umma_commit(bar_s(j & 1));
+      };
+      mbar_wait(bar_q, 0);
+      issue_qk(0);
+      for (int j = 0; j < n_kt; ++j) {
+        // S[(j+1)&1] was last read by softmax_{j-1}, whose bar_p this thread has already observed.
+        if (j + 1 < n_kt) issue_qk(j + 1);
+        mbar_wait(bar_p(j & 1), (j >> 1) & 1);  // P_j written; QK_j therefore complete
         tc_fence_after();
-        // QK_j has completed (bar_s fired before bar_p could): K stage st is free -> prefetch K_{j+2}
-        if (j + 2 < n_kt) {
+        if (j + ATT_KST < n_kt) {  // K stage of tile j is free
+          const int st = j % ATT_KST;
           mbar_expect_tx(bar_k(st), ATT_KV_BYTES);
-          tma_load_3d(&tmK, bar_k(st), sK + st * ATT_KV_BYTES, 0, (j + 2) * ATT_BN, bh);
+          tma_load_3d(&tmK, bar_k(st), sK + st * ATT_KV_BYTES, 0, (j + ATT_KST) * ATT_BN, bh);
         }
-        mbar_wait(bar_v(st), ph);
-        tc_fence_after();
         {
-          const uint64_t pd = umma_desc_k_sw128(sP);
+          const int st = j % ATT_KST;
+          mbar_wait(bar_v(st), (j / ATT_KST) & 1);
+          tc_fence_after();
+          const uint64_t pd = umma_desc_k_sw128(sP + (j & 1) * ATT_P_BYTES);
 #pragma unroll
           for (int k = 0; k < ATT_BN / 16; ++k) {
             const uint64_t vd = umma_desc_mn_sw128_attn(sV + st * ATT_KV_BYTES + k * 2048);
-            umma_bf16_ss(tmem + 64, pd + 2 * k, vd, idesc_pv, k != 0);
+            umma_bf16_ss(tmem_o, pd + 2 * k, vd, idesc_pv, (j | k) != 0);
           }
+          umma_commit(bar_pv(j & 1));
         }
-        umma_commit(bar_o);
-        if (j + 2 < n_kt) {
-          // V stage st is reusable once PV_j has read it
-          mbar_wait(bar_o, j & 1);
+        if (j >= 1 && j - 1 + ATT_KST < n_kt) {  // V stage of tile j-1 is free once PV_{j-1} has completed
+          mbar_wait(bar_pv((j - 1) & 1), ((j - 1) >> 1) & 1);
+          const int st = (j - 1) % ATT_KST;
           mbar_expect_tx(bar_v(st), ATT_KV_BYTES);
-          tma_load_3d(&tmV, bar_v(st), sV + st * ATT_KV_BYTES, 0, (j + 2) * ATT_BN, bh);
+          tma_load_3d(&tmV, bar_v(st), sV + st * ATT_KV_BYTES, 0, (j - 1 + ATT_KST) * ATT_BN, bh);
         }
       }
     }
@@ -147,88 +155,105 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     // ------------------------------ softmax / output warps ------------------------------
     const int row = row0 + warp * 32 + lane;
     const int kv_end = kv_end_of(row);
-    const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
-    const uint32_t p_row = sP + (uint32_t)(warp * 32 + lane) * 128;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
     const int sw = lane & 7;  // == row & 7
     constexpr float LOG2E = 1.4426950408889634f;
-    float m_run = -INFINITY, l_run = 0.f;
-    float o_acc[ATT_D];
-#pragma unroll
-    for (int d = 0; d < ATT_D; ++d) o_acc[d] = 0.f;
+    float m_ref2 = 0.f;  // reference maximum, pre-multiplied by log2(e)
+    float l_run = 0.f;
 
     for (int j = 0; j < n_kt; ++j) {
       const int k0 = j * ATT_BN;
-      mbar_wait(bar_s, j & 1);
+      const int b = j & 1;
+      mbar_wait(bar_s(b), (j >> 1) & 1);
       tc_fence_after();
-      // pass A: row maximum over the visible keys of this tile
-      float m_tile = -INFINITY;
+      float s[64];
+      __syncwarp();
+      tmem_ld_32x32(tmem + lane_off + b * 64, s);
+      tmem_ld_32x32(tmem + lane_off + b * 64 + 32, s + 32);
+      tmem_ld_wait();
+      const bool partial = k0 + ATT_BN > kv_end;  // this row does not see the whole tile
+      if (partial) {
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        float s[32];
-        __syncwarp();
-        tmem_ld_32x32(t_lane + c * 32, s);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float v = (k0 + c * 32 + i < kv_end) ? s[i] : -INFINITY;
-          m_tile = fmaxf(m_tile, v);
-        }
+        for (int i = 0; i < 64; ++i) s[i] = (k0 + i < kv_end) ? s[i] : -INFINITY;
       }
-      const float m_new = fmaxf(m_run, m_tile);  // finite from the first tile on (key 0 is always visible)
-      const float alpha = exp2f((m_run - m_new) * LOG2E);
-      const float mneg = -m_new * LOG2E;
+      float mx = s[0];
+#pragma unroll
+      for (int i = 1; i < 64; ++i) mx = fmaxf(mx, s[i]);
+      const float mx2 = mx * LOG2E;
+      if (j == 0) {
+        m_ref2 = mx2;  // finite: key 0 is visible to every query
+      } else if (__any_sync(0xffffffffu, mx2 - m_ref2 > ATT_RESCALE_LOG2)) {
+        // rare: rebase the accumulator of the rows that overflowed the reference
+        const bool need = mx2 - m_ref2 > ATT_RESCALE_LOG2;
+        const float f = need ? exp2f(m_ref2 - mx2) : 1.f;
+        mbar_wait(bar_pv((j - 1) & 1), ((j - 1) >> 1) & 1);  // every earlier P V has landed in TMEM
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          float o[32];
+          __syncwarp();
+          tmem_ld_32x32(tmem_o + lane_off + c * 32, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] *= f;
+          tmem_st_32x32(tmem_o + lane_off + c * 32, o);
+        }
+        tmem_st_wait();
+        l_run *= f;
+        if (need) m_ref2 = mx2;
+      }
       float l_tile = 0.f;
-      // pass B: probabilities -> bf16 -> swizzled smem (A operand of P V)
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        float s[32];
-        __syncwarp();
-        tmem_ld_32x32(t_lane + c * 32, s);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float p = (k0 + c * 32 + i < kv_end) ? exp2f(fmaf(s[i], LOG2E, mneg)) : 0.f;
-          l_tile += p;
-          s[i] = p;
-        }
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {  // 16-byte chunk (8 keys) index c*4+g, XOR-swizzled with row%8
-          const uint32_t addr = p_row + (uint32_t)(((c * 4 + g) ^ sw) << 4);
-          const uint32_t w0 = pack_bf16x2(s[8 * g + 0], s[8 * g + 1]), w1 = pack_bf16x2(s[8 * g + 2], s[8 * g + 3]);
-          const uint32_t w2 = pack_bf16x2(s[8 * g + 4], s[8 * g + 5]), w3 = pack_bf16x2(s[8 * g + 6], s[8 * g + 7]);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3)
-                       : "memory");
-        }
+      for (int i = 0; i < 64; ++i) {
+        s[i] = fast_exp2(fmaf(s[i], LOG2E, -m_ref2));  // masked entries: exp2(-inf) = 0
+        l_tile += s[i];
       }
-      l_run = l_run * alpha + l_tile;
-      m_run = m_new;
+      l_run += l_tile;
+      if (j >= 2) mbar_wait(bar_pv(b), ((j - 2) >> 1) & 1);  // P buffer b was read by PV_{j-2}
+      const uint32_t p_row = sP + b * ATT_P_BYTES + (uint32_t)(warp * 32 + lane) * 128;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {  // 16-byte chunk (8 keys), XOR-swizzled with row%8 (SWIZZLE_128B)
+        const uint32_t addr = p_row + (uint32_t)((g ^ sw) << 4);
+        const uint32_t w0 = pack_bf16x2(s[8 * g + 0], s[8 * g + 1]), w1 = pack_bf16x2(s[8 * g + 2], s[8 * g + 3]);
+        const uint32_t w2 = pack_bf16x2(s[8 * g + 4], s[8 * g + 5]), w3 = pack_bf16x2(s[8 * g + 6], s[8 * g + 7]);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3)
+                     : "memory");
+      }
       tc_fence_before();
       fence_proxy_async_smem();
-      mbar_arrive(bar_p);
-      // fold O_j into the running output
-      mbar_wait(bar_o, j & 1);
-      tc_fence_after();
+      mbar_arrive(bar_p(b));
+    }
+    // ---- epilogue: O / l -> bf16, staged through smem (P buffers are free) for coalesced 128-byte rows ----
+    mbar_wait(bar_pv((n_kt - 1) & 1), ((n_kt - 1) >> 1) & 1);
+    tc_fence_after();
+    const float inv = 1.f / l_run;
+    uint8_t* stg = smem_raw + (sP - smem_u32(smem_raw)) + warp * (32 * ATT_OSTG_LD);
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        float o[32];
-        __syncwarp();
-        tmem_ld_32x32(t_lane + 64 + c * 32, o);
-        tmem_ld_wait();
+    for (int c = 0; c < 2; ++c) {
+      float o[32];
+      __syncwarp();
+      tmem_ld_32x32(tmem_o + lane_off + c * 32, o);
+      tmem_ld_wait();
+      uint4* d4 = reinterpret_cast<uint4*>(stg + lane * ATT_OSTG_LD + c * 64);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha, o[i]);
+      for (int g = 0; g < 4; ++g) {
+        uint4 w;
+        w.x = pack_bf16x2(o[8 * g + 0] * inv, o[8 * g + 1] * inv);
+        w.y = pack_bf16x2(o[8 * g + 2] * inv, o[8 * g + 3] * inv);
+        w.z = pack_bf16x2(o[8 * g + 4] * inv, o[8 * g + 5] * inv);
+        w.w = pack_bf16x2(o[8 * g + 6] * inv, o[8 * g + 7] * inv);
+        d4[g] = w;
       }
     }
-    if (row < Lq) {
-      const float inv = 1.f / l_run;
-      uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)seq * Lq + row) * (size_t)(H * ATT_D) + head * ATT_D);
+    __syncwarp();
+    const int rsub = lane >> 3, ch = lane & 7;
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        uint4 w;
-        w.x = pack_bf16x2(o_acc[8 * g + 0] * inv, o_acc[8 * g + 1] * inv);
-        w.y = pack_bf16x2(o_acc[8 * g + 2] * inv, o_acc[8 * g + 3] * inv);
-        w.z = pack_bf16x2(o_acc[8 * g + 4] * inv, o_acc[8 * g + 5] * inv);
-        w.w = pack_bf16x2(o_acc[8 * g + 6] * inv, o_acc[8 * g + 7] * inv);
-        dst[g] = w;
+    for (int i = 0; i < 8; ++i) {
+      const int r = rsub + 4 * i;
+      const int rg = row0 + warp * 32 + r;
+      if (rg < Lq) {
+        uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)seq * Lq + rg) * (size_t)(H * ATT_D) + head * ATT_D);
+        dst[ch] = *reinterpret_cast<const uint4*>(stg + r * ATT_OSTG_LD + ch * 16);
       }
     }
   }
@@ -236,7 +261,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   __syncthreads();
   if (warp == 4) {
     tc_fence_after();
-    tmem_dealloc(tmem, 128);
+    tmem_dealloc(tmem, 256);
   }
 }
 

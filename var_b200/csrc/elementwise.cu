@@ -11,51 +11,68 @@ namespace vb {
 // LN(x) * (1 + scale[seq]) + shift[seq] -> bf16        (basic_var.py:157-158,174; LayerNorm without affine)
 // one warp per row; the row lives in registers between the statistics and the normalisation pass
 // ------------------------------------------------------------------------------------------------
-constexpr int LN_MAXV = 20;  // float4 per lane: supports C <= 2560
+constexpr int LN_MAXV = 20;   // float4 per lane: supports C <= 2560
+constexpr int LN_ROWS = 32;   // rows of one sequence per CTA (8 warps x 4 rows)
 
+// A CTA owns LN_ROWS consecutive rows of ONE sequence, so (1+scale) and shift are staged in shared memory once and
+// the only global traffic per row is the 4C-byte read and the 2C-byte write (the first version re-read 8C bytes of
+// adaLN parameters per row through L2 and ran at 2.3 TB/s).
 __global__ void __launch_bounds__(256)
 ln_modulate_kernel(const float* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
-                   int ada_ld, int rows_per_seq, __nv_bfloat16* __restrict__ out, int M, int C, float eps) {
+                   int ada_ld, int rows_per_seq, __nv_bfloat16* __restrict__ out, int C, float eps) {
+  extern __shared__ float4 ln_sm[];  // [C/4] (1+scale), [C/4] shift
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (row >= M) return;
+  const int seq = blockIdx.y;
   const int nvec = C >> 2;
-  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * C);
-  float4 v[LN_MAXV];
-  float sum = 0.f;
-#pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
-    const int idx = lane + 32 * i;
-    if (idx < nvec) {
-      v[i] = xr[idx];
-      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  float4* s1 = ln_sm;
+  float4* sh = ln_sm + nvec;
+  {
+    const float4* sc = reinterpret_cast<const float4*>(scale + (size_t)seq * ada_ld);
+    const float4* sf = reinterpret_cast<const float4*>(shift + (size_t)seq * ada_ld);
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+      float4 a = __ldg(sc + i);
+      s1[i] = make_float4(1.f + a.x, 1.f + a.y, 1.f + a.z, 1.f + a.w);
+      sh[i] = __ldg(sf + i);
     }
   }
-  const float mean = warp_sum(sum) / (float)C;
-  float sq = 0.f;
+  __syncthreads();
+  const int t_end = min(rows_per_seq, (int)(blockIdx.x + 1) * LN_ROWS);
+  for (int t = blockIdx.x * LN_ROWS + warp; t < t_end; t += 8) {
+    const size_t row = (size_t)seq * rows_per_seq + t;
+    const float4* xr = reinterpret_cast<const float4*>(x + row * C);
+    float4 v[LN_MAXV];
+    float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
-    const int idx = lane + 32 * i;
-    if (idx < nvec) {
-      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-      sq += (a * a + b * b) + (c * c + d * d);
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nvec) {
+        v[i] = xr[idx];
+        sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      }
     }
-  }
-  const float rstd = 1.f / sqrtf(warp_sum(sq) / (float)C + eps);
-  const int seq = row / rows_per_seq;
-  const float4* sc = reinterpret_cast<const float4*>(scale + (size_t)seq * ada_ld);
-  const float4* sh = reinterpret_cast<const float4*>(shift + (size_t)seq * ada_ld);
-  uint2* o = reinterpret_cast<uint2*>(out + (size_t)row * C);
+    const float mean = warp_sum(sum) / (float)C;
+    float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
-    const int idx = lane + 32 * i;
-    if (idx < nvec) {
-      const float4 s = __ldg(sc + idx), h = __ldg(sh + idx);
-      const float a = (v[i].x - mean) * rstd * (1.f + s.x) + h.x;
-      const float b = (v[i].y - mean) * rstd * (1.f + s.y) + h.y;
-      const float c = (v[i].z - mean) * rstd * (1.f + s.z) + h.z;
-      const float d = (v[i].w - mean) * rstd * (1.f + s.w) + h.w;
-      o[idx] = make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d));
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nvec) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        sq += (a * a + b * b) + (c * c + d * d);
+      }
+    }
+    const float rstd = 1.f / sqrtf(warp_sum(sq) / (float)C + eps);
+    uint2* o = reinterpret_cast<uint2*>(out + row * C);
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nvec) {
+        const float4 s = s1[idx], h = sh[idx];
+        const float a = (v[i].x - mean) * rstd * s.x + h.x;
+        const float b = (v[i].y - mean) * rstd * s.y + h.y;
+        const float c = (v[i].z - mean) * rstd * s.z + h.z;
+        const float d = (v[i].w - mean) * rstd * s.w + h.w;
+        o[idx] = make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d));
+      }
     }
   }
 }
@@ -64,10 +81,11 @@ int ln_modulate(const float* x, const float* scale, const float* shift, int ada_
                 int C, float eps, cudaStream_t st) {
   VB_REQUIRE(x && scale && shift && out, "ln_modulate: null pointer");
   VB_REQUIRE(C % 4 == 0 && C <= LN_MAXV * 128, "ln_modulate: C=%d unsupported", C);
-  VB_REQUIRE(M > 0 && rows_per_seq > 0, "ln_modulate: bad M=%d rows_per_seq=%d", M, rows_per_seq);
-  const int wpb = 8;
-  ln_modulate_kernel<<<(M + wpb - 1) / wpb, wpb * 32, 0, st>>>(x, scale, shift, ada_ld, rows_per_seq,
-                                                               reinterpret_cast<__nv_bfloat16*>(out), M, C, eps);
+  VB_REQUIRE(M > 0 && rows_per_seq > 0 && M % rows_per_seq == 0, "ln_modulate: bad M=%d rows_per_seq=%d", M, rows_per_seq);
+  VB_REQUIRE(ada_ld % 4 == 0 && M / rows_per_seq <= 65535, "ln_modulate: bad ada_ld=%d or too many sequences", ada_ld);
+  dim3 grid((rows_per_seq + LN_ROWS - 1) / LN_ROWS, M / rows_per_seq);
+  ln_modulate_kernel<<<grid, 256, (size_t)C * 8, st>>>(x, scale, shift, ada_ld, rows_per_seq,
+                                                       reinterpret_cast<__nv_bfloat16*>(out), C, eps);
   VB_CUDA_CHECK(cudaGetLastError());
   vb::count_launch();
   return VB_OK;
@@ -115,40 +133,59 @@ int expand_shared_aln(const float* shared, int shared_ld, const float* gss, floa
 //   row t <  first_rows : class_emb[label] + pos_start[t] + lvl_pos[pos0 + t]
 //   row t >= first_rows : word_embed(x_in[seq % n_x, t - first_rows, :]) + lvl_pos[pos0 + t]
 // ------------------------------------------------------------------------------------------------
+constexpr int EMB_ROWS = 32;  // rows per CTA
+
+// CTA = 256 channels x EMB_ROWS rows. Each thread keeps its channel's 32 word_embed weights in registers (w_word is
+// stored transposed [Cvae, C] so the load is coalesced) and walks the rows; x_in rows are staged in shared memory.
 __global__ void __launch_bounds__(256)
 embed_kernel(const float* __restrict__ x_in, int n_x, int l_in, const int* __restrict__ labels,
              const float* __restrict__ class_emb, const float* __restrict__ pos_start,
-             const float* __restrict__ lvl_pos, const float* __restrict__ w_word, const float* __restrict__ b_word,
-             float* __restrict__ out, int l, int first_rows, int pos0, int C, int Cv) {
-  __shared__ float xin[64];
-  const int t = blockIdx.x, s = blockIdx.y;
-  float* o = out + ((size_t)s * l + t) * C;
-  const float* lp = lvl_pos + (size_t)(pos0 + t) * C;
-  if (t < first_rows) {
-    const float* e = class_emb + (size_t)__ldg(labels + s) * C;
-    const float* ps = pos_start + (size_t)t * C;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) o[c] = (e[c] + ps[c]) + lp[c];
-    return;
+             const float* __restrict__ lvl_pos, const float* __restrict__ w_word_t, const float* __restrict__ b_word,
+             float* __restrict__ out, int n_rows, int l, int first_rows, int pos0, int C) {
+  __shared__ float xin[EMB_ROWS][32];
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  const int r0 = blockIdx.y * EMB_ROWS;
+  const int nr = min(EMB_ROWS, n_rows - r0);
+  for (int i = threadIdx.x; i < nr * 32; i += 256) {
+    const int r = r0 + (i >> 5), k = i & 31;
+    const int s = r / l, t = r - s * l;
+    xin[i >> 5][k] = (t >= first_rows) ? x_in[((size_t)(s % n_x) * l_in + (t - first_rows)) * 32 + k] : 0.f;
   }
-  const float* xi = x_in + ((size_t)(s % n_x) * l_in + (t - first_rows)) * Cv;
-  if (threadIdx.x < Cv) xin[threadIdx.x] = xi[threadIdx.x];
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float* w = w_word + (size_t)c * Cv;
-    float acc = 0.f;
-    for (int k = 0; k < Cv; ++k) acc = fmaf(xin[k], __ldg(w + k), acc);
-    o[c] = (acc + b_word[c]) + lp[c];
+  if (c >= C) return;
+  float w[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) w[k] = __ldg(w_word_t + (size_t)k * C + c);
+  const float bw = __ldg(b_word + c);
+  for (int i = 0; i < nr; ++i) {
+    const int r = r0 + i;
+    const int s = r / l, t = r - s * l;
+    const float lp = __ldg(lvl_pos + (size_t)(pos0 + t) * C + c);
+    float v;
+    if (t < first_rows) {
+      v = (__ldg(class_emb + (size_t)__ldg(labels + s) * C + c) + __ldg(pos_start + (size_t)t * C + c)) + lp;
+    } else {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 32; ++k) acc = fmaf(xin[i][k], w[k], acc);
+      v = (acc + bw) + lp;
+    }
+    out[(size_t)r * C + c] = v;
   }
 }
 
 int embed_tokens(const float* x_in, int n_x, int l_in, const int* labels, const float* class_emb,
-                 const float* pos_start, const float* lvl_pos, const float* w_word, const float* b_word, float* out,
+                 const float* pos_start, const float* lvl_pos, const float* w_word_t, const float* b_word, float* out,
                  int n_seq, int l, int first_rows, int pos0, int C, int Cv, cudaStream_t st) {
-  VB_REQUIRE(out && labels && class_emb && pos_start && lvl_pos && w_word && b_word, "embed: null pointer");
-  VB_REQUIRE(Cv <= 64 && n_seq > 0 && l > 0 && n_seq <= 65535, "embed: bad shape Cv=%d n_seq=%d l=%d", Cv, n_seq, l);
+  VB_REQUIRE(out && labels && class_emb && pos_start && lvl_pos && w_word_t && b_word, "embed: null pointer");
+  VB_REQUIRE(Cv == 32, "embed: Cvae=%d unsupported (kernel is specialised for 32)", Cv);
+  VB_REQUIRE(n_seq > 0 && l > 0, "embed: bad shape n_seq=%d l=%d", n_seq, l);
   VB_REQUIRE(first_rows >= l || (x_in && n_x > 0), "embed: x_in required");
-  embed_kernel<<<dim3(l, n_seq), 256, 0, st>>>(x_in, n_x > 0 ? n_x : 1, l_in, labels, class_emb, pos_start, lvl_pos,
-                                               w_word, b_word, out, l, first_rows, pos0, C, Cv);
+  const int n_rows = n_seq * l;
+  dim3 grid((C + 255) / 256, (n_rows + EMB_ROWS - 1) / EMB_ROWS);
+  VB_REQUIRE(grid.y <= 65535, "embed: too many rows (%d)", n_rows);
+  embed_kernel<<<grid, 256, 0, st>>>(x_in, n_x > 0 ? n_x : 1, l_in, labels, class_emb, pos_start, lvl_pos, w_word_t, b_word,
+                                     out, n_rows, l, first_rows, pos0, C);
   VB_CUDA_CHECK(cudaGetLastError());
   vb::count_launch();
   return VB_OK;

@@ -19,7 +19,7 @@ int cond_silu(const float* class_emb, const int* labels, void* out, int n_seq, i
 int expand_shared_aln(const float* shared, int shared_ld, const float* gss, float* ada, int ada_ld, int depth, int C,
                       int n_seq, cudaStream_t st);
 int embed_tokens(const float* x_in, int n_x, int l_in, const int* labels, const float* class_emb,
-                 const float* pos_start, const float* lvl_pos, const float* w_word, const float* b_word, float* out,
+                 const float* pos_start, const float* lvl_pos, const float* w_word_t, const float* b_word, float* out,
                  int n_seq, int l, int first_rows, int pos0, int C, int Cv, cudaStream_t st);
 int score_finalize(const void* part, int n_tiles, const float* gt_logit, int n_seq, int L, int n_scales,
                    const int* level_end, float* tok_logp, float* per_scale, float* total, int first_pos,

@@ -312,7 +312,7 @@ class PackedModel:
             b_ada = torch.cat([b.ada_lin[1].bias for b in var.blocks] + [var.head_nm.ada_lin[1].bias])
             gss = None
         t = dict(w_ada=bf(w_ada), b_ada=f32(b_ada), w_head=bf(var.head.weight), b_head=f32(var.head.bias),
-                 w_word=f32(var.word_embed.weight), b_word=f32(var.word_embed.bias), class_emb=f32(var.class_emb.weight),
+                 w_word=f32(var.word_embed.weight.t()), b_word=f32(var.word_embed.bias), class_emb=f32(var.class_emb.weight),
                  pos_start=f32(var.pos_start.reshape(var.first_l, C_)),
                  lvl_pos=f32(var.lvl_embed.weight[var.lvl_1L.reshape(-1)] + var.pos_1LC.reshape(var.L, C_)))
         m = L.ModelDesc()
