@@ -73,7 +73,7 @@ typedef struct var_b200_gemm_args {
   /* SCORE */
   const int32_t* gt; /* row m uses gt[m % gt_mod] */
   int gt_mod;        /* 0 = M */
-  float* part;       /* [M, ceil(N / var_b200_gemm_tile_n(N)), 2] (max, sumexp) */
+  float* part;       /* [M, 2*ceil(N / var_b200_gemm_tile_n(N)), 2]: (max, sumexp) per row, tile and epilogue half */
   float* gt_logit;   /* [M] */
 } var_b200_gemm_args_t;
 

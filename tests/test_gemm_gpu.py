@@ -90,7 +90,7 @@ def test_gemm_gate_resid_inplace():
 
 def test_gemm_qkv_scatter():
     torch.manual_seed(3)
-    n_seq, l, H, Lmax, pos0 = 4, 36, 16, 91, 55
+    n_seq, l, H, Lmax, pos0 = 4, 36, 16, 100, 55
     Cdim = H * 64
     M = n_seq * l
     A = (torch.randn(M, Cdim, device="cuda") / math.sqrt(Cdim)).bfloat16()
@@ -122,7 +122,7 @@ def test_gemm_score_partials():
     gt = torch.randint(0, N, (M,), device="cuda", dtype=torch.int32)
     bn = L.load().var_b200_gemm_tile_n(N)
     nt = (N + bn - 1) // bn
-    part = torch.zeros(M, nt, 2, device="cuda")
+    part = torch.zeros(M, 2 * nt, 2, device="cuda")
     gl = torch.zeros(M, device="cuda")
     _gemm(A, W, L.EPI_SCORE, bias=bias, gt=gt, part=part, gt_logit=gl)
     logits = _ref(A, W) + bias

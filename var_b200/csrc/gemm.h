@@ -32,7 +32,7 @@ struct GemmParams {
   // EPI_SCORE
   const int* gt;    // ground-truth token of row m = gt[m % gt_mod]
   int gt_mod;
-  float2* part;     // [M, n_tiles] (max, sum exp(x - max)) over the tile's columns
+  float2* part;     // [M, 2*n_tiles] (max, sum exp(x - max)) per row, tile and epilogue half
   float* gt_logit;  // [M]
 };
 

@@ -14,8 +14,8 @@ namespace vb {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 192;  // warp0: TMA, warp1: MMA + TMEM owner, warps 2-5: epilogue
-constexpr int EPI_STG_LD = 36;      // floats per staging row (32 + 4 pad: 16-byte aligned, bank-spread)
+constexpr int GEMM_THREADS = 320;  // warp0: TMA, warp1: MMA + TMEM owner, warps 2-9: epilogue
+constexpr int EPI_STG_LD = 20;      // floats per staging row (16 + 4 pad: 16-byte aligned)
 
 template <int BN>
 struct GemmCfg {
@@ -23,7 +23,7 @@ struct GemmCfg {
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 192 ? 5 : 6);
-  static constexpr int STG_BYTES = 4 * 32 * EPI_STG_LD * 4;       // epilogue staging, one 32x36 fp32 tile per warp
+  static constexpr int STG_BYTES = 8 * 32 * EPI_STG_LD * 4;       // epilogue staging, one 32x20 fp32 tile per warp
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024;  // +1024: manual alignment slack
 };
 
@@ -59,7 +59,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+      mbar_init(tempty_bar(s), 8);  // one arrive per epilogue warp
     }
     mbar_fence_init();
   }
@@ -118,7 +118,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // ------------------------------ epilogue warps ------------------------------
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    // Eight warps: two per TMEM lane quarter, interleaving the column chunks of the tile between them, so that the
+    // epilogue (which is ALU/latency bound: one accumulator row per thread) keeps up with the 8192-cycle main loop
+    // of a K=1024 tile.
+    const int quarter = warp & 3;          // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;      // which interleaved half of the column chunks
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
@@ -131,20 +135,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t taddr = tmem_base + as * 256 + ((uint32_t)(quarter * 32) << 16);
       const int n_base = n_blk * BN;
 
-      // Staging tile private to this warp: accumulator rows (one per thread, as TMEM delivers them) are transposed
-      // through shared memory so that every global access below is a run of full 128-byte lines
-      // (4 rows x 128 B per warp instruction) instead of 32 scattered 16-byte pieces.
-      float* stg = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + STAGES * Cfg::STAGE_BYTES) +
-                   quarter * (32 * EPI_STG_LD);
-      const int rsub = lane >> 3, cg = lane & 7;
-      const int row_w0 = m_blk * GEMM_BM + quarter * 32;  // first row of this warp
-
       if constexpr (EPI == EPI_QKV) {
         const int seq = row / p.rows_per_seq;
         const int t = row - seq * p.rows_per_seq;
-        (void)t;
 #pragma unroll 1
-        for (int c = 0; c < BN / 64; ++c) {
+        for (int c = half; c < BN / 64; c += 2) {
           const int n0 = n_base + c * 64;
           if (n0 >= p.N) break;
           float v[64];
@@ -165,29 +160,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mul = 1.f / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize(dim=-1), eps 1e-12
             if (which == 0) mul *= __ldg(p.q_scale + head);
           }
-          uint4* srow = reinterpret_cast<uint4*>(stg + lane * EPI_STG_LD);
+          if (row_ok) {
+            __nv_bfloat16* dst;
+            if (which == 0)
+              dst = p.q_out + (((size_t)seq * p.H + head) * p.rows_per_seq + t) * 64;
+            else
+              dst = (which == 1 ? p.k_cache : p.v_cache) + (((size_t)seq * p.H + head) * p.Lmax + p.pos0 + t) * 64;
+            uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            uint4 o;
-            o.x = pack_bf16x2(v[8 * j + 0] * mul, v[8 * j + 1] * mul);
-            o.y = pack_bf16x2(v[8 * j + 2] * mul, v[8 * j + 3] * mul);
-            o.z = pack_bf16x2(v[8 * j + 4] * mul, v[8 * j + 5] * mul);
-            o.w = pack_bf16x2(v[8 * j + 6] * mul, v[8 * j + 7] * mul);
-            srow[j] = o;
-          }
-          __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = rsub + 4 * i;
-            const int rg = row_w0 + r;
-            if (rg < p.M) {
-              const int sq = rg / p.rows_per_seq, tt = rg - sq * p.rows_per_seq;
-              __nv_bfloat16* dst;
-              if (which == 0)
-                dst = p.q_out + (((size_t)sq * p.H + head) * p.rows_per_seq + tt) * 64;
-              else
-                dst = (which == 1 ? p.k_cache : p.v_cache) + (((size_t)sq * p.H + head) * p.Lmax + p.pos0 + tt) * 64;
-              reinterpret_cast<uint4*>(dst)[cg] = reinterpret_cast<const uint4*>(stg + r * EPI_STG_LD)[cg];
+            for (int j = 0; j < 8; ++j) {
+              uint4 o;
+              o.x = pack_bf16x2(v[8 * j + 0] * mul, v[8 * j + 1] * mul);
+              o.y = pack_bf16x2(v[8 * j + 2] * mul, v[8 * j + 3] * mul);
+              o.z = pack_bf16x2(v[8 * j + 4] * mul, v[8 * j + 5] * mul);
+              o.w = pack_bf16x2(v[8 * j + 6] * mul, v[8 * j + 7] * mul);
+              d4[j] = o;
             }
           }
         }
@@ -195,7 +182,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         float run_max = -INFINITY, run_sum = 0.f;
         const int gt = row_ok ? __ldg(p.gt + (row % p.gt_mod)) : -1;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = half; c < BN / 32; c += 2) {
           const int n0 = n_base + c * 32;
           if (n0 >= p.N) break;
           float v[32];
@@ -215,55 +202,100 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             p.gt_logit[row] = g;
           }
           const float new_max = fmaxf(run_max, cmax);
-          float s = 0.f;
+          float sacc = 0.f;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) s += __expf(v[j] - new_max);
-          run_sum = run_sum * __expf(run_max - new_max) + s;
+          for (int j = 0; j < 32; ++j) sacc += __expf(v[j] - new_max);
+          run_sum = run_sum * __expf(run_max - new_max) + sacc;
           run_max = new_max;
         }
-        if (row_ok) p.part[(size_t)row * n_tiles + n_blk] = make_float2(run_max, run_sum);
-      } else {
-        int seqs[8];
-        if constexpr (EPI == EPI_GATE_RESID) {
+        // one partial per (row, tile, half); an empty half contributes (-inf, 0)
+        if (row_ok) p.part[((size_t)row * n_tiles + n_blk) * 2 + half] = make_float2(run_max, run_sum);
+      } else if constexpr (EPI == EPI_GATE_RESID) {
+        // Residual update needs coalesced reads of resid/gate: transpose 32x16 accumulator pieces through a private
+        // smem tile so that each warp instruction touches 8 rows x 64 contiguous bytes.
+        float* stg = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + STAGES * Cfg::STAGE_BYTES) +
+                     (warp - 2) * (32 * EPI_STG_LD);
+        const int rsub = lane >> 2, cg = lane & 3;
+        const int row_w0 = m_blk * GEMM_BM + quarter * 32;
+        int seqs[4];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) seqs[i] = (row_w0 + rsub + 4 * i) / p.rows_per_seq;
-        }
+        for (int i = 0; i < 4; ++i) seqs[i] = (row_w0 + rsub + 8 * i) / p.rows_per_seq;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = half; c < BN / 32; c += 2) {
           const int n0 = n_base + c * 32;
           if (n0 >= p.N) break;
           float v[32];
           __syncwarp();
           tmem_ld_32x32(taddr + c * 32, v);
           tmem_ld_wait();
-          float4* srow = reinterpret_cast<float4*>(stg + lane * EPI_STG_LD);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) srow[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          __syncwarp();
-          const int col = n0 + 4 * cg;
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+          for (int h2 = 0; h2 < 2; ++h2) {
+            float4* srow = reinterpret_cast<float4*>(stg + lane * EPI_STG_LD);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = rsub + 4 * i;
-            const int rg = row_w0 + r;
-            if (rg >= p.M) continue;  // no warp-collective op inside this loop
-            float4 a = *reinterpret_cast<const float4*>(stg + r * EPI_STG_LD + 4 * cg);
-            a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
-            const size_t off = (size_t)rg * p.N + col;
-            if constexpr (EPI == EPI_BIAS_F32) {
-              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) = a;
-            } else if constexpr (EPI == EPI_GATE_RESID) {
-              const float4 g = __ldg(reinterpret_cast<const float4*>(p.gate + (size_t)seqs[i] * p.gate_ld + col));
-              const float4 rs = *reinterpret_cast<const float4*>(p.resid + off);
-              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) =
-                  make_float4(fmaf(a.x, g.x, rs.x), fmaf(a.y, g.y, rs.y), fmaf(a.z, g.z, rs.z), fmaf(a.w, g.w, rs.w));
-            } else {  // EPI_BIAS_BF16 / EPI_GELU_BF16
-              if constexpr (EPI == EPI_GELU_BF16) {
-                a.x = gelu_tanh(a.x); a.y = gelu_tanh(a.y); a.z = gelu_tanh(a.z); a.w = gelu_tanh(a.w);
+            for (int j = 0; j < 4; ++j)
+              srow[j] = make_float4(v[16 * h2 + 4 * j], v[16 * h2 + 4 * j + 1], v[16 * h2 + 4 * j + 2], v[16 * h2 + 4 * j + 3]);
+            __syncwarp();
+            const int col = n0 + 16 * h2 + 4 * cg;
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+            float4 rs[4], g4[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {  // all loads first: resid may alias out, so the compiler cannot hoist them
+              const int rg = row_w0 + rsub + 8 * i;
+              if (rg < p.M) {
+                rs[i] = *reinterpret_cast<const float4*>(p.resid + (size_t)rg * p.N + col);
+                g4[i] = __ldg(reinterpret_cast<const float4*>(p.gate + (size_t)seqs[i] * p.gate_ld + col));
               }
-              *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off) =
-                  make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = rsub + 8 * i;
+              const int rg = row_w0 + r;
+              if (rg < p.M) {
+                const float4 a = *reinterpret_cast<const float4*>(stg + r * EPI_STG_LD + 4 * cg);
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)rg * p.N + col) =
+                    make_float4(fmaf(a.x + b4.x, g4[i].x, rs[i].x), fmaf(a.y + b4.y, g4[i].y, rs[i].y),
+                                fmaf(a.z + b4.z, g4[i].z, rs[i].z), fmaf(a.w + b4.w, g4[i].w, rs[i].w));
+              }
+            }
+            __syncwarp();
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int c = half; c < BN / 32; c += 2) {
+          const int n0 = n_base + c * 32;
+          if (n0 >= p.N) break;
+          float v[32];
+          __syncwarp();
+          tmem_ld_32x32(taddr + c * 32, v);
+          tmem_ld_wait();
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+            }
+          }
+          if (!row_ok) {
+            // nothing to store for rows beyond M (the TMEM load above stays warp-convergent)
+          } else if constexpr (EPI == EPI_BIAS_F32) {
+            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)row * p.N + n0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {  // EPI_BIAS_BF16 / EPI_GELU_BF16
+            if constexpr (EPI == EPI_GELU_BF16) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
+            }
+            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.N + n0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 w;
+              w.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+              w.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+              w.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+              w.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+              o[j] = w;
             }
           }
         }
