@@ -56,7 +56,7 @@ typedef struct var_b200_gemm_args {
   const void* W; /* [N,K] bf16 row-major (nn.Linear weight) */
   int M, N, K;
   int epilogue;      /* VAR_B200_EPI_* */
-  int force_bn;      /* 0 = auto tile width, else 128 / 192 / 256 */
+  int force_bn;      /* 0 = auto tile width, else 128 / 192 / 256; | 0x10000 forces the 1-CTA kernel */
   const float* bias; /* [N] or NULL (required for QKV / SCORE) */
   void* out;         /* [M,N] fp32 or bf16 */
   /* GATE_RESID */

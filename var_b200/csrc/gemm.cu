@@ -6,9 +6,9 @@
 
 namespace vb {
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CTAS>
 static int launch_one(const void* A, const void* W, const GemmParams& p, cudaStream_t st) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CTAS>;
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.M};
@@ -20,35 +20,48 @@ static int launch_one(const void* A, const void* W, const GemmParams& p, cudaStr
   {
     uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.N};
     uint64_t str[1] = {(uint64_t)p.K * 2};
-    uint32_t box[2] = {GEMM_BK, (uint32_t)BN};
+    uint32_t box[2] = {GEMM_BK, (uint32_t)(BN / CTAS)};
     int r = make_tmap_bf16_sw128(&tmB, W, 2, dims, str, box);
     if (r) return r;
   }
-  auto kern = gemm_bf16_kernel<BN, EPI>;
+  auto kern = gemm_bf16_kernel<BN, EPI, CTAS>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     VB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
+  const int m_tiles = (p.M + GEMM_BM * CTAS - 1) / (GEMM_BM * CTAS);
   const int n_tiles = (p.N + BN - 1) / BN;
   const int total = m_tiles * n_tiles;
-  const int grid = total < sm_count() ? total : sm_count();
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
+  const int max_cl = sm_count() / CTAS;
+  const int ncl = total < max_cl ? total : max_cl;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(ncl * CTAS);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTAS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  VB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
   VB_CUDA_CHECK(cudaGetLastError());
   vb::count_launch();
   return VB_OK;
 }
 
-template <int BN>
+template <int BN, int CTAS>
 static int launch_bn(const void* A, const void* W, const GemmParams& p, int epi, cudaStream_t st) {
   switch (epi) {
-    case EPI_BIAS_F32: return launch_one<BN, EPI_BIAS_F32>(A, W, p, st);
-    case EPI_BIAS_BF16: return launch_one<BN, EPI_BIAS_BF16>(A, W, p, st);
-    case EPI_GELU_BF16: return launch_one<BN, EPI_GELU_BF16>(A, W, p, st);
-    case EPI_GATE_RESID: return launch_one<BN, EPI_GATE_RESID>(A, W, p, st);
-    case EPI_QKV: return launch_one<BN, EPI_QKV>(A, W, p, st);
-    case EPI_SCORE: return launch_one<BN, EPI_SCORE>(A, W, p, st);
+    case EPI_BIAS_F32: return launch_one<BN, EPI_BIAS_F32, CTAS>(A, W, p, st);
+    case EPI_BIAS_BF16: return launch_one<BN, EPI_BIAS_BF16, CTAS>(A, W, p, st);
+    case EPI_GELU_BF16: return launch_one<BN, EPI_GELU_BF16, CTAS>(A, W, p, st);
+    case EPI_GATE_RESID: return launch_one<BN, EPI_GATE_RESID, CTAS>(A, W, p, st);
+    case EPI_QKV: return launch_one<BN, EPI_QKV, CTAS>(A, W, p, st);
+    case EPI_SCORE: return launch_one<BN, EPI_SCORE, CTAS>(A, W, p, st);
   }
   set_error("gemm: unknown epilogue %d", epi);
   return VB_ERR_ARG;
@@ -85,11 +98,21 @@ int gemm_launch(const void* A, const void* W, const GemmParams& p, int epi, cuda
     if (epi == EPI_GATE_RESID)
       VB_REQUIRE(p.resid && p.gate && p.rows_per_seq > 0, "gemm/gate: null pointer or rows_per_seq=%d", p.rows_per_seq);
   }
-  const int bn = force_bn ? force_bn : gemm_pick_bn(p.N);
-  switch (bn) {
-    case 256: return launch_bn<256>(A, W, p, epi, st);
-    case 192: return launch_bn<192>(A, W, p, epi, st);
-    case 128: return launch_bn<128>(A, W, p, epi, st);
+  const int bn = force_bn ? (force_bn & 0xffff) : gemm_pick_bn(p.N);
+  // CTA-pair tiles (256 x BN) unless the problem is a single 128-row tile or the caller forces 1-CTA (bit 16)
+  const bool pair = !(force_bn & 0x10000) && p.M > GEMM_BM;
+  if (pair) {
+    switch (bn) {
+      case 256: return launch_bn<256, 2>(A, W, p, epi, st);
+      case 192: return launch_bn<192, 2>(A, W, p, epi, st);
+      case 128: return launch_bn<128, 2>(A, W, p, epi, st);
+    }
+  } else {
+    switch (bn) {
+      case 256: return launch_bn<256, 1>(A, W, p, epi, st);
+      case 192: return launch_bn<192, 1>(A, W, p, epi, st);
+      case 128: return launch_bn<128, 1>(A, W, p, epi, st);
+    }
   }
   set_error("gemm: unsupported tile width %d", bn);
   return VB_ERR_ARG;

@@ -38,7 +38,8 @@ struct GemmParams {
 
 // Tile width the launcher will use for a given N (needed to size EPI_SCORE partials: n_tiles = ceil(N / bn)).
 int gemm_pick_bn(int N);
-// A: [M,K] bf16 row-major, W: [N,K] bf16 row-major (nn.Linear layout). force_bn: 0 = auto, else 128/192/256.
+// A: [M,K] bf16 row-major, W: [N,K] bf16 row-major (nn.Linear layout). force_bn: 0 = auto, else 128/192/256,
+// optionally | 0x10000 to force the 1-CTA kernel (the default is the CTA-pair kernel whenever M > 128).
 int gemm_launch(const void* A, const void* W, const GemmParams& p, int epi, cudaStream_t st, int force_bn = 0);
 
 }  // namespace vb

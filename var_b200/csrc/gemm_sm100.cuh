@@ -1,37 +1,42 @@
 // Persistent warp-specialised bf16 GEMM for sm_100a:  D[M,N] = A[M,K] * W[N,K]^T  (fp32 accumulate in TMEM)
 //   * A and W are K-major (row-major activations, nn.Linear weight layout) and arrive through TMA
 //     (128B-swizzled 64-column boxes) into a multi-stage smem ring
-//   * one elected thread issues tcgen05.mma (UMMA 128 x BN x 16, cta_group::1)
+//   * one elected thread issues tcgen05.mma: CTAS=1 -> UMMA 128 x BN x 16 (cta_group::1);
+//     CTAS=2 -> a CTA pair (cluster of 2 SMs) computes a 256 x BN tile with cta_group::2: each CTA stages its own
+//     128 rows of A and HALF of the W tile, so the per-SM L2->SMEM traffic per FLOP drops by a third (the 1-CTA
+//     kernel is capped near 60 % tensor-active by that ingress, profiles/r01_gemm_1cta_ncu.txt)
 //   * accumulators are double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps
 //     the main loop of tile i+1
-//   * four epilogue warps read TMEM with tcgen05.ld (one accumulator row per thread) and apply the
-//     fused epilogue of the VAR block (reference semantics cited per mode below)
+//   * eight epilogue warps read TMEM with tcgen05.ld (one accumulator row per thread) and apply the
+//     fused epilogue of the VAR block (reference semantics cited per mode in gemm.h)
 #pragma once
 #include "common.cuh"
 #include "gemm.h"
 
 namespace vb {
 
-constexpr int GEMM_BM = 128;
+constexpr int GEMM_BM = 128;        // accumulator rows per CTA (TMEM lanes)
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 320;  // warp0: TMA, warp1: MMA + TMEM owner, warps 2-9: epilogue
+constexpr int GEMM_THREADS = 320;   // warp0: TMA, warp1: MMA + TMEM owner, warps 2-9: epilogue
 constexpr int EPI_STG_LD = 20;      // floats per staging row (16 + 4 pad: 16-byte aligned)
 
-template <int BN>
+template <int BN, int CTAS>
 struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
-  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int B_BYTES = (BN / CTAS) * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 192 ? 5 : 6);
-  static constexpr int STG_BYTES = 8 * 32 * EPI_STG_LD * 4;       // epilogue staging, one 32x20 fp32 tile per warp
+  static constexpr int STG_BYTES = 8 * 32 * EPI_STG_LD * 4;  // epilogue staging, one 32x20 fp32 tile per warp
+  static constexpr int BUDGET = 232448 - 2048 - STG_BYTES;  // 227 KB per CTA minus alignment slack / static smem
+  static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024;  // +1024: manual alignment slack
 };
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CTAS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CTAS>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int TILE_M = GEMM_BM * CTAS;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bars[2 * STAGES + 4];
   __shared__ uint32_t tmem_base_smem;
@@ -39,13 +44,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int rank = (CTAS == 2) ? (int)cluster_ctarank() : 0;  // CTA 0 of the pair issues the MMAs
+  const int cid = blockIdx.x / CTAS, ncl = gridDim.x / CTAS;   // tile scheduler runs per cluster
 
   auto full_bar = [&](int s) { return smem_u32(&bars[s]); };
   auto empty_bar = [&](int s) { return smem_u32(&bars[STAGES + s]); };
   auto tfull_bar = [&](int s) { return smem_u32(&bars[2 * STAGES + s]); };
   auto tempty_bar = [&](int s) { return smem_u32(&bars[2 * STAGES + 2 + s]); };
 
-  const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
+  const int m_tiles = (p.M + TILE_M - 1) / TILE_M;
   const int n_tiles = (p.N + BN - 1) / BN;
   const int total_tiles = m_tiles * n_tiles;
   const int num_kb = p.K / GEMM_BK;
@@ -54,46 +61,57 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(full_bar(s), 1);   // the (leader) producer's arrive.expect_tx; TMA bytes of both CTAs complete it
+      mbar_init(empty_bar(s), 1);  // one tcgen05.commit (multicast to both CTAs when CTAS == 2)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 8);  // one arrive per epilogue warp
+      mbar_init(tempty_bar(s), 8 * CTAS);  // one arrive per epilogue warp of every CTA of the pair
     }
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_smem), 512);
+  if (warp == 1) {
+    if constexpr (CTAS == 2) tmem_alloc_cg2(smem_u32(&tmem_base_smem), 512);
+    else tmem_alloc(smem_u32(&tmem_base_smem), 512);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp == 0) {
-    // ------------------------------ TMA producer ------------------------------
+    // ------------------------------ TMA producer (every CTA loads its own operand slices) ------------------------------
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = cid; tile < total_tiles; tile += ncl) {
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
-          mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-          tma_load_2d(&tmA, full_bar(stage), sa, kb * GEMM_BK, m_blk * GEMM_BM);
-          tma_load_2d(&tmB, full_bar(stage), sa + Cfg::A_BYTES, kb * GEMM_BK, n_blk * BN);
+          if constexpr (CTAS == 2) {
+            // completion bytes of BOTH CTAs are credited to the leader's full barrier (it gates the pair's MMAs)
+            const uint32_t fb = mapa_shared(full_bar(stage), 0);
+            if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
+            tma_load_2d_cg2(&tmA, fb, sa, kb * GEMM_BK, m_blk * TILE_M + rank * GEMM_BM);
+            tma_load_2d_cg2(&tmB, fb, sa + Cfg::A_BYTES, kb * GEMM_BK, n_blk * BN + rank * (BN / 2));
+          } else {
+            mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+            tma_load_2d(&tmA, full_bar(stage), sa, kb * GEMM_BK, m_blk * GEMM_BM);
+            tma_load_2d(&tmB, full_bar(stage), sa + Cfg::A_BYTES, kb * GEMM_BK, n_blk * BN);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------ MMA issuer ------------------------------
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
+    // ------------------------------ MMA issuer (leader CTA only) ------------------------------
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BN);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = cid; tile < total_tiles; tile += ncl, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(tempty_bar(as), aphase ^ 1);
@@ -108,12 +126,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the 128B swizzle atom: +2 in the (addr>>4) field
-            umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            if constexpr (CTAS == 2) umma_bf16_ss_cg2(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            else umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           }
-          umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs have read it
+          // smem slot reusable (in both CTAs) once these MMAs have read it
+          if constexpr (CTAS == 2) umma_commit_cg2_mc(empty_bar(stage), 3); else umma_commit(empty_bar(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(tfull_bar(as));  // accumulator complete
+        // accumulator complete: wake the epilogue warps of both CTAs
+        if constexpr (CTAS == 2) umma_commit_cg2_mc(tfull_bar(as), 3); else umma_commit(tfull_bar(as));
       }
     }
   } else {
@@ -124,13 +145,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int quarter = warp & 3;          // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;      // which interleaved half of the column chunks
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = cid; tile < total_tiles; tile += ncl, ++it) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
-      const int row = m_blk * GEMM_BM + quarter * 32 + lane;
+      const int row = m_blk * TILE_M + rank * GEMM_BM + quarter * 32 + lane;
       const bool row_ok = row < p.M;
       const uint32_t taddr = tmem_base + as * 256 + ((uint32_t)(quarter * 32) << 16);
       const int n_base = n_blk * BN;
@@ -216,7 +237,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         float* stg = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + STAGES * Cfg::STAGE_BYTES) +
                      (warp - 2) * (32 * EPI_STG_LD);
         const int rsub = lane >> 2, cg = lane & 3;
-        const int row_w0 = m_blk * GEMM_BM + quarter * 32;
+        const int row_w0 = m_blk * TILE_M + rank * GEMM_BM + quarter * 32;
         int seqs[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) seqs[i] = (row_w0 + rsub + 8 * i) / p.rows_per_seq;
@@ -303,15 +324,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // release this accumulator stage back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (lane == 0) {
+        if constexpr (CTAS == 2) mbar_arrive_cluster(mapa_shared(tempty_bar(as), 0));  // the leader CTA's MMA thread waits
+        else mbar_arrive(tempty_bar(as));
+      }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if constexpr (CTAS == 2) tmem_dealloc_cg2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
