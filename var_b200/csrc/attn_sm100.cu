@@ -170,7 +170,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       __syncwarp();
       tmem_ld_32x32(tmem + lane_off + b * 64, s);
       tmem_ld_32x32(tmem + lane_off + b * 64 + 32, s + 32);
-      tmem_ld_wait();
+      tmem_ld_wait_dep(s);
+      tmem_ld_wait_dep(s + 32);
       const bool partial = k0 + ATT_BN > kv_end;  // this row does not see the whole tile
       if (partial) {
 #pragma unroll
@@ -193,7 +194,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
           float o[32];
           __syncwarp();
           tmem_ld_32x32(tmem_o + lane_off + c * 32, o);
-          tmem_ld_wait();
+          tmem_ld_wait_dep(o);
 #pragma unroll
           for (int i = 0; i < 32; ++i) o[i] *= f;
           tmem_st_32x32(tmem_o + lane_off + c * 32, o);
@@ -233,7 +234,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       float o[32];
       __syncwarp();
       tmem_ld_32x32(tmem_o + lane_off + c * 32, o);
-      tmem_ld_wait();
+      tmem_ld_wait_dep(o);
       uint4* d4 = reinterpret_cast<uint4*>(stg + lane * ATT_OSTG_LD + c * 64);
 #pragma unroll
       for (int g = 0; g < 4; ++g) {

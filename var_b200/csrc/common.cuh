@@ -206,6 +206,19 @@ __device__ __forceinline__ void umma_commit_cg2_mc(uint32_t bar, uint16_t cta_ma
                : "memory");
 }
 
+// tcgen05.wait::ld that also names the 32 destination registers as read-write operands: the compiler cannot move
+// arithmetic on them above the wait (it does not know tcgen05.ld is asynchronous).
+__device__ __forceinline__ void tmem_ld_wait_dep(float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                 "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+
 // store 32 consecutive fp32 columns of the thread's TMEM lane (inverse of tmem_ld_32x32)
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const float* v) {
   const uint32_t* r = reinterpret_cast<const uint32_t*>(v);

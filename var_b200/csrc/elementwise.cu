@@ -17,6 +17,7 @@ constexpr int LN_ROWS = 32;   // rows of one sequence per CTA (8 warps x 4 rows)
 // A CTA owns LN_ROWS consecutive rows of ONE sequence, so (1+scale) and shift are staged in shared memory once and
 // the only global traffic per row is the 4C-byte read and the 2C-byte write (the first version re-read 8C bytes of
 // adaLN parameters per row through L2 and ran at 2.3 TB/s).
+template <int LN_NV>  // float4 per lane held in registers: C <= 128 * LN_NV
 __global__ void __launch_bounds__(256)
 ln_modulate_kernel(const float* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
                    int ada_ld, int rows_per_seq, __nv_bfloat16* __restrict__ out, int C, float eps) {
@@ -40,10 +41,10 @@ ln_modulate_kernel(const float* __restrict__ x, const float* __restrict__ scale,
   for (int t = blockIdx.x * LN_ROWS + warp; t < t_end; t += 8) {
     const size_t row = (size_t)seq * rows_per_seq + t;
     const float4* xr = reinterpret_cast<const float4*>(x + row * C);
-    float4 v[LN_MAXV];
+    float4 v[LN_NV];
     float sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
+    for (int i = 0; i < LN_NV; ++i) {
       const int idx = lane + 32 * i;
       if (idx < nvec) {
         v[i] = xr[idx];
@@ -53,7 +54,7 @@ ln_modulate_kernel(const float* __restrict__ x, const float* __restrict__ scale,
     const float mean = warp_sum(sum) / (float)C;
     float sq = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
+    for (int i = 0; i < LN_NV; ++i) {
       const int idx = lane + 32 * i;
       if (idx < nvec) {
         const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
@@ -63,7 +64,7 @@ ln_modulate_kernel(const float* __restrict__ x, const float* __restrict__ scale,
     const float rstd = 1.f / sqrtf(warp_sum(sq) / (float)C + eps);
     uint2* o = reinterpret_cast<uint2*>(out + row * C);
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
+    for (int i = 0; i < LN_NV; ++i) {
       const int idx = lane + 32 * i;
       if (idx < nvec) {
         const float4 s = s1[idx], h = sh[idx];
@@ -84,8 +85,13 @@ int ln_modulate(const float* x, const float* scale, const float* shift, int ada_
   VB_REQUIRE(M > 0 && rows_per_seq > 0 && M % rows_per_seq == 0, "ln_modulate: bad M=%d rows_per_seq=%d", M, rows_per_seq);
   VB_REQUIRE(ada_ld % 4 == 0 && M / rows_per_seq <= 65535, "ln_modulate: bad ada_ld=%d or too many sequences", ada_ld);
   dim3 grid((rows_per_seq + LN_ROWS - 1) / LN_ROWS, M / rows_per_seq);
-  ln_modulate_kernel<<<grid, 256, (size_t)C * 8, st>>>(x, scale, shift, ada_ld, rows_per_seq,
-                                                       reinterpret_cast<__nv_bfloat16*>(out), C, eps);
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+  if (C <= 1024)
+    ln_modulate_kernel<8><<<grid, 256, (size_t)C * 8, st>>>(x, scale, shift, ada_ld, rows_per_seq, o, C, eps);
+  else if (C <= 2048)
+    ln_modulate_kernel<16><<<grid, 256, (size_t)C * 8, st>>>(x, scale, shift, ada_ld, rows_per_seq, o, C, eps);
+  else
+    ln_modulate_kernel<LN_MAXV><<<grid, 256, (size_t)C * 8, st>>>(x, scale, shift, ada_ld, rows_per_seq, o, C, eps);
   VB_CUDA_CHECK(cudaGetLastError());
   vb::count_launch();
   return VB_OK;

@@ -167,7 +167,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           __syncwarp();
           tmem_ld_32x32(taddr + c * 64, v);
           tmem_ld_32x32(taddr + c * 64 + 32, v + 32);
-          tmem_ld_wait();
+          tmem_ld_wait_dep(v);
+          tmem_ld_wait_dep(v + 32);
           const int which = n0 / p.C;  // 0 q, 1 k, 2 v
           const int head = (n0 - which * p.C) >> 6;
           float ss = 0.f;
@@ -209,7 +210,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           float v[32];
           __syncwarp();
           tmem_ld_32x32(taddr + c * 32, v);
-          tmem_ld_wait();
+          tmem_ld_wait_dep(v);
           float cmax = -INFINITY;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -248,7 +249,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           float v[32];
           __syncwarp();
           tmem_ld_32x32(taddr + c * 32, v);
-          tmem_ld_wait();
+          tmem_ld_wait_dep(v);
 #pragma unroll
           for (int h2 = 0; h2 < 2; ++h2) {
             float4* srow = reinterpret_cast<float4*>(stg + lane * EPI_STG_LD);
@@ -282,14 +283,27 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       } else {
-#pragma unroll 1
-        for (int c = half; c < BN / 32; c += 2) {
-          const int n0 = n_base + c * 32;
-          if (n0 >= p.N) break;
-          float v[32];
+        // software-pipelined: the TMEM load of chunk i+1 is in flight while chunk i is converted and stored
+        constexpr int NCH = (BN / 32 + 1) / 2;  // chunks per warp (interleaved with the sibling warp)
+        float vbuf[2][32];
+        int n_valid = 0;
+#pragma unroll
+        for (int i = 0; i < NCH; ++i)
+          if ((half + 2 * i) * 32 < BN && n_base + (half + 2 * i) * 32 < p.N) n_valid = i + 1;
+        if (n_valid > 0) {
           __syncwarp();
-          tmem_ld_32x32(taddr + c * 32, v);
-          tmem_ld_wait();
+          tmem_ld_32x32(taddr + half * 32, vbuf[0]);
+        }
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+          if (i >= n_valid) break;
+          float* v = vbuf[i & 1];
+          const int n0 = n_base + (half + 2 * i) * 32;
+          tmem_ld_wait_dep(v);
+          if (i + 1 < n_valid) {
+            __syncwarp();
+            tmem_ld_32x32(taddr + (half + 2 * (i + 1)) * 32, vbuf[(i + 1) & 1]);
+          }
           if (p.bias != nullptr) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -298,7 +312,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
           if (!row_ok) {
-            // nothing to store for rows beyond M (the TMEM load above stays warp-convergent)
+            // nothing to store for rows beyond M (the TMEM loads stay warp-convergent)
           } else if constexpr (EPI == EPI_BIAS_F32) {
             float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)row * p.N + n0);
 #pragma unroll

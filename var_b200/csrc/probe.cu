@@ -65,7 +65,7 @@ umma_probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     float v[32];
     __syncwarp();
     tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16) + c * 32, v);
-    tmem_ld_wait();
+    tmem_ld_wait_dep(v);
     for (int j = 0; j < 32; ++j) D[(size_t)row * N + c * 32 + j] = v[j];
   }
   tc_fence_before();
