@@ -155,10 +155,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bool row_ok = row < p.M;
       const uint32_t taddr = tmem_base + as * 256 + ((uint32_t)(quarter * 32) << 16);
       const int n_base = n_blk * BN;
+      // private 32 x 20-float staging tile of this warp (transposes accumulator rows into coalesced global accesses)
+      float* stg = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + STAGES * Cfg::STAGE_BYTES) +
+                   (warp - 2) * (32 * EPI_STG_LD);
+      const int rsub = lane >> 2, cg = lane & 3;
+      const int row_w0 = m_blk * TILE_M + rank * GEMM_BM + quarter * 32;  // first row of this warp
 
       if constexpr (EPI == EPI_QKV) {
-        const int seq = row / p.rows_per_seq;
-        const int t = row - seq * p.rows_per_seq;
 #pragma unroll 1
         for (int c = half; c < BN / 64; c += 2) {
           const int n0 = n_base + c * 64;
@@ -182,22 +185,35 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mul = 1.f / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize(dim=-1), eps 1e-12
             if (which == 0) mul *= __ldg(p.q_scale + head);
           }
-          if (row_ok) {
-            __nv_bfloat16* dst;
-            if (which == 0)
-              dst = p.q_out + (((size_t)seq * p.H + head) * p.rows_per_seq + t) * 64;
-            else
-              dst = (which == 1 ? p.k_cache : p.v_cache) + (((size_t)seq * p.H + head) * p.Lmax + p.pos0 + t) * 64;
-            uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+          for (int h2 = 0; h2 < 2; ++h2) {  // 64-byte halves of the 128-byte head row
+            uint4* srow = reinterpret_cast<uint4*>(stg + lane * EPI_STG_LD);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int e = 32 * h2 + 8 * j;
               uint4 o;
-              o.x = pack_bf16x2(v[8 * j + 0] * mul, v[8 * j + 1] * mul);
-              o.y = pack_bf16x2(v[8 * j + 2] * mul, v[8 * j + 3] * mul);
-              o.z = pack_bf16x2(v[8 * j + 4] * mul, v[8 * j + 5] * mul);
-              o.w = pack_bf16x2(v[8 * j + 6] * mul, v[8 * j + 7] * mul);
-              d4[j] = o;
+              o.x = pack_bf16x2(v[e + 0] * mul, v[e + 1] * mul);
+              o.y = pack_bf16x2(v[e + 2] * mul, v[e + 3] * mul);
+              o.z = pack_bf16x2(v[e + 4] * mul, v[e + 5] * mul);
+              o.w = pack_bf16x2(v[e + 6] * mul, v[e + 7] * mul);
+              srow[j] = o;
             }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = rsub + 8 * i;
+              const int rg = row_w0 + r;
+              if (rg < p.M) {
+                const int sq = rg / p.rows_per_seq, tt = rg - sq * p.rows_per_seq;
+                __nv_bfloat16* dst;
+                if (which == 0)
+                  dst = p.q_out + (((size_t)sq * p.H + head) * p.rows_per_seq + tt) * 64;
+                else
+                  dst = (which == 1 ? p.k_cache : p.v_cache) + (((size_t)sq * p.H + head) * p.Lmax + p.pos0 + tt) * 64;
+                *reinterpret_cast<uint4*>(dst + 32 * h2 + cg * 8) = *reinterpret_cast<const uint4*>(stg + r * EPI_STG_LD + cg * 4);
+              }
+            }
+            __syncwarp();
           }
         }
       } else if constexpr (EPI == EPI_SCORE) {
@@ -235,10 +251,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       } else if constexpr (EPI == EPI_GATE_RESID) {
         // Residual update needs coalesced reads of resid/gate: transpose 32x16 accumulator pieces through a private
         // smem tile so that each warp instruction touches 8 rows x 64 contiguous bytes.
-        float* stg = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + STAGES * Cfg::STAGE_BYTES) +
-                     (warp - 2) * (32 * EPI_STG_LD);
-        const int rsub = lane >> 2, cg = lane & 3;
-        const int row_w0 = m_blk * TILE_M + rank * GEMM_BM + quarter * 32;
         int seqs[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) seqs[i] = (row_w0 + rsub + 8 * i) / p.rows_per_seq;
@@ -317,12 +329,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)row * p.N + n0);
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else {  // EPI_BIAS_BF16 / EPI_GELU_BF16
-            if constexpr (EPI == EPI_GELU_BF16) {
+          } else if constexpr (EPI == EPI_GELU_BF16) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
-            }
-            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.N + n0);
+            for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
+          }
+          if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_GELU_BF16) {
+            // transpose the 32 rows x 64 B of this chunk through the warp's staging tile: each store instruction then
+            // writes 8 rows x 64 contiguous bytes (whole sectors) instead of 32 scattered 16-byte pieces
+            uint4* srow = reinterpret_cast<uint4*>(stg + lane * EPI_STG_LD);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint4 w;
@@ -330,8 +344,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               w.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
               w.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
               w.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-              o[j] = w;
+              srow[j] = w;
             }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = rsub + 8 * i;
+              const int rg = row_w0 + r;
+              if (rg < p.M)
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)rg * p.N + n0 + cg * 8) =
+                    *reinterpret_cast<const uint4*>(stg + r * EPI_STG_LD + cg * 4);
+            }
+            __syncwarp();
           }
         }
       }
