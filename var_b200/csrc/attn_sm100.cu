@@ -31,7 +31,6 @@ constexpr int ATT_Q_BYTES = ATT_BM * ATT_D * 2;   // 16 KB
 constexpr int ATT_KV_BYTES = ATT_BN * ATT_D * 2;  // 8 KB
 constexpr int ATT_P_BYTES = ATT_BM * ATT_BN * 2;  // 16 KB
 constexpr int ATT_SMEM = ATT_Q_BYTES + 2 * ATT_KST * ATT_KV_BYTES + 2 * ATT_P_BYTES + 1024;
-constexpr int ATT_OSTG_LD = 144;  // bytes per staged output row (128 + 16 pad)
 constexpr float ATT_RESCALE_LOG2 = 80.f;
 
 struct AttnLevels {
@@ -49,12 +48,19 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128_attn(uint32_t smem_addr) 
   return d;
 }
 
+// Work item = (sequence, head, 128-row query tile). CTAs are persistent (2 per SM) and walk items
+// blockIdx.x, blockIdx.x + gridDim.x, ...: the K/V tile stream is prefetched across item boundaries, so the TMA /
+// TMEM-allocation / first-QK latency of an item is paid once per CTA instead of once per item.
+struct AttnItem {
+  int item, j, n_kt, bh, row0;
+};
+
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
             const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, int Lq, int H, int q_pos0,
-            const AttnLevels lv) {
+            const AttnLevels lv, int n_qt, int total_items) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t bars[1 + 2 * ATT_KST + 6];  // q | k[3] | v[3] | s[2] | p[2] | pv[2]
+  __shared__ uint64_t bars[2 + 2 * ATT_KST + 6];  // q | oread | k[3] | v[3] | s[2] | p[2] | pv[2]
   __shared__ uint32_t tmem_base_smem;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = base;
@@ -62,30 +68,43 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   const uint32_t sV = sK + ATT_KST * ATT_KV_BYTES;
   const uint32_t sP = sV + ATT_KST * ATT_KV_BYTES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q_tile = blockIdx.x, head = blockIdx.y, seq = blockIdx.z;
-  const int bh = seq * H + head;
-  const uint32_t bar_q = smem_u32(&bars[0]);
-  auto bar_k = [&](int s) { return smem_u32(&bars[1 + s]); };
-  auto bar_v = [&](int s) { return smem_u32(&bars[1 + ATT_KST + s]); };
-  auto bar_s = [&](int s) { return smem_u32(&bars[1 + 2 * ATT_KST + s]); };
-  auto bar_p = [&](int s) { return smem_u32(&bars[3 + 2 * ATT_KST + s]); };
-  auto bar_pv = [&](int s) { return smem_u32(&bars[5 + 2 * ATT_KST + s]); };
+  const uint32_t bar_q = smem_u32(&bars[0]), bar_oread = smem_u32(&bars[1]);
+  auto bar_k = [&](int s) { return smem_u32(&bars[2 + s]); };
+  auto bar_v = [&](int s) { return smem_u32(&bars[2 + ATT_KST + s]); };
+  auto bar_s = [&](int s) { return smem_u32(&bars[2 + 2 * ATT_KST + s]); };
+  auto bar_p = [&](int s) { return smem_u32(&bars[4 + 2 * ATT_KST + s]); };
+  auto bar_pv = [&](int s) { return smem_u32(&bars[6 + 2 * ATT_KST + s]); };
 
-  // visible keys for the rows of this tile
-  const int row0 = q_tile * ATT_BM;
-  auto kv_end_of = [&](int row) {  // row index inside this call's query block
+  auto kv_end_of = [&](int row) {  // visible keys of query row `row` of this call's query block
     const int pos = q_pos0 + (row < Lq ? row : Lq - 1);
     int e = lv.end[lv.n - 1];
     for (int s = lv.n - 1; s >= 0; --s)
       if (pos < lv.end[s]) e = lv.end[s];
     return e;
   };
-  const int last_row = (row0 + ATT_BM - 1 < Lq) ? row0 + ATT_BM - 1 : Lq - 1;
-  const int kv_max = kv_end_of(last_row);
-  const int n_kt = (kv_max + ATT_BN - 1) / ATT_BN;
+  auto decode = [&](AttnItem& c) {
+    if (c.item >= total_items) return;
+    const int q_tile = c.item % n_qt;
+    c.bh = c.item / n_qt;
+    c.row0 = q_tile * ATT_BM;
+    const int last_row = (c.row0 + ATT_BM - 1 < Lq) ? c.row0 + ATT_BM - 1 : Lq - 1;
+    c.n_kt = (kv_end_of(last_row) + ATT_BN - 1) / ATT_BN;
+    c.j = 0;
+  };
+  auto next_item = [&](AttnItem& c) {
+    c.item += gridDim.x;
+    decode(c);
+  };
+  auto next_tile = [&](AttnItem& c) {
+    if (++c.j == c.n_kt) next_item(c);
+  };
 
   if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
     mbar_init(bar_q, 1);
+    mbar_init(bar_oread, 128);
     for (int s = 0; s < ATT_KST; ++s) { mbar_init(bar_k(s), 1); mbar_init(bar_v(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(bar_s(s), 1); mbar_init(bar_p(s), 128); mbar_init(bar_pv(s), 1); }
     mbar_fence_init();
@@ -101,161 +120,202 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     if (lane == 0) {
       constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_BM, ATT_BN);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BM, ATT_D) | (1u << 16);  // B (V) is MN-major
-      mbar_expect_tx(bar_q, ATT_Q_BYTES);
-      tma_load_3d(&tmQ, bar_q, sQ, 0, row0, bh);
-      for (int j = 0; j < ATT_KST && j < n_kt; ++j) {
-        mbar_expect_tx(bar_k(j), ATT_KV_BYTES);
-        tma_load_3d(&tmK, bar_k(j), sK + j * ATT_KV_BYTES, 0, j * ATT_BN, bh);
-        mbar_expect_tx(bar_v(j), ATT_KV_BYTES);
-        tma_load_3d(&tmV, bar_v(j), sV + j * ATT_KV_BYTES, 0, j * ATT_BN, bh);
+      AttnItem cur{(int)blockIdx.x, 0, 0, 0, 0};
+      decode(cur);
+      AttnItem kc = cur, vc = cur;  // K / V load cursors run ahead of the compute cursor along the tile stream
+      int kpos = 0, vpos = 0;
+      auto load_k = [&]() {
+        const int st = kpos % ATT_KST;
+        mbar_expect_tx(bar_k(st), ATT_KV_BYTES);
+        tma_load_3d(&tmK, bar_k(st), sK + st * ATT_KV_BYTES, 0, kc.j * ATT_BN, kc.bh);
+        next_tile(kc);
+        ++kpos;
+      };
+      auto load_v = [&]() {
+        const int st = vpos % ATT_KST;
+        mbar_expect_tx(bar_v(st), ATT_KV_BYTES);
+        tma_load_3d(&tmV, bar_v(st), sV + st * ATT_KV_BYTES, 0, vc.j * ATT_BN, vc.bh);
+        next_tile(vc);
+        ++vpos;
+      };
+      if (cur.item < total_items) {
+        mbar_expect_tx(bar_q, ATT_Q_BYTES);
+        tma_load_3d(&tmQ, bar_q, sQ, 0, cur.row0, cur.bh);
+      }
+      for (int i = 0; i < ATT_KST; ++i) {
+        if (kc.item < total_items) load_k();
+        if (vc.item < total_items) load_v();
       }
       const uint64_t qd = umma_desc_k_sw128(sQ);
-      auto issue_qk = [&](int j) {
-        const int st = j % ATT_KST;
-        mbar_wait(bar_k(st), (j / ATT_KST) & 1);
+      auto issue_qk = [&](int g) {  // g: global key-tile index of this CTA
+        const int st = g % ATT_KST;
+        mbar_wait(bar_k(st), (g / ATT_KST) & 1);
         tc_fence_after();
         const uint64_t kd = umma_desc_k_sw128(sK + st * ATT_KV_BYTES);
 #pragma unroll
-        for (int k = 0; k < ATT_D / 16; ++k) umma_bf16_ss(tmem + (j & 1) * 64, qd + 2 * k, kd + 2 * k, idesc_qk, k != 0);
-        umma_commit(bar_s(j & 1));
+        for (int k = 0; k < ATT_D / 16; ++k) umma_bf16_ss(tmem + (g & 1) * 64, qd + 2 * k, kd + 2 * k, idesc_qk, k != 0);
+        umma_commit(bar_s(g & 1));
       };
-      mbar_wait(bar_q, 0);
-      issue_qk(0);
-      for (int j = 0; j < n_kt; ++j) {
-        // S[(j+1)&1] was last read by softmax_{j-1}, whose bar_p this thread has already observed.
-        if (j + 1 < n_kt) issue_qk(j + 1);
-        mbar_wait(bar_p(j & 1), (j >> 1) & 1);  // P_j written; QK_j therefore complete
-        tc_fence_after();
-        if (j + ATT_KST < n_kt) {  // K stage of tile j is free
-          const int st = j % ATT_KST;
-          mbar_expect_tx(bar_k(st), ATT_KV_BYTES);
-          tma_load_3d(&tmK, bar_k(st), sK + st * ATT_KV_BYTES, 0, (j + ATT_KST) * ATT_BN, bh);
-        }
-        {
-          const int st = j % ATT_KST;
-          mbar_wait(bar_v(st), (j / ATT_KST) & 1);
+      int G = 0, it = 0;
+      while (cur.item < total_items) {
+        const int n_kt = cur.n_kt;
+        mbar_wait(bar_q, it & 1);
+        issue_qk(G);
+        for (int j = 0; j < n_kt; ++j) {
+          const int g = G + j;
+          // S[(g+1)&1] was last read by the softmax of tile g-1, whose bar_p this thread has already observed
+          if (j + 1 < n_kt) issue_qk(g + 1);
+          mbar_wait(bar_p(g & 1), (g >> 1) & 1);  // P_g written; QK_g therefore complete
           tc_fence_after();
-          const uint64_t pd = umma_desc_k_sw128(sP + (j & 1) * ATT_P_BYTES);
+          if (kc.item < total_items) load_k();  // stream position g + 3 reuses the K stage of tile g
+          if (j == n_kt - 1) {                  // last QK of this item has read sQ: fetch the next item's queries
+            AttnItem nx = cur;
+            next_item(nx);
+            if (nx.item < total_items) {
+              mbar_expect_tx(bar_q, ATT_Q_BYTES);
+              tma_load_3d(&tmQ, bar_q, sQ, 0, nx.row0, nx.bh);
+            }
+          }
+          const int st = g % ATT_KST;
+          mbar_wait(bar_v(st), (g / ATT_KST) & 1);
+          if (j == 0 && it > 0) mbar_wait(bar_oread, (it - 1) & 1);  // previous item's output has left TMEM
+          tc_fence_after();
+          const uint64_t pd = umma_desc_k_sw128(sP + (g & 1) * ATT_P_BYTES);
 #pragma unroll
           for (int k = 0; k < ATT_BN / 16; ++k) {
             const uint64_t vd = umma_desc_mn_sw128_attn(sV + st * ATT_KV_BYTES + k * 2048);
             umma_bf16_ss(tmem_o, pd + 2 * k, vd, idesc_pv, (j | k) != 0);
           }
-          umma_commit(bar_pv(j & 1));
+          umma_commit(bar_pv(g & 1));
+          if (g >= 1 && vc.item < total_items) {  // stream position g + 2 reuses the V stage of tile g - 1
+            mbar_wait(bar_pv((g - 1) & 1), ((g - 1) >> 1) & 1);
+            load_v();
+          }
         }
-        if (j >= 1 && j - 1 + ATT_KST < n_kt) {  // V stage of tile j-1 is free once PV_{j-1} has completed
-          mbar_wait(bar_pv((j - 1) & 1), ((j - 1) >> 1) & 1);
-          const int st = (j - 1) % ATT_KST;
-          mbar_expect_tx(bar_v(st), ATT_KV_BYTES);
-          tma_load_3d(&tmV, bar_v(st), sV + st * ATT_KV_BYTES, 0, (j - 1 + ATT_KST) * ATT_BN, bh);
-        }
+        G += n_kt;
+        ++it;
+        next_item(cur);
       }
     }
   } else {
     // ------------------------------ softmax / output warps ------------------------------
-    const int row = row0 + warp * 32 + lane;
-    const int kv_end = kv_end_of(row);
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
     const int sw = lane & 7;  // == row & 7
     constexpr float LOG2E = 1.4426950408889634f;
-    float m_ref2 = 0.f;  // reference maximum, pre-multiplied by log2(e)
-    float l_run = 0.f;
-
-    for (int j = 0; j < n_kt; ++j) {
-      const int k0 = j * ATT_BN;
-      const int b = j & 1;
-      mbar_wait(bar_s(b), (j >> 1) & 1);
-      tc_fence_after();
-      float s[64];
-      __syncwarp();
-      tmem_ld_32x32(tmem + lane_off + b * 64, s);
-      tmem_ld_32x32(tmem + lane_off + b * 64 + 32, s + 32);
-      tmem_ld_wait_dep(s);
-      tmem_ld_wait_dep(s + 32);
-      const bool partial = k0 + ATT_BN > kv_end;  // this row does not see the whole tile
-      if (partial) {
-#pragma unroll
-        for (int i = 0; i < 64; ++i) s[i] = (k0 + i < kv_end) ? s[i] : -INFINITY;
-      }
-      float mx = s[0];
-#pragma unroll
-      for (int i = 1; i < 64; ++i) mx = fmaxf(mx, s[i]);
-      const float mx2 = mx * LOG2E;
-      if (j == 0) {
-        m_ref2 = mx2;  // finite: key 0 is visible to every query
-      } else if (__any_sync(0xffffffffu, mx2 - m_ref2 > ATT_RESCALE_LOG2)) {
-        // rare: rebase the accumulator of the rows that overflowed the reference
-        const bool need = mx2 - m_ref2 > ATT_RESCALE_LOG2;
-        const float f = need ? exp2f(m_ref2 - mx2) : 1.f;
-        mbar_wait(bar_pv((j - 1) & 1), ((j - 1) >> 1) & 1);  // every earlier P V has landed in TMEM
+    AttnItem cur{(int)blockIdx.x, 0, 0, 0, 0};
+    decode(cur);
+    int G = 0;
+    while (cur.item < total_items) {
+      const int n_kt = cur.n_kt;
+      const int row = cur.row0 + warp * 32 + lane;
+      const int kv_end = kv_end_of(row);
+      const int head = cur.bh % H, seq = cur.bh / H;
+      float m_ref2 = 0.f;  // reference maximum, pre-multiplied by log2(e)
+      float l_run = 0.f;
+      for (int j = 0; j < n_kt; ++j) {
+        const int g = G + j;
+        const int k0 = j * ATT_BN;
+        const int b = g & 1;
+        mbar_wait(bar_s(b), (g >> 1) & 1);
         tc_fence_after();
+        float s[64];
+        __syncwarp();
+        tmem_ld_32x32(tmem + lane_off + b * 64, s);
+        tmem_ld_32x32(tmem + lane_off + b * 64 + 32, s + 32);
+        tmem_ld_wait_dep(s);
+        tmem_ld_wait_dep(s + 32);
+        const bool partial = k0 + ATT_BN > kv_end;  // this row does not see the whole tile
+        if (partial) {
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          float o[32];
-          __syncwarp();
-          tmem_ld_32x32(tmem_o + lane_off + c * 32, o);
-          tmem_ld_wait_dep(o);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] *= f;
-          tmem_st_32x32(tmem_o + lane_off + c * 32, o);
+          for (int i = 0; i < 64; ++i) s[i] = (k0 + i < kv_end) ? s[i] : -INFINITY;
         }
-        tmem_st_wait();
-        l_run *= f;
-        if (need) m_ref2 = mx2;
-      }
-      float l_tile = 0.f;
+        float mx = s[0];
 #pragma unroll
-      for (int i = 0; i < 64; ++i) {
-        s[i] = fast_exp2(fmaf(s[i], LOG2E, -m_ref2));  // masked entries: exp2(-inf) = 0
-        l_tile += s[i];
-      }
-      l_run += l_tile;
-      if (j >= 2) mbar_wait(bar_pv(b), ((j - 2) >> 1) & 1);  // P buffer b was read by PV_{j-2}
-      const uint32_t p_row = sP + b * ATT_P_BYTES + (uint32_t)(warp * 32 + lane) * 128;
+        for (int i = 1; i < 64; ++i) mx = fmaxf(mx, s[i]);
+        const float mx2 = mx * LOG2E;
+        if (j == 0) {
+          m_ref2 = mx2;  // finite: key 0 is visible to every query
+        } else if (__any_sync(0xffffffffu, mx2 - m_ref2 > ATT_RESCALE_LOG2)) {
+          // rare: rebase the accumulator of the rows that overflowed the reference
+          const bool need = mx2 - m_ref2 > ATT_RESCALE_LOG2;
+          const float f = need ? exp2f(m_ref2 - mx2) : 1.f;
+          mbar_wait(bar_pv((g - 1) & 1), ((g - 1) >> 1) & 1);  // every earlier P V of this item has landed in TMEM
+          tc_fence_after();
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {  // 16-byte chunk (8 keys), XOR-swizzled with row%8 (SWIZZLE_128B)
-        const uint32_t addr = p_row + (uint32_t)((g ^ sw) << 4);
-        const uint32_t w0 = pack_bf16x2(s[8 * g + 0], s[8 * g + 1]), w1 = pack_bf16x2(s[8 * g + 2], s[8 * g + 3]);
-        const uint32_t w2 = pack_bf16x2(s[8 * g + 4], s[8 * g + 5]), w3 = pack_bf16x2(s[8 * g + 6], s[8 * g + 7]);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3)
-                     : "memory");
-      }
-      tc_fence_before();
-      fence_proxy_async_smem();
-      mbar_arrive(bar_p(b));
-    }
-    // ---- epilogue: O / l -> bf16, staged through smem (P buffers are free) for coalesced 128-byte rows ----
-    mbar_wait(bar_pv((n_kt - 1) & 1), ((n_kt - 1) >> 1) & 1);
-    tc_fence_after();
-    const float inv = 1.f / l_run;
-    uint8_t* stg = smem_raw + (sP - smem_u32(smem_raw)) + warp * (32 * ATT_OSTG_LD);
+          for (int c = 0; c < 2; ++c) {
+            float o[32];
+            __syncwarp();
+            tmem_ld_32x32(tmem_o + lane_off + c * 32, o);
+            tmem_ld_wait_dep(o);
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      float o[32];
+            for (int i = 0; i < 32; ++i) o[i] *= f;
+            tmem_st_32x32(tmem_o + lane_off + c * 32, o);
+          }
+          tmem_st_wait();
+          l_run *= f;
+          if (need) m_ref2 = mx2;
+        }
+        float l_tile = 0.f;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+          s[i] = fast_exp2(fmaf(s[i], LOG2E, -m_ref2));  // masked entries: exp2(-inf) = 0
+          l_tile += s[i];
+        }
+        l_run += l_tile;
+        if (g >= 2) mbar_wait(bar_pv(b), ((g - 2) >> 1) & 1);  // P buffer b was read by the P V of tile g-2
+        const uint32_t p_row = sP + b * ATT_P_BYTES + (uint32_t)(warp * 32 + lane) * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {  // 16-byte chunk (8 keys), XOR-swizzled with row%8 (SWIZZLE_128B)
+          const uint32_t addr = p_row + (uint32_t)((c ^ sw) << 4);
+          const uint32_t w0 = pack_bf16x2(s[8 * c + 0], s[8 * c + 1]), w1 = pack_bf16x2(s[8 * c + 2], s[8 * c + 3]);
+          const uint32_t w2 = pack_bf16x2(s[8 * c + 4], s[8 * c + 5]), w3 = pack_bf16x2(s[8 * c + 6], s[8 * c + 7]);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3)
+                       : "memory");
+        }
+        tc_fence_before();
+        fence_proxy_async_smem();
+        mbar_arrive(bar_p(b));
+      }
+      // ---- item epilogue: O / l -> bf16, staged through this warp's own rows of P[0] for coalesced 128-byte rows ----
+      const int g_last = G + n_kt - 1;
+      mbar_wait(bar_pv(g_last & 1), (g_last >> 1) & 1);  // all P V of this item (and everything before) complete
+      tc_fence_after();
+      const float inv = 1.f / l_run;
+      float o[64];
       __syncwarp();
-      tmem_ld_32x32(tmem_o + lane_off + c * 32, o);
+      tmem_ld_32x32(tmem_o + lane_off, o);
+      tmem_ld_32x32(tmem_o + lane_off + 32, o + 32);
       tmem_ld_wait_dep(o);
-      uint4* d4 = reinterpret_cast<uint4*>(stg + lane * ATT_OSTG_LD + c * 64);
+      tmem_ld_wait_dep(o + 32);
+      tc_fence_before();
+      mbar_arrive(bar_oread);  // the issuer may overwrite O with the next item's first P V
+      const uint32_t stg = sP + (uint32_t)(warp * 32) * 128;  // rows of this warp inside P[0]: no other warp writes them
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint4 w;
-        w.x = pack_bf16x2(o[8 * g + 0] * inv, o[8 * g + 1] * inv);
-        w.y = pack_bf16x2(o[8 * g + 2] * inv, o[8 * g + 3] * inv);
-        w.z = pack_bf16x2(o[8 * g + 4] * inv, o[8 * g + 5] * inv);
-        w.w = pack_bf16x2(o[8 * g + 6] * inv, o[8 * g + 7] * inv);
-        d4[g] = w;
+      for (int c = 0; c < 8; ++c) {
+        const uint32_t addr = stg + (uint32_t)lane * 128 + (uint32_t)((c ^ sw) << 4);
+        const uint32_t w0 = pack_bf16x2(o[8 * c + 0] * inv, o[8 * c + 1] * inv);
+        const uint32_t w1 = pack_bf16x2(o[8 * c + 2] * inv, o[8 * c + 3] * inv);
+        const uint32_t w2 = pack_bf16x2(o[8 * c + 4] * inv, o[8 * c + 5] * inv);
+        const uint32_t w3 = pack_bf16x2(o[8 * c + 6] * inv, o[8 * c + 7] * inv);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
       }
-    }
-    __syncwarp();
-    const int rsub = lane >> 3, ch = lane & 7;
+      __syncwarp();
+      const int rsub = lane >> 3, ch = lane & 7;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = rsub + 4 * i;
-      const int rg = row0 + warp * 32 + r;
-      if (rg < Lq) {
-        uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)seq * Lq + rg) * (size_t)(H * ATT_D) + head * ATT_D);
-        dst[ch] = *reinterpret_cast<const uint4*>(stg + r * ATT_OSTG_LD + ch * 16);
+      for (int i = 0; i < 8; ++i) {
+        const int r = rsub + 4 * i;
+        const int rg = cur.row0 + warp * 32 + r;
+        uint32_t w0, w1, w2, w3;
+        const uint32_t addr = stg + (uint32_t)r * 128 + (uint32_t)((ch ^ (r & 7)) << 4);
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(addr) : "memory");
+        if (rg < Lq) {
+          uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)seq * Lq + rg) * (size_t)(H * ATT_D) + head * ATT_D);
+          dst[ch] = make_uint4(w0, w1, w2, w3);
+        }
       }
+      __syncwarp();  // staging reads done before this warp's next P writes
+      G += n_kt;
+      next_item(cur);
     }
   }
   tc_fence_before();
@@ -275,7 +335,6 @@ int attn_launch(const AttnArgs& a, cudaStream_t st) {
              a.q_pos0, a.q_pos0 + a.Lq, a.level_end[a.n_scales - 1]);
   VB_REQUIRE(a.level_end[a.n_scales - 1] <= a.Lmax, "attn: sequence %d exceeds cache rows %d", a.level_end[a.n_scales - 1],
              a.Lmax);
-  VB_REQUIRE(a.n_seq <= 65535 && a.H <= 65535, "attn: grid too large");
   AttnLevels lv;
   lv.n = a.n_scales;
   for (int i = 0; i < VB_MAX_SCALES; ++i) lv.end[i] = i < a.n_scales ? a.level_end[i] : a.level_end[a.n_scales - 1];
@@ -302,9 +361,12 @@ int attn_launch(const AttnArgs& a, cudaStream_t st) {
     VB_CUDA_CHECK(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     attr_set = true;
   }
-  dim3 grid((a.Lq + ATT_BM - 1) / ATT_BM, a.H, a.n_seq);
+  const int n_qt = (a.Lq + ATT_BM - 1) / ATT_BM;
+  const long long total = (long long)n_qt * a.H * a.n_seq;
+  VB_REQUIRE(total < (1ll << 31), "attn: too many work items");
+  const int grid = (int)(total < 2ll * sm_count() ? total : 2ll * sm_count());
   attn_kernel<<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, reinterpret_cast<__nv_bfloat16*>(a.out), a.Lq, a.H,
-                                                   a.q_pos0, lv);
+                                                   a.q_pos0, lv, n_qt, (int)total);
   VB_CUDA_CHECK(cudaGetLastError());
   vb::count_launch();
   return VB_OK;
