@@ -57,7 +57,7 @@ struct AttnItem {
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
             const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, int Lq, int H, int q_pos0,
-            const AttnLevels lv, int n_qt, int total_items) {
+            const __grid_constant__ AttnLevels lv, int n_qt, int total_items) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bars[2 + 2 * ATT_KST + 6];  // q | oread | k[3] | v[3] | s[2] | p[2] | pv[2]
   __shared__ uint32_t tmem_base_smem;
@@ -75,10 +75,11 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   auto bar_pv = [&](int s) { return smem_u32(&bars[6 + 2 * ATT_KST + s]); };
 
   auto kv_end_of = [&](int row) {  // visible keys of query row `row` of this call's query block
+    // lv.end is padded with the sequence length up to VB_MAX_SCALES: fixed trip count, constant-bank operands
     const int pos = q_pos0 + (row < Lq ? row : Lq - 1);
-    int e = lv.end[lv.n - 1];
-    for (int s = lv.n - 1; s >= 0; --s)
-      if (pos < lv.end[s]) e = lv.end[s];
+    int e = lv.end[VB_MAX_SCALES - 1];
+#pragma unroll
+    for (int s = VB_MAX_SCALES - 2; s >= 0; --s) e = (pos < lv.end[s]) ? lv.end[s] : e;
     return e;
   };
   auto decode = [&](AttnItem& c) {
@@ -223,10 +224,11 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         tmem_ld_32x32(tmem + lane_off + b * 64 + 32, s + 32);
         tmem_ld_wait_dep(s);
         tmem_ld_wait_dep(s + 32);
-        const bool partial = k0 + ATT_BN > kv_end;  // this row does not see the whole tile
+        const int lim = kv_end - k0;     // keys [0, lim) of this tile are visible to this row
+        const bool partial = lim < ATT_BN;
         if (partial) {
 #pragma unroll
-          for (int i = 0; i < 64; ++i) s[i] = (k0 + i < kv_end) ? s[i] : -INFINITY;
+          for (int i = 0; i < 64; ++i) s[i] = (i < lim) ? s[i] : -INFINITY;
         }
         if (j == 0) {  // reference maximum = row maximum of the first key tile (finite: key 0 is always visible)
           float mx = fmaxf(s[0], s[1]);
@@ -259,7 +261,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
           tmem_ld_wait_dep(s + 32);
           if (partial) {
 #pragma unroll
-            for (int i = 0; i < 64; ++i) s[i] = (k0 + i < kv_end) ? s[i] : -INFINITY;
+            for (int i = 0; i < 64; ++i) s[i] = (i < lim) ? s[i] : -INFINITY;
           }
           float mx = s[0];
 #pragma unroll
