@@ -35,6 +35,15 @@ extern "C" {
 VAR_B200_API const char* var_b200_last_error(void);
 /* Number of kernels this library has launched so far in the process. */
 VAR_B200_API long long var_b200_launch_count(void);
+/* Per-kernel CUDA-event timing (measurement aid for bench.py): between _begin and _end every kernel this library
+ * launches is bracketed by events on its stream; _end synchronises the device and returns the summed milliseconds
+ * and launch counts per kernel class (index = VAR_B200_PK_*). */
+enum { VAR_B200_PK_GEMM_BIAS_F32 = 0, VAR_B200_PK_GEMM_BIAS_BF16, VAR_B200_PK_GEMM_GELU, VAR_B200_PK_GEMM_GATE_RESID,
+       VAR_B200_PK_GEMM_QKV, VAR_B200_PK_GEMM_SCORE, VAR_B200_PK_ATTN, VAR_B200_PK_LN, VAR_B200_PK_EMBED,
+       VAR_B200_PK_COND, VAR_B200_PK_SAMPLE, VAR_B200_PK_QUANT, VAR_B200_PK_SCORE_FIN, VAR_B200_PK_OTHER,
+       VAR_B200_PK_COUNT };
+VAR_B200_API void var_b200_profile_begin(void);
+VAR_B200_API int var_b200_profile_end(double* ms_by_kind /* host */, long long* n_by_kind /* host */, int n_kinds);
 
 /* ------------------------------------------------------------------------------------------------
  * GEMM family:  D[M,N] = A[M,K] * W[N,K]^T, bf16 operands, fp32 accumulation on tcgen05/TMEM.

@@ -399,6 +399,7 @@ int attn_launch(const AttnArgs& a, cudaStream_t st) {
   // One item per CTA: measured faster than persistent CTAs with static striding (649 vs 510 us on the d16 scoring
   // shape) because item costs vary 3..11 key tiles; the kernel's item loop is kept for a dynamic scheduler.
   const int grid = (int)total;
+  vb::ProfScope prof_scope(vb::PK_ATTN, st);
   attn_kernel<<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, reinterpret_cast<__nv_bfloat16*>(a.out), a.Lq, a.H,
                                                    a.q_pos0, lv, n_qt, (int)total);
   VB_CUDA_CHECK(cudaGetLastError());

@@ -86,6 +86,7 @@ int ln_modulate(const float* x, const float* scale, const float* shift, int ada_
   VB_REQUIRE(ada_ld % 4 == 0 && M / rows_per_seq <= 65535, "ln_modulate: bad ada_ld=%d or too many sequences", ada_ld);
   dim3 grid((rows_per_seq + LN_ROWS - 1) / LN_ROWS, M / rows_per_seq);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+  vb::ProfScope prof_scope(vb::PK_LN, st);
   if (C <= 1024)
     ln_modulate_kernel<8><<<grid, 256, (size_t)C * 8, st>>>(x, scale, shift, ada_ld, rows_per_seq, o, C, eps);
   else if (C <= 2048)
@@ -112,6 +113,7 @@ __global__ void cond_silu_kernel(const float* __restrict__ class_emb, const int*
 
 int cond_silu(const float* class_emb, const int* labels, void* out, int n_seq, int C, cudaStream_t st) {
   VB_REQUIRE(class_emb && labels && out && n_seq > 0, "cond_silu: bad arguments");
+  vb::ProfScope prof_scope(vb::PK_COND, st);
   cond_silu_kernel<<<n_seq, 256, 0, st>>>(class_emb, labels, reinterpret_cast<__nv_bfloat16*>(out), n_seq, C);
   VB_CUDA_CHECK(cudaGetLastError());
   vb::count_launch();
@@ -128,6 +130,7 @@ __global__ void expand_shared_aln_kernel(const float* __restrict__ shared, int s
 
 int expand_shared_aln(const float* shared, int shared_ld, const float* gss, float* ada, int ada_ld, int depth, int C,
                       int n_seq, cudaStream_t st) {
+  vb::ProfScope prof_scope(vb::PK_OTHER, st);
   expand_shared_aln_kernel<<<dim3(depth, n_seq), 256, 0, st>>>(shared, shared_ld, gss, ada, ada_ld, depth, 6 * C);
   VB_CUDA_CHECK(cudaGetLastError());
   vb::count_launch();
@@ -190,6 +193,7 @@ int embed_tokens(const float* x_in, int n_x, int l_in, const int* labels, const 
   const int n_rows = n_seq * l;
   dim3 grid((C + 255) / 256, (n_rows + EMB_ROWS - 1) / EMB_ROWS);
   VB_REQUIRE(grid.y <= 65535, "embed: too many rows (%d)", n_rows);
+  vb::ProfScope prof_scope(vb::PK_EMBED, st);
   embed_kernel<<<grid, 256, 0, st>>>(x_in, n_x > 0 ? n_x : 1, l_in, labels, class_emb, pos_start, lvl_pos, w_word_t, b_word,
                                      out, n_rows, l, first_rows, pos0, C);
   VB_CUDA_CHECK(cudaGetLastError());
@@ -253,6 +257,7 @@ int score_finalize(const void* part, int n_tiles, const float* gt_logit, int n_s
   AttnLevelsPOD lv;
   lv.n = n_scales;
   for (int i = 0; i < VB_MAX_SCALES; ++i) lv.end[i] = level_end[i < n_scales ? i : n_scales - 1];
+  vb::ProfScope prof_scope(vb::PK_SCORE_FIN, st);
   score_finalize_kernel<<<n_seq, 256, 0, st>>>(reinterpret_cast<const float2*>(part), n_tiles, gt_logit, L, lv, tok_logp,
                                                per_scale, total, first_pos);
   VB_CUDA_CHECK(cudaGetLastError());

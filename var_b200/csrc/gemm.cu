@@ -47,6 +47,7 @@ static int launch_one(const void* A, const void* W, const GemmParams& p, cudaStr
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  vb::ProfScope prof_scope(EPI, st);
   VB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
   VB_CUDA_CHECK(cudaGetLastError());
   vb::count_launch();

@@ -10,6 +10,7 @@
 #include <mutex>
 #include <string>
 #include <unordered_map>
+#include <vector>
 
 #include "common.cuh"
 
@@ -103,6 +104,30 @@ int make_tmap_bf16_sw128(CUtensorMap* out, const void* gptr, int rank, const uin
 static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// ---------------------------------------------------------------- per-kernel event timing
+struct ProfRec {
+  int kind;
+  cudaEvent_t a, b;
+};
+static bool g_prof_on = false;
+static std::vector<ProfRec*> g_prof;
+static std::mutex g_prof_mu;
+
+ProfScope::ProfScope(int k, cudaStream_t s) : kind(k), st(s), rec(nullptr) {
+  if (!g_prof_on) return;
+  ProfRec* r = new ProfRec{k, nullptr, nullptr};
+  if (cudaEventCreate(&r->a) != cudaSuccess || cudaEventCreate(&r->b) != cudaSuccess) { delete r; return; }
+  cudaEventRecord(r->a, s);
+  rec = r;
+}
+ProfScope::~ProfScope() {
+  if (!rec) return;
+  ProfRec* r = static_cast<ProfRec*>(rec);
+  cudaEventRecord(r->b, st);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof.push_back(r);
+}
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -117,3 +142,27 @@ int sm_count() {
 
 extern "C" const char* var_b200_last_error(void) { return vb::get_error(); }
 extern "C" long long var_b200_launch_count(void) { return vb::g_launches.load(); }
+
+extern "C" void var_b200_profile_begin(void) {
+  std::lock_guard<std::mutex> lk(vb::g_prof_mu);
+  for (auto* r : vb::g_prof) { cudaEventDestroy(r->a); cudaEventDestroy(r->b); delete r; }
+  vb::g_prof.clear();
+  vb::g_prof_on = true;
+}
+
+extern "C" int var_b200_profile_end(double* ms_by_kind, long long* n_by_kind, int n_kinds) {
+  vb::g_prof_on = false;
+  if (cudaDeviceSynchronize() != cudaSuccess) return vb::VB_ERR_CUDA;
+  std::lock_guard<std::mutex> lk(vb::g_prof_mu);
+  for (int i = 0; i < n_kinds; ++i) { ms_by_kind[i] = 0.0; n_by_kind[i] = 0; }
+  for (auto* r : vb::g_prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r->a, r->b) == cudaSuccess && r->kind < n_kinds) {
+      ms_by_kind[r->kind] += ms;
+      n_by_kind[r->kind] += 1;
+    }
+    cudaEventDestroy(r->a); cudaEventDestroy(r->b); delete r;
+  }
+  vb::g_prof.clear();
+  return vb::VB_OK;
+}

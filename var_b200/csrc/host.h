@@ -18,6 +18,20 @@ int sm_count();
 // number of kernels this library has launched in the process (bench.py's gpu_launches claim)
 void count_launch(int n = 1);
 
+// Optional per-kernel CUDA-event timing (var_b200_profile_begin / _end): every launcher opens a ProfScope on its
+// stream; when profiling is off this is two predictable branches.
+enum ProfKind : int {
+  PK_GEMM_BIAS_F32 = 0, PK_GEMM_BIAS_BF16, PK_GEMM_GELU, PK_GEMM_GATE_RESID, PK_GEMM_QKV, PK_GEMM_SCORE,
+  PK_ATTN, PK_LN, PK_EMBED, PK_COND, PK_SAMPLE, PK_QUANT, PK_SCORE_FIN, PK_OTHER, PK_COUNT
+};
+struct ProfScope {
+  int kind;
+  cudaStream_t st;
+  void* rec;
+  ProfScope(int kind, cudaStream_t st);
+  ~ProfScope();
+};
+
 #define VB_CUDA_CHECK(expr)                                                                  \
   do {                                                                                       \
     cudaError_t _e = (expr);                                                                 \

@@ -346,6 +346,7 @@ int quant_launch(const QuantArgs& a, cudaStream_t st) {
     VB_CUDA_CHECK(cudaFuncSetAttribute(quant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
+  vb::ProfScope prof_scope(vb::PK_QUANT, st);
   quant_kernel<<<a.B, QT, smem, st>>>(p);
   VB_CUDA_CHECK(cudaGetLastError());
   vb::count_launch();

@@ -188,6 +188,7 @@ int sample_launch(const SampleArgs& a, cudaStream_t st) {
     attr = smem;
   }
   const float opt = (float)(1.0 + a.t), tf = (float)a.t;
+  vb::ProfScope prof_scope(vb::PK_SAMPLE, st);
   sample_kernel<<<a.B * a.l, ST, smem, st>>>(a.logits, a.B, a.l, a.V, a.use_cfg, opt, tf, a.q, a.top_k, a.top_p, (float)(1.0 - (double)a.top_p),
                                              reinterpret_cast<long long*>(a.idx_out), a.mixed_out, use_p ? vp2 : 0);
   VB_CUDA_CHECK(cudaGetLastError());

@@ -78,6 +78,10 @@ def load() -> C.CDLL:
     lib.var_b200_last_error.argtypes = []
     lib.var_b200_launch_count.restype = C.c_longlong
     lib.var_b200_launch_count.argtypes = []
+    lib.var_b200_profile_begin.restype = None
+    lib.var_b200_profile_begin.argtypes = []
+    lib.var_b200_profile_end.restype = C.c_int
+    lib.var_b200_profile_end.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]
     _declare(lib)
     _lib = lib
     return lib
@@ -124,6 +128,26 @@ def _EXTRA_SIGS(vp, i32, i64, f32):
         "var_b200_head_logits": [C.POINTER(ModelDesc), vp, vp, i32, i32, vp, vp, sz, vp],
         "var_b200_head_score": [C.POINTER(ModelDesc), vp, vp, i32, i32, vp, i32, i32, vp, vp, vp, vp, sz, vp],
     }
+
+
+PROF_KINDS = ["gemm_bias_f32", "gemm_bias_bf16", "gemm_gelu", "gemm_gate_resid", "gemm_qkv", "gemm_score", "attn", "ln_modulate",
+              "embed", "cond_silu", "sample", "quant", "score_finalize", "other"]
+
+
+class kernel_profile:
+    """Context manager: CUDA-event time of every kernel class launched inside the block -> .ms / .n dicts."""
+
+    def __enter__(self):
+        load().var_b200_profile_begin()
+        return self
+
+    def __exit__(self, *exc):
+        n = len(PROF_KINDS)
+        ms, cnt = (C.c_double * n)(), (C.c_longlong * n)()
+        check(load().var_b200_profile_end(ms, cnt, n), "profile_end")
+        self.ms = {k: ms[i] for i, k in enumerate(PROF_KINDS) if cnt[i]}
+        self.n = {k: cnt[i] for i, k in enumerate(PROF_KINDS) if cnt[i]}
+        return False
 
 
 def check(rc: int, what: str = "") -> None:
