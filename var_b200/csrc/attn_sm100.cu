@@ -27,11 +27,13 @@ constexpr int ATT_BM = 128;  // query rows per CTA
 constexpr int ATT_BN = 64;   // keys per tile
 constexpr int ATT_D = 64;    // head dim
 constexpr int ATT_THREADS = 288;   // 8 softmax warps + 1 issuer warp
-constexpr int ATT_KST = 3;                        // K / V ring depth
+constexpr int ATT_KST = 4;                        // K ring depth (QK runs two tiles ahead of the softmax)
+constexpr int ATT_VST = 3;                        // V ring depth
+constexpr int ATT_SST = 3;                        // S buffers in TMEM
 constexpr int ATT_Q_BYTES = ATT_BM * ATT_D * 2;   // 16 KB
 constexpr int ATT_KV_BYTES = ATT_BN * ATT_D * 2;  // 8 KB
 constexpr int ATT_P_BYTES = ATT_BM * ATT_BN * 2;  // 16 KB
-constexpr int ATT_SMEM = ATT_Q_BYTES + 2 * ATT_KST * ATT_KV_BYTES + 2 * ATT_P_BYTES + 1024;
+constexpr int ATT_SMEM = ATT_Q_BYTES + (ATT_KST + ATT_VST) * ATT_KV_BYTES + 2 * ATT_P_BYTES + 1024;
 constexpr float ATT_RESCALE_LOG2 = 80.f;
 
 struct AttnLevels {
@@ -60,21 +62,21 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
             const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, int Lq, int H, int q_pos0,
             const __grid_constant__ AttnLevels lv, int n_qt, int total_items) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t bars[2 + 2 * ATT_KST + 6];  // q | oread | k[3] | v[3] | s[2] | p[2] | pv[2]
+  __shared__ uint64_t bars[2 + ATT_KST + ATT_VST + ATT_SST + 4];  // q | oread | k[] | v[] | s[] | p[2] | pv[2]
   __shared__ uint32_t tmem_base_smem;
   __shared__ float xch[2][ATT_BM];  // row max / row sum exchange between the two warps of a lane quarter
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = base;
   const uint32_t sK = sQ + ATT_Q_BYTES;
   const uint32_t sV = sK + ATT_KST * ATT_KV_BYTES;
-  const uint32_t sP = sV + ATT_KST * ATT_KV_BYTES;
+  const uint32_t sP = sV + ATT_VST * ATT_KV_BYTES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar_q = smem_u32(&bars[0]), bar_oread = smem_u32(&bars[1]);
   auto bar_k = [&](int s) { return smem_u32(&bars[2 + s]); };
   auto bar_v = [&](int s) { return smem_u32(&bars[2 + ATT_KST + s]); };
-  auto bar_s = [&](int s) { return smem_u32(&bars[2 + 2 * ATT_KST + s]); };
-  auto bar_p = [&](int s) { return smem_u32(&bars[4 + 2 * ATT_KST + s]); };
-  auto bar_pv = [&](int s) { return smem_u32(&bars[6 + 2 * ATT_KST + s]); };
+  auto bar_s = [&](int s) { return smem_u32(&bars[2 + ATT_KST + ATT_VST + s]); };
+  auto bar_p = [&](int s) { return smem_u32(&bars[2 + ATT_KST + ATT_VST + ATT_SST + s]); };
+  auto bar_pv = [&](int s) { return smem_u32(&bars[4 + ATT_KST + ATT_VST + ATT_SST + s]); };
 
   auto kv_end_of = [&](int row) {  // visible keys of query row `row` of this call's query block
     // lv.end is padded with the sequence length up to VB_MAX_SCALES: fixed trip count, constant-bank operands
@@ -107,8 +109,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     tma_prefetch_desc(&tmV);
     mbar_init(bar_q, 1);
     mbar_init(bar_oread, 256);
-    for (int s = 0; s < ATT_KST; ++s) { mbar_init(bar_k(s), 1); mbar_init(bar_v(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(bar_s(s), 1); mbar_init(bar_p(s), 256); mbar_init(bar_pv(s), 1); }
+    for (int s = 0; s < ATT_KST; ++s) mbar_init(bar_k(s), 1);
+    for (int s = 0; s < ATT_VST; ++s) mbar_init(bar_v(s), 1);
+    for (int s = 0; s < ATT_SST; ++s) mbar_init(bar_s(s), 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(bar_p(s), 256); mbar_init(bar_pv(s), 1); }
     mbar_fence_init();
   }
   if (warp == 8) tmem_alloc(smem_u32(&tmem_base_smem), 256);
@@ -116,7 +120,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_smem;
-  const uint32_t tmem_o = tmem + 128;
+  const uint32_t tmem_o = tmem + ATT_SST * 64;  // S ring in columns [0,192), O in [192,256)
 
   if (warp == 8) {
     if (lane == 0) {
@@ -134,7 +138,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         ++kpos;
       };
       auto load_v = [&]() {
-        const int st = vpos % ATT_KST;
+        const int st = vpos % ATT_VST;
         mbar_expect_tx(bar_v(st), ATT_KV_BYTES);
         tma_load_3d(&tmV, bar_v(st), sV + st * ATT_KV_BYTES, 0, vc.j * ATT_BN, vc.bh);
         next_tile(vc);
@@ -144,10 +148,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         mbar_expect_tx(bar_q, ATT_Q_BYTES);
         tma_load_3d(&tmQ, bar_q, sQ, 0, cur.row0, cur.bh);
       }
-      for (int i = 0; i < ATT_KST; ++i) {
+      for (int i = 0; i < ATT_KST; ++i)
         if (kc.item < total_items) load_k();
+      for (int i = 0; i < ATT_VST; ++i)
         if (vc.item < total_items) load_v();
-      }
       const uint64_t qd = umma_desc_k_sw128(sQ);
       auto issue_qk = [&](int g) {  // g: global key-tile index of this CTA
         const int st = g % ATT_KST;
@@ -155,21 +159,24 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         tc_fence_after();
         const uint64_t kd = umma_desc_k_sw128(sK + st * ATT_KV_BYTES);
 #pragma unroll
-        for (int k = 0; k < ATT_D / 16; ++k) umma_bf16_ss(tmem + (g & 1) * 64, qd + 2 * k, kd + 2 * k, idesc_qk, k != 0);
-        umma_commit(bar_s(g & 1));
+        for (int k = 0; k < ATT_D / 16; ++k)
+          umma_bf16_ss(tmem + (g % ATT_SST) * 64, qd + 2 * k, kd + 2 * k, idesc_qk, k != 0);
+        umma_commit(bar_s(g % ATT_SST));
       };
       int G = 0, it = 0;
       while (cur.item < total_items) {
         const int n_kt = cur.n_kt;
         mbar_wait(bar_q, it & 1);
+        // QK runs two tiles ahead of the softmax (the tcgen05 issue->commit->mbarrier round trip is ~1 us)
         issue_qk(G);
+        if (n_kt > 1) issue_qk(G + 1);
         for (int j = 0; j < n_kt; ++j) {
           const int g = G + j;
-          // S[(g+1)&1] was last read by the softmax of tile g-1, whose bar_p this thread has already observed
-          if (j + 1 < n_kt) issue_qk(g + 1);
+          // S[(g+2)%3] was last read by the softmax of tile g-1, whose bar_p this thread has already observed
+          if (j + 2 < n_kt) issue_qk(g + 2);
           mbar_wait(bar_p(g & 1), (g >> 1) & 1);  // P_g written; QK_g therefore complete
           tc_fence_after();
-          if (kc.item < total_items) load_k();  // stream position g + 3 reuses the K stage of tile g
+          if (kc.item < total_items) load_k();  // stream position g + ATT_KST reuses the K stage of tile g
           if (j == n_kt - 1) {                  // last QK of this item has read sQ: fetch the next item's queries
             AttnItem nx = cur;
             next_item(nx);
@@ -178,8 +185,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
               tma_load_3d(&tmQ, bar_q, sQ, 0, nx.row0, nx.bh);
             }
           }
-          const int st = g % ATT_KST;
-          mbar_wait(bar_v(st), (g / ATT_KST) & 1);
+          const int st = g % ATT_VST;
+          mbar_wait(bar_v(st), (g / ATT_VST) & 1);
           if (j == 0 && it > 0) mbar_wait(bar_oread, (it - 1) & 1);  // previous item's output has left TMEM
           tc_fence_after();
           const uint64_t pd = umma_desc_k_sw128(sP + (g & 1) * ATT_P_BYTES);
@@ -221,11 +228,12 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       for (int j = 0; j < n_kt; ++j) {
         const int g = G + j;
         const int b = g & 1;
-        mbar_wait(bar_s(b), (g >> 1) & 1);
+        const int sb = g % ATT_SST;
+        mbar_wait(bar_s(sb), (g / ATT_SST) & 1);
         tc_fence_after();
         float s[32];
         __syncwarp();
-        tmem_ld_32x32(tmem + lane_off + b * 64 + half * 32, s);
+        tmem_ld_32x32(tmem + lane_off + sb * 64 + half * 32, s);
         tmem_ld_wait_dep(s);
         const int lim = kv_end - j * ATT_BN - half * 32;  // keys [0, lim) of this warp's 32 columns are visible
         if (lim < 32) {
