@@ -7,9 +7,9 @@
 // largest level end among its 128 query rows and masks per row inside the last tiles. The KV-cached decode step
 // (attn_bias=None, keys = all cached + current scale) is the same kernel with every query on the newest level.
 //
-// One CTA = 128 query rows of one (sequence, head). Warps 0-7: softmax; warps w and w+4 share the 32 rows of TMEM
-// lane quarter w&3 and split the 64 keys of every tile (and the 64 output columns) in halves; warp 8: TMA producer +
-// UMMA issuer (one elected thread).
+// One CTA = 128 query rows of one (sequence, head). Warps 0-3: softmax (one row per thread == one TMEM lane),
+// warp 4: TMA producer + UMMA issuer (one elected thread). (An 8-warp variant that split the keys of a tile between
+// warp pairs measured no faster: the kernel is bound by the per-tile issue/commit/mbarrier round trips.)
 //   S_j = Q K_j^T : UMMA 128x64x16 x4, Q and K tiles K-major SW128 in smem, S double-buffered in TMEM [0,64),[64,128)
 //   P_j = exp2(..): registers -> bf16 -> smem (K-major SW128, A operand of the second MMA), double-buffered
 //   O  += P_j V_j : UMMA 128x64x16 x4, V tile in its natural [key, d] layout = MN-major B operand, TMEM [128,192)
@@ -26,7 +26,7 @@ namespace vb {
 constexpr int ATT_BM = 128;  // query rows per CTA
 constexpr int ATT_BN = 64;   // keys per tile
 constexpr int ATT_D = 64;    // head dim
-constexpr int ATT_THREADS = 288;   // 8 softmax warps + 1 issuer warp
+constexpr int ATT_THREADS = 160;   // 4 softmax warps + 1 issuer warp
 constexpr int ATT_KST = 4;                        // K ring depth (QK runs two tiles ahead of the softmax)
 constexpr int ATT_VST = 3;                        // V ring depth
 constexpr int ATT_SST = 3;                        // S buffers in TMEM
@@ -64,7 +64,6 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bars[2 + ATT_KST + ATT_VST + ATT_SST + 4];  // q | oread | k[] | v[] | s[] | p[2] | pv[2]
   __shared__ uint32_t tmem_base_smem;
-  __shared__ float xch[2][ATT_BM];  // row max / row sum exchange between the two warps of a lane quarter
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = base;
   const uint32_t sK = sQ + ATT_Q_BYTES;
@@ -108,21 +107,21 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     mbar_init(bar_q, 1);
-    mbar_init(bar_oread, 256);
+    mbar_init(bar_oread, 4);   // one arrive per softmax warp
     for (int s = 0; s < ATT_KST; ++s) mbar_init(bar_k(s), 1);
     for (int s = 0; s < ATT_VST; ++s) mbar_init(bar_v(s), 1);
     for (int s = 0; s < ATT_SST; ++s) mbar_init(bar_s(s), 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(bar_p(s), 256); mbar_init(bar_pv(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(bar_p(s), 4); mbar_init(bar_pv(s), 1); }
     mbar_fence_init();
   }
-  if (warp == 8) tmem_alloc(smem_u32(&tmem_base_smem), 256);
+  if (warp == 4) tmem_alloc(smem_u32(&tmem_base_smem), 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_smem;
   const uint32_t tmem_o = tmem + ATT_SST * 64;  // S ring in columns [0,192), O in [192,256)
 
-  if (warp == 8) {
+  if (warp == 4) {
     if (lane == 0) {
       constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_BM, ATT_BN);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BM, ATT_D) | (1u << 16);  // B (V) is MN-major
@@ -208,72 +207,50 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     }
   } else {
     // ------------------------------ softmax / output warps ------------------------------
-    const int quarter = warp & 3, half = warp >> 2;
-    const int rloc = quarter * 32 + lane;  // row inside the 128-row tile == TMEM lane
-    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
     const int sw = lane & 7;  // == row & 7
     constexpr float LOG2E = 1.4426950408889634f;
-    // the two warps of a quarter synchronise on a private named barrier (ids 1..4, 64 threads)
-    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory"); };
     AttnItem cur{(int)blockIdx.x, 0, 0, 0, 0};
     decode(cur);
     int G = 0;
     while (cur.item < total_items) {
       const int n_kt = cur.n_kt;
-      const int row = cur.row0 + rloc;
+      const int row = cur.row0 + warp * 32 + lane;
       const int kv_end = kv_end_of(row);
       const int head = cur.bh % H, seq = cur.bh / H;
-      float m_ref2 = 0.f;  // reference maximum of the row, pre-multiplied by log2(e)
-      float l_run = 0.f;   // this warp's share (its 32 key columns of every tile) of the row sum
+      float m_ref2 = 0.f;  // reference maximum, pre-multiplied by log2(e)
+      float l_run = 0.f;
       for (int j = 0; j < n_kt; ++j) {
         const int g = G + j;
+        const int k0 = j * ATT_BN;
         const int b = g & 1;
         const int sb = g % ATT_SST;
         mbar_wait(bar_s(sb), (g / ATT_SST) & 1);
         tc_fence_after();
-        float s[32];
+        float s[64];
         __syncwarp();
-        tmem_ld_32x32(tmem + lane_off + sb * 64 + half * 32, s);
+        tmem_ld_32x32(tmem + lane_off + sb * 64, s);
+        tmem_ld_32x32(tmem + lane_off + sb * 64 + 32, s + 32);
         tmem_ld_wait_dep(s);
-        const int lim = kv_end - j * ATT_BN - half * 32;  // keys [0, lim) of this warp's 32 columns are visible
-        if (lim < 32) {
+        tmem_ld_wait_dep(s + 32);
+        const int lim = kv_end - k0;     // keys [0, lim) of this tile are visible to this row
+        const bool partial = lim < ATT_BN;
+        if (partial) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) s[i] = (i < lim) ? s[i] : -INFINITY;
+          for (int i = 0; i < 64; ++i) s[i] = (i < lim) ? s[i] : -INFINITY;
         }
-        float mx = fmaxf(s[0], s[1]);
+        if (j == 0) {  // reference maximum = row maximum of the first key tile (finite: key 0 is always visible)
+          float mx = fmaxf(s[0], s[1]);
 #pragma unroll
-        for (int i = 2; i < 32; i += 2) mx = fmaxf(mx, fmaxf(s[i], s[i + 1]));
-        // row maximum over the whole 64-key tile: exchange with the partner warp
-        xch[half][rloc] = mx;
-        pair_sync();
-        const float mx2 = fmaxf(mx, xch[half ^ 1][rloc]) * LOG2E;
-        pair_sync();  // both reads done before the next write
-        if (j == 0) {
-          m_ref2 = mx2;  // finite: key 0 is visible to every query
-        } else if (__any_sync(0xffffffffu, mx2 - m_ref2 > ATT_RESCALE_LOG2)) {
-          // rare (needs a per-head scale > 27): rebase this warp's 32 accumulator columns of the overflowing rows.
-          // The partner warp sees the same row maxima, takes the same branch for the same rows.
-          const bool need = mx2 - m_ref2 > ATT_RESCALE_LOG2;
-          const float f = need ? exp2f(m_ref2 - mx2) : 1.f;
-          mbar_wait(bar_pv((g - 1) & 1), ((g - 1) >> 1) & 1);  // every earlier P V of this item has landed in TMEM
-          tc_fence_after();
-          float o[32];
-          __syncwarp();
-          tmem_ld_32x32(tmem_o + lane_off + half * 32, o);
-          tmem_ld_wait_dep(o);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] *= f;
-          tmem_st_32x32(tmem_o + lane_off + half * 32, o);
-          tmem_st_wait();
-          l_run *= f;
-          if (need) m_ref2 = mx2;
+          for (int i = 2; i < 64; i += 2) mx = fmaxf(mx, fmaxf(s[i], s[i + 1]));
+          m_ref2 = mx * LOG2E;
         }
         // p = exp2(s*log2e - m_ref2), packed 2-wide FMA / ADD (sm_100 f32x2 pipes); masked entries give exp2(-inf) = 0
         float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
         {
           const float2 l2e = make_float2(LOG2E, LOG2E), nm = make_float2(-m_ref2, -m_ref2);
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
+          for (int i = 0; i < 64; i += 4) {
             float2 a = __ffma2_rn(make_float2(s[i], s[i + 1]), l2e, nm);
             float2 c2 = __ffma2_rn(make_float2(s[i + 2], s[i + 3]), l2e, nm);
             a.x = fast_exp2(a.x); a.y = fast_exp2(a.y); c2.x = fast_exp2(c2.x); c2.y = fast_exp2(c2.y);
@@ -282,12 +259,55 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
             s[i] = a.x; s[i + 1] = a.y; s[i + 2] = c2.x; s[i + 3] = c2.y;
           }
         }
-        l_run += (acc0.x + acc0.y) + (acc1.x + acc1.y);
-        if (g >= 2) mbar_wait(bar_pv(b), ((g - 2) >> 1) & 1);  // P buffer b was read by the P V of tile g-2
-        const uint32_t p_row = sP + b * ATT_P_BYTES + (uint32_t)rloc * 128;
+        float l_tile = (acc0.x + acc0.y) + (acc1.x + acc1.y);
+        // Overflow guard: a tile whose scores exceed the reference by more than 2^80 shows up as a huge (or inf) row
+        // sum. Rare (needs a per-head scale > 27): rebase the TMEM accumulator on this tile's maximum and redo the tile.
+        if (__any_sync(0xffffffffu, !(l_tile < 1.2e24f))) {
+          __syncwarp();
+          tmem_ld_32x32(tmem + lane_off + sb * 64, s);
+          tmem_ld_32x32(tmem + lane_off + sb * 64 + 32, s + 32);
+          tmem_ld_wait_dep(s);
+          tmem_ld_wait_dep(s + 32);
+          if (partial) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {  // 16-byte chunk (8 keys) half*4+c, XOR-swizzled with row%8 (SWIZZLE_128B)
-          const uint32_t addr = p_row + (uint32_t)(((half * 4 + c) ^ sw) << 4);
+            for (int i = 0; i < 64; ++i) s[i] = (i < lim) ? s[i] : -INFINITY;
+          }
+          float mx = s[0];
+#pragma unroll
+          for (int i = 1; i < 64; ++i) mx = fmaxf(mx, s[i]);
+          const float mx2 = mx * LOG2E;
+          const bool need = mx2 > m_ref2;
+          const float f = need ? exp2f(m_ref2 - mx2) : 1.f;
+          if (j > 0) {
+            mbar_wait(bar_pv((g - 1) & 1), ((g - 1) >> 1) & 1);  // every earlier P V of this item has landed in TMEM
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              float o[32];
+              __syncwarp();
+              tmem_ld_32x32(tmem_o + lane_off + c * 32, o);
+              tmem_ld_wait_dep(o);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] *= f;
+              tmem_st_32x32(tmem_o + lane_off + c * 32, o);
+            }
+            tmem_st_wait();
+          }
+          l_run *= f;
+          if (need) m_ref2 = mx2;
+          l_tile = 0.f;
+#pragma unroll
+          for (int i = 0; i < 64; ++i) {
+            s[i] = fast_exp2(fmaf(s[i], LOG2E, -m_ref2));
+            l_tile += s[i];
+          }
+        }
+        l_run += l_tile;
+        if (g >= 2) mbar_wait(bar_pv(b), ((g - 2) >> 1) & 1);  // P buffer b was read by the P V of tile g-2
+        const uint32_t p_row = sP + b * ATT_P_BYTES + (uint32_t)(warp * 32 + lane) * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {  // 16-byte chunk (8 keys), XOR-swizzled with row%8 (SWIZZLE_128B)
+          const uint32_t addr = p_row + (uint32_t)((c ^ sw) << 4);
           const uint32_t w0 = pack_bf16x2(s[8 * c + 0], s[8 * c + 1]), w1 = pack_bf16x2(s[8 * c + 2], s[8 * c + 3]);
           const uint32_t w2 = pack_bf16x2(s[8 * c + 4], s[8 * c + 5]), w3 = pack_bf16x2(s[8 * c + 6], s[8 * c + 7]);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3)
@@ -295,28 +315,27 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         }
         tc_fence_before();
         fence_proxy_async_smem();
-        mbar_arrive(bar_p(b));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_p(b));
       }
-      // ---- item epilogue: O / l -> bf16; this warp owns output columns [32*half, +32) of its 32 rows ----
-      xch[half][rloc] = l_run;
-      pair_sync();
-      const float inv = 1.f / (l_run + xch[half ^ 1][rloc]);
-      pair_sync();
+      // ---- item epilogue: O / l -> bf16, staged through this warp's own rows of P[0] for coalesced 128-byte rows ----
       const int g_last = G + n_kt - 1;
       mbar_wait(bar_pv(g_last & 1), (g_last >> 1) & 1);  // all P V of this item (and everything before) complete
       tc_fence_after();
-      float o[32];
+      const float inv = 1.f / l_run;
+      float o[64];
       __syncwarp();
-      tmem_ld_32x32(tmem_o + lane_off + half * 32, o);
+      tmem_ld_32x32(tmem_o + lane_off, o);
+      tmem_ld_32x32(tmem_o + lane_off + 32, o + 32);
       tmem_ld_wait_dep(o);
+      tmem_ld_wait_dep(o + 32);
       tc_fence_before();
-      mbar_arrive(bar_oread);  // the issuer may overwrite O with the next item's first P V
-      // staging inside this quarter's rows of P[0] (both P V readers of it are complete; the next P writes to these
-      // rows come from this warp pair only, after the copy-out below)
-      const uint32_t stg = sP + (uint32_t)(quarter * 32) * 128;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_oread);  // the issuer may overwrite O with the next item's first P V
+      const uint32_t stg = sP + (uint32_t)(warp * 32) * 128;  // rows of this warp inside P[0]: no other warp writes them
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const uint32_t addr = stg + (uint32_t)lane * 128 + (uint32_t)(((half * 4 + c) ^ sw) << 4);
+      for (int c = 0; c < 8; ++c) {
+        const uint32_t addr = stg + (uint32_t)lane * 128 + (uint32_t)((c ^ sw) << 4);
         const uint32_t w0 = pack_bf16x2(o[8 * c + 0] * inv, o[8 * c + 1] * inv);
         const uint32_t w1 = pack_bf16x2(o[8 * c + 2] * inv, o[8 * c + 3] * inv);
         const uint32_t w2 = pack_bf16x2(o[8 * c + 4] * inv, o[8 * c + 5] * inv);
@@ -324,27 +343,27 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
       }
       __syncwarp();
-      const int rsub = lane >> 2, ch = lane & 3;  // 8 rows x 64 bytes per instruction
+      const int rsub = lane >> 3, ch = lane & 7;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = rsub + 8 * i;
-        const int rg = cur.row0 + quarter * 32 + r;
+      for (int i = 0; i < 8; ++i) {
+        const int r = rsub + 4 * i;
+        const int rg = cur.row0 + warp * 32 + r;
         uint32_t w0, w1, w2, w3;
-        const uint32_t addr = stg + (uint32_t)r * 128 + (uint32_t)(((half * 4 + ch) ^ (r & 7)) << 4);
+        const uint32_t addr = stg + (uint32_t)r * 128 + (uint32_t)((ch ^ (r & 7)) << 4);
         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(addr) : "memory");
         if (rg < Lq) {
-          uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)seq * Lq + rg) * (size_t)(H * ATT_D) + head * ATT_D + half * 32);
+          uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)seq * Lq + rg) * (size_t)(H * ATT_D) + head * ATT_D);
           dst[ch] = make_uint4(w0, w1, w2, w3);
         }
       }
-      pair_sync();  // both warps' staging reads are done before either writes the next item's P rows
+      __syncwarp();  // staging reads done before this warp's next P writes
       G += n_kt;
       next_item(cur);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 4) {
     tc_fence_after();
     tmem_dealloc(tmem, 256);
   }
