@@ -247,6 +247,7 @@ def main():
     from var_b200 import build_vae_var, lib as L
     from var_b200.init_utils import dense_init_
     lib = L.load()
+    torch.backends.cudnn.benchmark = True  # CNN encoder/decoder (boundary helpers, cuDNN): let cuDNN pick its algorithms
     pk = peaks()
 
     def barrier():

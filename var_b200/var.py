@@ -178,6 +178,8 @@ class VAR(nn.Module):
 
     # ------------------------------------------------------------------ forward passes
     def _labels_i32(self, label_B: torch.Tensor, n: int) -> torch.Tensor:
+        if not label_B.is_cuda and label_B.numel() and (int(label_B.min()) < 0 or int(label_B.max()) > self.num_classes):
+            raise IndexError(f"class label out of range [0, {self.num_classes}] (class_emb, models/var.py:61)")
         lab = label_B.reshape(-1).to(device=self.lvl_1L.device, dtype=torch.int32)
         if lab.numel() == 1 and n > 1:
             lab = lab.expand(n)
@@ -200,10 +202,10 @@ class VAR(nn.Module):
         pm = self._model()
         B = x_BLCv_wo_first_l.shape[0]
         dev = self.lvl_1L.device
-        label_B = label_B.to(dev)
         # same RNG side effect and label dropout as the reference (var.py:201)
-        label_B = torch.where(torch.rand(B, device=dev) < self.cond_drop_rate, self.num_classes, label_B)
+        drop = torch.rand(B, device=dev) < self.cond_drop_rate
         labels = self._labels_i32(label_B, B)
+        labels = torch.where(drop, self.num_classes, labels).to(torch.int32).contiguous()
         x_in = x_BLCv_wo_first_l.to(dev).float().contiguous()
         x = pm.embed(x_in, B, labels, B, self.L, self.first_l, 0)
         ada = pm.ada_params(labels)
