@@ -11,8 +11,9 @@
 // warp 4: TMA producer + UMMA issuer (one elected thread). (An 8-warp variant that split the keys of a tile between
 // warp pairs measured no faster: the kernel is bound by the per-tile issue/commit/mbarrier round trips.)
 //   S_j = Q K_j^T : UMMA 128x64x16 x4, Q and K tiles K-major SW128 in smem, S double-buffered in TMEM [0,64),[64,128)
-//   P_j = exp2(..): registers -> bf16 -> smem (K-major SW128, A operand of the second MMA), double-buffered
-//   O  += P_j V_j : UMMA 128x64x16 x4, V tile in its natural [key, d] layout = MN-major B operand, TMEM [128,192)
+//   P_j = exp2(..): registers -> bf16 -> TMEM, overwriting the first 32 columns of S_j (tcgen05.st); the second MMA
+//                   takes its A operand straight from tensor memory (no smem round trip, no proxy fence)
+//   O  += P_j V_j : UMMA(TS) 128x64x16 x4, V tile in its natural [key, d] layout = MN-major B operand, TMEM [192,256)
 // The output accumulates in TMEM across key tiles against a per-row reference maximum fixed at the first tile
 // (q_hat.k_hat is bounded by the per-head scale <= 100, basic_var.py:101): softmax warps never wait for P V and the
 // tensor pipe runs QK_{j+1} under softmax_j. If a later tile exceeds the reference by more than 2^80 (only possible
@@ -33,7 +34,7 @@ constexpr int ATT_SST = 3;                        // S buffers in TMEM
 constexpr int ATT_Q_BYTES = ATT_BM * ATT_D * 2;   // 16 KB
 constexpr int ATT_KV_BYTES = ATT_BN * ATT_D * 2;  // 8 KB
 constexpr int ATT_P_BYTES = ATT_BM * ATT_BN * 2;  // 16 KB
-constexpr int ATT_SMEM = ATT_Q_BYTES + (ATT_KST + ATT_VST) * ATT_KV_BYTES + 2 * ATT_P_BYTES + 1024;
+constexpr int ATT_SMEM = ATT_Q_BYTES + (ATT_KST + ATT_VST) * ATT_KV_BYTES + ATT_P_BYTES + 1024;  // sP: output staging
 constexpr float ATT_RESCALE_LOG2 = 80.f;
 
 struct AttnLevels {
@@ -188,11 +189,11 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
           mbar_wait(bar_v(st), (g / ATT_VST) & 1);
           if (j == 0 && it > 0) mbar_wait(bar_oread, (it - 1) & 1);  // previous item's output has left TMEM
           tc_fence_after();
-          const uint64_t pd = umma_desc_k_sw128(sP + (g & 1) * ATT_P_BYTES);
+          const uint32_t p_tmem = tmem + (g % ATT_SST) * 64;  // P_g sits in the first 32 columns of S_g's buffer
 #pragma unroll
-          for (int k = 0; k < ATT_BN / 16; ++k) {
+          for (int k = 0; k < ATT_BN / 16; ++k) {  // 16 keys = 8 packed columns per K-step
             const uint64_t vd = umma_desc_mn_sw128_attn(sV + st * ATT_KV_BYTES + k * 2048);
-            umma_bf16_ss(tmem_o, pd + 2 * k, vd, idesc_pv, (j | k) != 0);
+            umma_bf16_ts(tmem_o, p_tmem + 8 * k, vd, idesc_pv, (j | k) != 0);
           }
           umma_commit(bar_pv(g & 1));
           if (g >= 1 && vc.item < total_items) {  // stream position g + 2 reuses the V stage of tile g - 1
@@ -303,18 +304,15 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
           }
         }
         l_run += l_tile;
-        if (g >= 2) mbar_wait(bar_pv(b), ((g - 2) >> 1) & 1);  // P buffer b was read by the P V of tile g-2
-        const uint32_t p_row = sP + b * ATT_P_BYTES + (uint32_t)(warp * 32 + lane) * 128;
+        {  // P_g (bf16, two keys per 32-bit column) overwrites this thread's row of S_g: columns [sb*64, sb*64+32)
+          float pk[32];
+          uint32_t* pw = reinterpret_cast<uint32_t*>(pk);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {  // 16-byte chunk (8 keys), XOR-swizzled with row%8 (SWIZZLE_128B)
-          const uint32_t addr = p_row + (uint32_t)((c ^ sw) << 4);
-          const uint32_t w0 = pack_bf16x2(s[8 * c + 0], s[8 * c + 1]), w1 = pack_bf16x2(s[8 * c + 2], s[8 * c + 3]);
-          const uint32_t w2 = pack_bf16x2(s[8 * c + 4], s[8 * c + 5]), w3 = pack_bf16x2(s[8 * c + 6], s[8 * c + 7]);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3)
-                       : "memory");
+          for (int c = 0; c < 32; ++c) pw[c] = pack_bf16x2(s[2 * c], s[2 * c + 1]);
+          tmem_st_32x32(tmem + lane_off + sb * 64, pk);
+          tmem_st_wait();
         }
         tc_fence_before();
-        fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_p(b));
       }
