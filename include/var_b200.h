@@ -123,9 +123,12 @@ typedef struct var_b200_quant {
 } var_b200_quant_t;
 
 /* f_to_idxBl_or_fhat (quant.py:135-166). idx_out: int64, scale blocks [B, ph*pw] concatenated.
- * fhat_list: NULL or [S,B,Cvae,H,W] (the to_fhat=True list). work: 2*B*Cvae*H*W floats. */
+ * fhat_list: NULL or [S,B,Cvae,H,W] (the to_fhat=True list). work: var_b200_quant_encode_workspace(qz, B) bytes.
+ * search_mode 0: codebook search on the tensor cores (bf16 UMMA distance filter + exact fp32 re-rank, one search
+ * launch per scale); 1: single fused kernel with an fp32 CUDA-core search. Both return identical indices. */
+VAR_B200_API size_t var_b200_quant_encode_workspace(const var_b200_quant_t* qz, int B);
 VAR_B200_API int var_b200_quant_encode(const var_b200_quant_t* qz, const float* f, int B, int64_t* idx_out,
-                                       float* fhat_list, float* work, void* stream);
+                                       float* fhat_list, void* work, size_t work_bytes, int search_mode, void* stream);
 /* idxBl_to_var_input (quant.py:169-184) and embed_to_fhat(all_to_max_scale=True) (quant.py:107-121) in one pass.
  * var_input: NULL or [B, L - l_0, Cvae]; fhat_list: NULL or [S,B,Cvae,H,W]; fhat_last: [B,Cvae,H,W] (required). */
 VAR_B200_API int var_b200_quant_decode(const var_b200_quant_t* qz, const int64_t* idx, int B, float* var_input,

@@ -20,9 +20,13 @@ def _t(a):
 
 
 # ------------------------------------------------------------------------------------------------ quantizer
-@pytest.mark.parametrize("B,sigma", [(3, 1.5), (64, 1.0), (64, 3.0), (1, 0.0)])
-def test_quant_encode_bit_exact(B, sigma):
+@pytest.mark.parametrize("mode", [0, 1], ids=["tensorcore_filter", "fused_fp32"])
+@pytest.mark.parametrize("B,sigma", [(3, 1.5), (64, 1.0), (64, 3.0), (1, 0.0), (5, 0.05), (2, 30.0)])
+def test_quant_encode_bit_exact(B, sigma, mode):
+    """Both search paths (bf16 UMMA distance filter + exact fp32 re-rank; fused fp32 CUDA-core search) must return the
+    oracle's indices bit for bit."""
     vae, _ = seeded_models(device=DEV)
+    vae.quantize.search_mode = mode
     qo = quant_oracle_of(vae)
     g = torch.Generator().manual_seed(100 + B)
     f = (torch.randn(B, 32, 16, 16, generator=g) * sigma).numpy()
@@ -36,6 +40,7 @@ def test_quant_encode_bit_exact(B, sigma):
         got_f = vae.quantize.f_to_idxBl_or_fhat(_t(f), to_fhat=True)
         for a, b in zip(got_f, ref_f):
             assert np.array_equal(a.cpu().numpy(), b), "f_hat not bit-identical to the oracle"
+    vae.quantize.search_mode = 0
 
 
 def test_quant_encode_matches_reference_golden_and_nonsquare():

@@ -10,6 +10,8 @@
 #include "quant.h"
 #include "sampler.h"
 
+#include <algorithm>
+
 using namespace vb;
 
 namespace {
@@ -264,17 +266,71 @@ static int fill_quant(const var_b200_quant_t* qz, int B, QuantArgs& a) {
   return VB_OK;
 }
 
+static size_t quant_tokens_max(const var_b200_quant_t* qz, int B) {
+  size_t m = 0;
+  for (int i = 0; i < qz->n_scales; ++i) m = std::max(m, (size_t)B * qz->ph[i] * qz->pw[i]);
+  return m;
+}
+
+extern "C" size_t var_b200_quant_encode_workspace(const var_b200_quant_t* qz, int B) {
+  if (!qz || B <= 0 || qz->n_scales <= 0) return 0;
+  const size_t img = (size_t)qz->Cvae * qz->ph[qz->n_scales - 1] * qz->pw[qz->n_scales - 1];
+  const size_t nt = quant_tokens_max(qz, B);
+  size_t b = 0;
+  b += align_up(2 * B * img * 4);          // f_rest, f_hat
+  b += align_up(nt * qz->Cvae * 4);        // pooled tokens fp32
+  b += align_up(nt * 64 * 2);              // pooled tokens bf16 (K padded to 64)
+  b += align_up(nt * 4);                   // |z|^2
+  b += align_up((size_t)qz->V * 64 * 2);   // codebook bf16 (K padded to 64)
+  return b;
+}
+
 extern "C" int var_b200_quant_encode(const var_b200_quant_t* qz, const float* f, int B, int64_t* idx_out, float* fhat_list,
-                                     float* work, void* stream) {
+                                     void* work, size_t work_bytes, int search_mode, void* stream) {
   QuantArgs a;
   int rc = fill_quant(qz, B, a);
   if (rc) return rc;
   VB_REQUIRE(f && idx_out && work && B > 0, "quant_encode: bad arguments");
+  VB_REQUIRE(work_bytes >= var_b200_quant_encode_workspace(qz, B), "quant_encode: workspace %zu < %zu", work_bytes,
+             var_b200_quant_encode_workspace(qz, B));
+  VB_REQUIRE(search_mode == 0 || search_mode == 1, "quant_encode: search_mode=%d", search_mode);
+  cudaStream_t st = (cudaStream_t)stream;
   const size_t img = (size_t)a.Cvae * a.H * a.W;
-  a.si_begin = 0; a.si_end = a.S;
-  a.f = f; a.f_rest = work; a.f_hat = work + (size_t)B * img; a.zero_fhat = 1;
+  const size_t nt = quant_tokens_max(qz, B);
+  Carver cv(work, work_bytes);
+  float* rest_hat = reinterpret_cast<float*>(cv.take(2 * B * img * 4));
+  float* z = reinterpret_cast<float*>(cv.take(nt * a.Cvae * 4));
+  void* zb = cv.take(nt * 64 * 2);
+  float* zz = reinterpret_cast<float*>(cv.take(nt * 4));
+  void* cb16 = cv.take((size_t)a.V * 64 * 2);
+  a.f_rest = rest_hat; a.f_hat = rest_hat + (size_t)B * img;
   a.idx_concat = 1; a.idx = idx_out; a.fhat_list = fhat_list;
-  return quant_launch(a, (cudaStream_t)stream);
+  if (search_mode == 1) {  // fused single kernel, fp32 CUDA-core search
+    a.si_begin = 0; a.si_end = a.S; a.f = f; a.zero_fhat = 1; a.split = 0;
+    return quant_launch(a, st);
+  }
+  // tensor-core search: [pool s0] -> for every scale: [UMMA filter + exact re-rank] -> [update s, pool s+1]
+  rc = quant_prepare_codebook(a.codebook, cb16, a.V, st);
+  if (rc) return rc;
+  a.z_out = z; a.zb_out = zb; a.zz_out = zz;
+  a.si_begin = 0; a.si_end = 1; a.f = f; a.zero_fhat = 1; a.split = 1;
+  rc = quant_launch(a, st);
+  if (rc) return rc;
+  a.f = nullptr; a.zero_fhat = 0; a.split = 2;
+  size_t off = 0;
+  for (int si = 0; si < a.S; ++si) {
+    const int n_tok = B * a.ph[si] * a.pw[si];
+    QuantSearchArgs sa{};
+    sa.zb = zb; sa.z = z; sa.zz = zz; sa.cb_bf16 = cb16; sa.codebook = a.codebook; sa.N = n_tok; sa.V = a.V;
+    sa.idx_out = idx_out + off;
+    rc = quant_search_launch(sa, st);
+    if (rc) return rc;
+    a.si_begin = si; a.si_end = si + 1;
+    rc = quant_launch(a, st);
+    if (rc) return rc;
+    off += n_tok;
+  }
+  return VB_OK;
 }
 
 extern "C" int var_b200_quant_decode(const var_b200_quant_t* qz, const int64_t* idx, int B, float* var_input,

@@ -42,6 +42,11 @@ struct QuantKParams {
   float* next_tokens;     // optional token-major area(f_hat -> next scale): row stride next_stride tokens per image
   int next_stride;
   float* next_nchw;       // optional [B,CV,ph_next,pw_next] (single-scale step only)
+  // split encode (search done by the tensor-core kernel between launches)
+  int split;              // 0: fused, 1: init + pool scale si_begin only, 2: update scale si_begin from idx, pool si_begin+1
+  float* z_out;           // pooled tokens [B*l, CV] fp32 (token-major)
+  __nv_bfloat16* zb_out;  // same, bf16, K padded to 64 with zeros: [B*l, 64]
+  float* zz_out;          // |z|^2 per token [B*l] (sequential fp32 sum, the oracle's order)
 };
 
 __device__ __forceinline__ float q_cubic1(float x) {
@@ -90,14 +95,50 @@ __global__ void __launch_bounds__(QT, 1) quant_kernel(const QuantKParams p) {
   const size_t img = (size_t)CV * HW;
   float* f_hat = p.f_hat + (size_t)b * img;
   float* f_rest = p.f_rest ? p.f_rest + (size_t)b * img : nullptr;
-  const bool encode = p.f != nullptr;
+  const bool encode = p.f != nullptr && p.split == 0;         // search inside this kernel (fp32 CUDA cores)
+  const bool upd_rest = f_rest != nullptr && (encode || p.split == 2);
 
   for (int i = tid; i < CV * plane; i += QT) hup[i] = 0.f;
   if (p.zero_fhat)
     for (size_t i = tid; i < img; i += QT) f_hat[i] = 0.f;
-  if (encode) {
+  if (p.f != nullptr) {
     const float* f = p.f + (size_t)b * img;
     for (size_t i = tid; i < img; i += QT) f_rest[i] = f[i];
+  }
+  // pooled tokens of scale `ps` -> global (input of the tensor-core search kernel)
+  auto pool_out = [&](int ps) {
+    const int ph = p.ph[ps], pw = p.pw[ps], l = ph * pw;
+    const bool last = (ps == p.S - 1);
+    for (int t0 = 0; t0 < l; t0 += Q_CHUNK) {
+      const int lc = min(Q_CHUNK, l - t0);
+      __syncthreads();
+      for (int i = tid; i < CV * lc; i += QT) {
+        const int c = i / lc, t = i - c * lc, tok = t0 + t;
+        const float* pl = f_rest + (size_t)c * HW;
+        zbuf[c * Q_CHUNK + t] = last ? pl[tok] : area_at(pl, H, W, ph, pw, tok / pw, tok % pw);
+      }
+      __syncthreads();
+      for (int t = tid; t < lc; t += QT) {
+        float s = 0.f;
+        for (int c = 0; c < CV; ++c) { const float z = zbuf[c * Q_CHUNK + t]; s = s + z * z; }
+        p.zz_out[(size_t)b * l + t0 + t] = s;
+      }
+      for (int i = tid; i < lc * 64; i += QT) {
+        const int t = i >> 6, c = i & 63;
+        const size_t tok = (size_t)b * l + t0 + t;
+        const float z = c < CV ? zbuf[c * Q_CHUNK + t] : 0.f;
+        if (c < CV) p.z_out[tok * CV + c] = z;
+        p.zb_out[tok * 64 + c] = __float2bfloat16_rn(z);
+      }
+    }
+    __syncthreads();
+  };
+  if (p.split == 1) {
+    __syncthreads();
+    pool_out(p.si_begin);
+    return;
+  }
+  if (encode) {
     for (int v = tid; v < p.V; v += QT) {
       const float* e = p.codebook + (size_t)v * CV;
       float s = 0.f;
@@ -284,7 +325,7 @@ __global__ void __launch_bounds__(QT, 1) quant_kernel(const QuantKParams p) {
         const size_t g = (size_t)co * HW + pix;
         const float nh = f_hat[g] + hphi;
         f_hat[g] = nh;
-        if (encode) f_rest[g] = f_rest[g] - hphi;
+        if (upd_rest) f_rest[g] = f_rest[g] - hphi;
         if (p.fhat_list) p.fhat_list[((size_t)si * p.B + b) * img + g] = nh;
       }
     }
@@ -303,6 +344,7 @@ __global__ void __launch_bounds__(QT, 1) quant_kernel(const QuantKParams p) {
     }
     if (p.idx_concat) idx_off += (long long)p.B * l;
     __syncthreads();
+    if (p.split == 2 && !last) pool_out(si + 1);
   }
 }
 
@@ -323,6 +365,7 @@ int quant_launch(const QuantArgs& a, cudaStream_t st) {
   VB_REQUIRE(a.si_begin >= 0 && a.si_begin < a.si_end && a.si_end <= a.S, "quant: bad scale range [%d,%d)", a.si_begin,
              a.si_end);
   VB_REQUIRE(!a.f || a.f_rest, "quant: encode needs the f_rest workspace");
+  VB_REQUIRE(a.split >= 0 && a.split <= 2, "quant: bad split mode %d", a.split);
   VB_REQUIRE(a.V > 0, "quant: empty codebook");
   QuantKParams p{};
   p.B = a.B; p.H = a.H; p.W = a.W; p.V = a.V; p.S = a.S;
@@ -339,7 +382,9 @@ int quant_launch(const QuantArgs& a, cudaStream_t st) {
   p.idx_concat = a.idx_concat;
   p.idx = reinterpret_cast<long long*>(a.idx);
   p.fhat_list = a.fhat_list; p.next_tokens = a.next_tokens; p.next_stride = a.next_stride; p.next_nchw = a.next_nchw;
-  const size_t smem = quant_smem_bytes(a.H, a.W, a.V, a.f != nullptr);
+  p.split = a.split; p.z_out = a.z_out; p.zb_out = reinterpret_cast<__nv_bfloat16*>(a.zb_out); p.zz_out = a.zz_out;
+  VB_REQUIRE(a.split == 0 || (a.z_out && a.zb_out && a.zz_out && a.f_rest), "quant: split mode needs pooled-token buffers");
+  const size_t smem = quant_smem_bytes(a.H, a.W, a.V, a.f != nullptr && a.split == 0);
   VB_REQUIRE(smem <= 227 * 1024, "quant: shared memory %zu exceeds 227 KB (V=%d too large?)", smem, a.V);
   static size_t attr = 0;
   if (smem > attr) {

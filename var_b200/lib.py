@@ -103,6 +103,8 @@ def _declare(lib: C.CDLL) -> None:
         fn = getattr(lib, name)
         fn.argtypes = [C.POINTER(ModelDesc), i32] if name == "var_b200_ada_workspace" else [C.POINTER(ModelDesc), i32, i32]
         fn.restype = C.c_size_t
+    lib.var_b200_quant_encode_workspace.argtypes = [C.POINTER(QuantDesc), i32]
+    lib.var_b200_quant_encode_workspace.restype = C.c_size_t
 
 
 def exported_symbols():
@@ -117,7 +119,7 @@ def _EXTRA_SIGS(vp, i32, i64, f32):
     return {
         "var_b200_attention": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, C.POINTER(C.c_int), vp],
         "var_b200_ln_modulate": [vp, vp, vp, i32, i32, vp, i32, i32, f32, vp],
-        "var_b200_quant_encode": [C.POINTER(QuantDesc), vp, i32, vp, vp, vp, vp],
+        "var_b200_quant_encode": [C.POINTER(QuantDesc), vp, i32, vp, vp, vp, sz, i32, vp],
         "var_b200_quant_decode": [C.POINTER(QuantDesc), vp, i32, vp, vp, vp, vp],
         "var_b200_quant_next_input": [C.POINTER(QuantDesc), i32, vp, vp, i32, vp, vp, vp],
         "var_b200_cfg_topk_sample": [vp, i32, i32, i32, i32, dbl, vp, i32, f32, vp, vp, vp],

@@ -83,6 +83,8 @@ class VectorQuantizer2(nn.Module):
         self.beta = beta
         self.embedding = nn.Embedding(vocab_size, Cvae)
         self.prog_si = -1
+        # 0: tensor-core distance filter + exact fp32 re-rank (default); 1: fused fp32 CUDA-core search. Same indices.
+        self.search_mode = 0
         self._pack_key = None
         self._packed = None
 
@@ -130,9 +132,10 @@ class VectorQuantizer2(nn.Module):
         Ltot = sum(h * w for h, w in patch_hws)
         idx = torch.empty(B * Ltot, dtype=torch.int64, device=f.device)
         fh = torch.empty((len(patch_hws), B, Cc, H, W), dtype=torch.float32, device=f.device) if to_fhat else None
-        work = torch.empty(2 * B * Cc * H * W, dtype=torch.float32, device=f.device)
-        L.check(L.load().var_b200_quant_encode(C.byref(d), f.data_ptr(), B, idx.data_ptr(), L.ptr(fh), work.data_ptr(),
-                                               L.current_stream()), "quant_encode")
+        lib = L.load()
+        work = torch.empty(lib.var_b200_quant_encode_workspace(C.byref(d), B), dtype=torch.uint8, device=f.device)
+        L.check(lib.var_b200_quant_encode(C.byref(d), f.data_ptr(), B, idx.data_ptr(), L.ptr(fh), work.data_ptr(),
+                                          work.numel(), int(self.search_mode), L.current_stream()), "quant_encode")
         if to_fhat:
             return [fh[i] for i in range(len(patch_hws))]
         out, off = [], 0
