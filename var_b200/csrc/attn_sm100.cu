@@ -18,6 +18,8 @@
 // (q_hat.k_hat is bounded by the per-head scale <= 100, basic_var.py:101): softmax warps never wait for P V and the
 // tensor pipe runs QK_{j+1} under softmax_j. If a later tile exceeds the reference by more than 2^80 (only possible
 // for scales > 27) the accumulator is rescaled in TMEM (tcgen05.ld / st), which is exact like the usual recurrence.
+#include <stdlib.h>
+
 #include "attn.h"
 #include "common.cuh"
 #include "host.h"
@@ -34,7 +36,7 @@ constexpr int ATT_SST = 3;                        // S buffers in TMEM
 constexpr int ATT_Q_BYTES = ATT_BM * ATT_D * 2;   // 16 KB
 constexpr int ATT_KV_BYTES = ATT_BN * ATT_D * 2;  // 8 KB
 constexpr int ATT_P_BYTES = ATT_BM * ATT_BN * 2;  // 16 KB
-constexpr int ATT_SMEM = ATT_Q_BYTES + (ATT_KST + ATT_VST) * ATT_KV_BYTES + ATT_P_BYTES + 1024;  // sP: output staging
+constexpr int ATT_SMEM = 2 * ATT_Q_BYTES + (ATT_KST + ATT_VST) * ATT_KV_BYTES + ATT_P_BYTES + 1024;  // 2 Q buffers; sP: output staging
 constexpr float ATT_RESCALE_LOG2 = 80.f;
 
 struct AttnLevels {
@@ -63,20 +65,21 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
             const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, int Lq, int H, int q_pos0,
             const __grid_constant__ AttnLevels lv, int n_qt, int total_items) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t bars[2 + ATT_KST + ATT_VST + ATT_SST + 4];  // q | oread | k[] | v[] | s[] | p[2] | pv[2]
+  __shared__ uint64_t bars[3 + ATT_KST + ATT_VST + ATT_SST + 4];  // q[2] | oread | k[] | v[] | s[] | p[2] | pv[2]
   __shared__ uint32_t tmem_base_smem;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = base;
-  const uint32_t sK = sQ + ATT_Q_BYTES;
+  const uint32_t sK = sQ + 2 * ATT_Q_BYTES;
   const uint32_t sV = sK + ATT_KST * ATT_KV_BYTES;
   const uint32_t sP = sV + ATT_VST * ATT_KV_BYTES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t bar_q = smem_u32(&bars[0]), bar_oread = smem_u32(&bars[1]);
-  auto bar_k = [&](int s) { return smem_u32(&bars[2 + s]); };
-  auto bar_v = [&](int s) { return smem_u32(&bars[2 + ATT_KST + s]); };
-  auto bar_s = [&](int s) { return smem_u32(&bars[2 + ATT_KST + ATT_VST + s]); };
-  auto bar_p = [&](int s) { return smem_u32(&bars[2 + ATT_KST + ATT_VST + ATT_SST + s]); };
-  auto bar_pv = [&](int s) { return smem_u32(&bars[4 + ATT_KST + ATT_VST + ATT_SST + s]); };
+  const uint32_t bar_oread = smem_u32(&bars[2]);
+  auto bar_q = [&](int s) { return smem_u32(&bars[s]); };
+  auto bar_k = [&](int s) { return smem_u32(&bars[3 + s]); };
+  auto bar_v = [&](int s) { return smem_u32(&bars[3 + ATT_KST + s]); };
+  auto bar_s = [&](int s) { return smem_u32(&bars[3 + ATT_KST + ATT_VST + s]); };
+  auto bar_p = [&](int s) { return smem_u32(&bars[3 + ATT_KST + ATT_VST + ATT_SST + s]); };
+  auto bar_pv = [&](int s) { return smem_u32(&bars[5 + ATT_KST + ATT_VST + ATT_SST + s]); };
 
   auto kv_end_of = [&](int row) {  // visible keys of query row `row` of this call's query block
     // lv.end is padded with the sequence length up to VB_MAX_SCALES: fixed trip count, constant-bank operands
@@ -107,7 +110,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
-    mbar_init(bar_q, 1);
+    mbar_init(bar_q(0), 1);
+    mbar_init(bar_q(1), 1);
     mbar_init(bar_oread, 4);   // one arrive per softmax warp
     for (int s = 0; s < ATT_KST; ++s) mbar_init(bar_k(s), 1);
     for (int s = 0; s < ATT_VST; ++s) mbar_init(bar_v(s), 1);
@@ -144,15 +148,16 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         next_tile(vc);
         ++vpos;
       };
-      if (cur.item < total_items) {
-        mbar_expect_tx(bar_q, ATT_Q_BYTES);
-        tma_load_3d(&tmQ, bar_q, sQ, 0, cur.row0, cur.bh);
-      }
+      auto load_q = [&](const AttnItem& c, int it_) {  // Q tiles are double-buffered across items
+        mbar_expect_tx(bar_q(it_ & 1), ATT_Q_BYTES);
+        tma_load_3d(&tmQ, bar_q(it_ & 1), sQ + (it_ & 1) * ATT_Q_BYTES, 0, c.row0, c.bh);
+      };
+      if (cur.item < total_items) load_q(cur, 0);
       for (int i = 0; i < ATT_KST; ++i)
         if (kc.item < total_items) load_k();
       for (int i = 0; i < ATT_VST; ++i)
         if (vc.item < total_items) load_v();
-      const uint64_t qd = umma_desc_k_sw128(sQ);
+      uint64_t qd = 0;
       auto issue_qk = [&](int g) {  // g: global key-tile index of this CTA
         const int st = g % ATT_KST;
         mbar_wait(bar_k(st), (g / ATT_KST) & 1);
@@ -166,7 +171,13 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       int G = 0, it = 0;
       while (cur.item < total_items) {
         const int n_kt = cur.n_kt;
-        mbar_wait(bar_q, it & 1);
+        {  // prefetch the next item's queries into the other Q buffer (its last reader, item it-1, has finished)
+          AttnItem nx = cur;
+          next_item(nx);
+          if (nx.item < total_items) load_q(nx, it + 1);
+        }
+        mbar_wait(bar_q(it & 1), (it >> 1) & 1);
+        qd = umma_desc_k_sw128(sQ + (it & 1) * ATT_Q_BYTES);
         // QK runs two tiles ahead of the softmax (the tcgen05 issue->commit->mbarrier round trip is ~1 us)
         issue_qk(G);
         if (n_kt > 1) issue_qk(G + 1);
@@ -177,14 +188,6 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
           mbar_wait(bar_p(g & 1), (g >> 1) & 1);  // P_g written; QK_g therefore complete
           tc_fence_after();
           if (kc.item < total_items) load_k();  // stream position g + ATT_KST reuses the K stage of tile g
-          if (j == n_kt - 1) {                  // last QK of this item has read sQ: fetch the next item's queries
-            AttnItem nx = cur;
-            next_item(nx);
-            if (nx.item < total_items) {
-              mbar_expect_tx(bar_q, ATT_Q_BYTES);
-              tma_load_3d(&tmQ, bar_q, sQ, 0, nx.row0, nx.bh);
-            }
-          }
           const int st = g % ATT_VST;
           mbar_wait(bar_v(st), (g / ATT_VST) & 1);
           if (j == 0 && it > 0) mbar_wait(bar_oread, (it - 1) & 1);  // previous item's output has left TMEM
@@ -405,9 +408,18 @@ int attn_launch(const AttnArgs& a, cudaStream_t st) {
   const int n_qt = (a.Lq + ATT_BM - 1) / ATT_BM;
   const long long total = (long long)n_qt * a.H * a.n_seq;
   VB_REQUIRE(total < (1ll << 31), "attn: too many work items");
-  // One item per CTA: measured faster than persistent CTAs with static striding (649 vs 510 us on the d16 scoring
-  // shape) because item costs vary 3..11 key tiles; the kernel's item loop is kept for a dynamic scheduler.
-  const int grid = (int)total;
+  // One work item per CTA by default. Persistent CTAs (2 per SM, stride = 1 mod n_qt so every CTA walks through all
+  // q tiles, next item's Q prefetched into the second buffer) are supported by the kernel and selectable with
+  // VAR_B200_ATTN_GRID=<n>: measured 94 ms vs 78 ms of attention time per d16 scoring step (item costs vary 3..11 key
+  // tiles and the hardware CTA scheduler balances them better than a static stride).
+  int grid = (int)total;
+  if (const char* e = getenv("VAR_B200_ATTN_GRID")) {  // measurement hook
+    int g = atoi(e);
+    if (g > 0 && g < total) {
+      while (g > 1 && g % n_qt != 1 % n_qt) --g;
+      grid = g;
+    }
+  }
   vb::ProfScope prof_scope(vb::PK_ATTN, st);
   attn_kernel<<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, reinterpret_cast<__nv_bfloat16*>(a.out), a.Lq, a.H,
                                                    a.q_pos0, lv, n_qt, (int)total);
