@@ -217,6 +217,16 @@ VAR_B200_API int var_b200_head_score(const var_b200_model_t* m, const float* x, 
                                      const int32_t* gt, int gt_rows, int first_pos, float* scores, float* per_scale,
                                      float* tok_logp, void* work, size_t work_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * CFG-mixed teacher-forced scoring (var_analysis.py:320-346,437-466).
+ * tok_logp[s,t] = log_softmax((1+t_row[t])*logits_cond[s,t,:] - t_row[t]*logits_uncond[t,:])[gt[t]],
+ * t_row[t] = cfg * level(t)/(S-1) (device fp32 [L]); two rounded products and a subtraction as the reference.
+ * var_b200_scale_sums: per_scale[s,i] = sum of tok_logp over level i (t >= first_pos), total[s] = sum over levels. */
+VAR_B200_API int var_b200_cfg_token_logprob(const float* logits_cond, const float* logits_uncond, const int32_t* gt,
+                                            const float* t_row, int n_seq, int L, int V, float* tok_logp, void* stream);
+VAR_B200_API int var_b200_scale_sums(const float* tok_logp, int n_seq, int L, int n_scales, const int* level_end /* host */,
+                                     int first_pos, float* per_scale, float* total, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

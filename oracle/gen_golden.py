@@ -90,6 +90,18 @@ def main():
         var(labels, var_in)
         for h in hooks:
             h.remove()
+        # CFG-mixed scoring exactly as var_analysis.py:320-346,437-466 does it around VAR.forward
+        pn = var.patch_nums
+        unc = var(torch.tensor(1000), var_in[:1])
+        ratio = torch.cat([torch.full((p * p,), si / (len(pn) - 1)) for si, p in enumerate(pn)])
+        t_cfg = 1.5 * ratio.unsqueeze(0).unsqueeze(-1)
+        lg_c = var(torch.tensor([3, 999, 17]), var_in[:1].expand(3, -1, -1))
+        mixed = (1 + t_cfg) * lg_c - t_cfg * unc
+        glp = torch.nn.functional.log_softmax(mixed, dim=-1).gather(-1, gt[:1].expand(3, -1).unsqueeze(-1)).squeeze(-1)
+        cfg_scale_sums, st_ = [], 0
+        for p in pn:
+            cfg_scale_sums.append(glp[:, st_:st_ + p * p].sum(-1)); st_ += p * p
+        cfg_scale_sums = torch.stack(cfg_scale_sums, 1)
         # embed_to_fhat / idxBl_to_img path (decoder output pins the boundary function)
         img = vae.idxBl_to_img(idx, same_shape=True, last_one=True)
         f_enc = vae.quant_conv(vae.encoder(torch.rand(1, 3, 256, 256, generator=g) * 2 - 1))
@@ -101,7 +113,8 @@ def main():
         labels=labels.numpy(), logits_sub=logits[:, ::23, ::29].numpy(), lse=torch.logsumexp(logits, -1).numpy(),
         logp=logp.numpy(), scores=logp.sum(1).numpy(),
         block_sub=np.stack([a[:, ::23, ::7].numpy() for a in acts]),
-        img_sub=img[:, :, ::8, ::8].numpy(), f_enc_sub=f_enc[:, :, ::2, ::2].numpy())
+        img_sub=img[:, :, ::8, ::8].numpy(), f_enc_sub=f_enc[:, :, ::2, ::2].numpy(),
+        cfg_scale_sums=cfg_scale_sums.numpy(), cfg_tok_logp=glp.numpy())
 
     # ---------------------------------------------------------------- G3: sampler op (helpers.py:6-19) with replayed noise
     gs = torch.Generator().manual_seed(5)

@@ -91,6 +91,21 @@ def test_var_oracle_forward_matches_reference_golden():
     assert float(np.abs(g["block_sub"][1] - g["block_sub"][0]).max()) > 0.1
 
 
+def test_cfg_scoring_oracle_matches_reference_golden():
+    """var_analysis.py:320-346,437-466: CFG-mixed teacher-forced per-scale log-likelihoods."""
+    g = golden("quant_forward_d2.npz")
+    _, var = seeded_models()
+    sd, cfg = sd_cpu(var), var_cfg_of(var)
+    vin = torch.from_numpy(g["var_input"][:1])
+    gt = torch.from_numpy(g["idx"][:1].astype(np.int64))
+    unc = VO.var_forward(sd, cfg, torch.tensor([1000]), vin)
+    lc = VO.var_forward(sd, cfg, torch.tensor([3, 999, 17]), vin.expand(3, -1, -1))
+    total, per_scale, tok = VO.cfg_class_scores(lc, unc, gt, 1.5, PATCH_NUMS)
+    assert (tok - torch.from_numpy(g["cfg_tok_logp"])).abs().max() < 2e-3
+    assert (per_scale - torch.from_numpy(g["cfg_scale_sums"])).abs().max() < 2e-2
+    assert (total - per_scale.sum(1)).abs().max() < 1e-2
+
+
 def test_sampler_oracle_matches_reference_golden():
     g = golden("sampler.npz")
     lg, q = torch.from_numpy(g["logits"]), torch.from_numpy(g["q"])

@@ -212,6 +212,30 @@ def test_class_scores_vs_oracle():
     assert (tail.cpu() - VO.class_scores(ref_logits, gt, first_pos=424)).abs().max().item() < 1.0
 
 
+def test_cfg_class_scores_vs_oracle():
+    """CFG-mixed scoring (var_analysis.py:320-346,437-466): per-scale sums vs the fp32 oracle and the reference golden."""
+    from var_b200.scoring import class_log_likelihoods_cfg
+    g = golden("quant_forward_d2.npz")
+    vae, var = seeded_models(device=DEV)
+    sd, cfg = sd_cpu(var), var_cfg_of(var)
+    idx_np = split_scales(g["idx"][:1])
+    labels = torch.tensor([3, 999, 17])
+    vin = torch.from_numpy(g["var_input"][:1])
+    gt = torch.from_numpy(g["idx"][:1].astype(np.int64))
+    unc = VO.var_forward(sd, cfg, torch.tensor([1000]), vin)
+    lc = VO.var_forward(sd, cfg, labels, vin.expand(3, -1, -1))
+    ref_total, ref_ps, ref_tok = VO.cfg_class_scores(lc, unc, gt, 1.5, PATCH_NUMS)
+    total, ps, tok = class_log_likelihoods_cfg(var, [_t(i) for i in idx_np], labels, 1.5, class_batch=2)
+    assert (tok.cpu() - ref_tok).abs().max().item() < 0.25          # mixing amplifies the bf16 logit error by up to 4x
+    assert (ps.cpu() - ref_ps).abs().max().item() < 2.0 and (total.cpu() - ref_total).abs().max().item() < 3.0
+    assert torch.argmax(total).item() == torch.argmax(ref_total).item()
+    assert (ps.cpu() - torch.from_numpy(g["cfg_scale_sums"])).abs().max().item() < 2.0
+    # cfg = 0 reduces to the plain scores (same kernels as class_log_likelihoods up to the fused epilogue)
+    from var_b200.scoring import class_log_likelihoods
+    t0, _, _ = class_log_likelihoods_cfg(var, [_t(i) for i in idx_np], labels, 0.0)
+    assert (t0 - class_log_likelihoods(var, [_t(i) for i in idx_np], labels)).abs().max().item() < 0.05
+
+
 # ------------------------------------------------------------------------------------------------ sampler
 @pytest.mark.parametrize("name,k,p", [("k900", 900, 0.0), ("k900p95", 900, 0.95), ("k0", 0, 0.0), ("p50", 0, 0.5)])
 def test_sampler_bit_exact(name, k, p):
@@ -279,3 +303,15 @@ def test_ar_sampling_end_to_end_consistency():
     vin = vae.quantize.idxBl_to_var_input(tr["idx"])
     tf = var(labels, vin)
     assert (tf[:, :1] - tr["logits"][0]).abs().max().item() < 2e-2
+
+
+def test_ar_cuda_graph_matches_eager():
+    """The captured 10-scale loop must reproduce the eager loop bit for bit for the same seed, and honour re-seeding."""
+    vae, var = seeded_models(device=DEV)
+    labels = torch.tensor([1, 2, 3], device=DEV)
+    eager = var.autoregressive_infer_cfg(3, labels, g_seed=5, cfg=1.5, top_k=900, decode=False)
+    graph = var.autoregressive_infer_cfg(3, labels, g_seed=5, cfg=1.5, top_k=900, decode=False, cuda_graph=True)
+    assert torch.equal(eager, graph)
+    eager2 = var.autoregressive_infer_cfg(3, labels + 7, g_seed=9, cfg=1.5, top_k=900, decode=False)
+    graph2 = var.autoregressive_infer_cfg(3, labels + 7, g_seed=9, cfg=1.5, top_k=900, decode=False, cuda_graph=True)
+    assert torch.equal(eager2, graph2) and not torch.equal(graph, graph2)

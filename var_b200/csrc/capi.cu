@@ -362,6 +362,18 @@ extern "C" int var_b200_quant_next_input(const var_b200_quant_t* qz, int si, flo
   return quant_launch(a, (cudaStream_t)stream);
 }
 
+// ------------------------------------------------------------------------------------------------ CFG scoring
+extern "C" int var_b200_cfg_token_logprob(const float* logits_cond, const float* logits_uncond, const int32_t* gt,
+                                          const float* t_row, int n_seq, int L, int V, float* tok_logp, void* stream) {
+  return cfg_token_logprob(logits_cond, logits_uncond, gt, t_row, n_seq, L, V, tok_logp, (cudaStream_t)stream);
+}
+
+extern "C" int var_b200_scale_sums(const float* tok_logp, int n_seq, int L, int n_scales, const int* level_end,
+                                   int first_pos, float* per_scale, float* total, void* stream) {
+  VB_REQUIRE(level_end != nullptr, "scale_sums: null level table");
+  return scale_sums(tok_logp, n_seq, L, n_scales, level_end, first_pos, per_scale, total, (cudaStream_t)stream);
+}
+
 // ------------------------------------------------------------------------------------------------ sampler
 extern "C" int var_b200_cfg_topk_sample(const float* logits, int B, int l, int V, int use_cfg, double t, const float* q,
                                         int top_k, float top_p, int64_t* idx_out, float* mixed_out, void* stream) {

@@ -265,4 +265,98 @@ int score_finalize(const void* part, int n_tiles, const float* gt_logit, int n_s
   return VB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// CFG-mixed teacher-forced scoring (var_analysis.py:320-346): x = (1+t)*cond - t*uncond with t = cfg * si/(S-1) per
+// position, then log_softmax(x)[gt]. One CTA per (class sequence, position) row of V logits.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+cfg_token_logprob_kernel(const float* __restrict__ lc, const float* __restrict__ lu, const int* __restrict__ gt,
+                         const float* __restrict__ t_row, int L, int V, float* __restrict__ tok_logp) {
+  __shared__ float red[8];
+  const int t = blockIdx.x, s = blockIdx.y;
+  const float* c = lc + ((size_t)s * L + t) * V;
+  const float* u = lu + (size_t)t * V;
+  const float tr = __ldg(t_row + t), opt = 1.f + tr;
+  const int g = __ldg(gt + t);
+  float m = -INFINITY;
+  for (int v = threadIdx.x; v < V; v += 256) m = fmaxf(m, __fsub_rn(__fmul_rn(opt, c[v]), __fmul_rn(tr, u[v])));
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = red[0];
+  for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int v = threadIdx.x; v < V; v += 256) sum += expf(__fsub_rn(__fmul_rn(opt, c[v]), __fmul_rn(tr, u[v])) - m);
+  sum = warp_sum(sum);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int i = 0; i < 8; ++i) tot += red[i];
+    const float xg = __fsub_rn(__fmul_rn(opt, c[g]), __fmul_rn(tr, u[g]));
+    tok_logp[(size_t)s * L + t] = xg - (m + logf(tot));
+  }
+}
+
+int cfg_token_logprob(const float* lc, const float* lu, const int* gt, const float* t_row, int n_seq, int L, int V,
+                      float* tok_logp, cudaStream_t st) {
+  VB_REQUIRE(lc && lu && gt && t_row && tok_logp && n_seq > 0 && L > 0 && V > 0, "cfg_token_logprob: bad arguments");
+  VB_REQUIRE(n_seq <= 65535, "cfg_token_logprob: too many sequences");
+  vb::ProfScope prof_scope(vb::PK_SCORE_FIN, st);
+  cfg_token_logprob_kernel<<<dim3(L, n_seq), 256, 0, st>>>(lc, lu, gt, t_row, L, V, tok_logp);
+  VB_CUDA_CHECK(cudaGetLastError());
+  vb::count_launch();
+  return VB_OK;
+}
+
+// per-scale / total sums of token log-likelihoods (var_analysis.py:437-466), fixed reduction order
+__global__ void __launch_bounds__(256)
+scale_sums_kernel(const float* __restrict__ tok_logp, int L, AttnLevelsPOD lv, int first_pos, float* __restrict__ per_scale,
+                  float* __restrict__ total) {
+  __shared__ float red[VB_MAX_SCALES][8];
+  const int s = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float acc[VB_MAX_SCALES];
+#pragma unroll
+  for (int i = 0; i < VB_MAX_SCALES; ++i) acc[i] = 0.f;
+  for (int t = threadIdx.x; t < L; t += blockDim.x) {
+    const float lp = tok_logp[(size_t)s * L + t];
+    int level = 0;
+    while (level < lv.n - 1 && t >= lv.end[level]) ++level;
+#pragma unroll
+    for (int i = 0; i < VB_MAX_SCALES; ++i)
+      if (i == level && t >= first_pos) acc[i] += lp;
+  }
+#pragma unroll
+  for (int i = 0; i < VB_MAX_SCALES; ++i) {
+    const float v = warp_sum(acc[i]);
+    if (lane == 0) red[i][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int i = 0; i < lv.n; ++i) {
+      float v = 0.f;
+      for (int w = 0; w < 8; ++w) v += red[i][w];
+      if (per_scale) per_scale[(size_t)s * lv.n + i] = v;
+      tot += v;
+    }
+    total[s] = tot;
+  }
+}
+
+int scale_sums(const float* tok_logp, int n_seq, int L, int n_scales, const int* level_end, int first_pos,
+               float* per_scale, float* total, cudaStream_t st) {
+  VB_REQUIRE(tok_logp && total && n_seq > 0 && L > 0, "scale_sums: bad arguments");
+  VB_REQUIRE(n_scales > 0 && n_scales <= VB_MAX_SCALES, "scale_sums: n_scales=%d", n_scales);
+  AttnLevelsPOD lv;
+  lv.n = n_scales;
+  for (int i = 0; i < VB_MAX_SCALES; ++i) lv.end[i] = level_end[i < n_scales ? i : n_scales - 1];
+  vb::ProfScope prof_scope(vb::PK_SCORE_FIN, st);
+  scale_sums_kernel<<<n_seq, 256, 0, st>>>(tok_logp, L, lv, first_pos, per_scale, total);
+  VB_CUDA_CHECK(cudaGetLastError());
+  vb::count_launch();
+  return VB_OK;
+}
+
 }  // namespace vb

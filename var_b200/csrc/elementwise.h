@@ -25,4 +25,9 @@ int score_finalize(const void* part, int n_tiles, const float* gt_logit, int n_s
                    const int* level_end, float* tok_logp, float* per_scale, float* total, int first_pos,
                    cudaStream_t st);
 
+int cfg_token_logprob(const float* lc, const float* lu, const int* gt, const float* t_row, int n_seq, int L, int V,
+                      float* tok_logp, cudaStream_t st);
+int scale_sums(const float* tok_logp, int n_seq, int L, int n_scales, const int* level_end, int first_pos,
+               float* per_scale, float* total, cudaStream_t st);
+
 }  // namespace vb

@@ -123,6 +123,8 @@ def _EXTRA_SIGS(vp, i32, i64, f32):
         "var_b200_quant_decode": [C.POINTER(QuantDesc), vp, i32, vp, vp, vp, vp],
         "var_b200_quant_next_input": [C.POINTER(QuantDesc), i32, vp, vp, i32, vp, vp, vp],
         "var_b200_cfg_topk_sample": [vp, i32, i32, i32, i32, dbl, vp, i32, f32, vp, vp, vp],
+        "var_b200_cfg_token_logprob": [vp, vp, vp, vp, i32, i32, i32, vp, vp],
+        "var_b200_scale_sums": [vp, i32, i32, i32, C.POINTER(C.c_int), i32, vp, vp, vp],
         "var_b200_ada_ld": [C.POINTER(ModelDesc)],
         "var_b200_ada_params": [C.POINTER(ModelDesc), vp, i32, vp, vp, sz, vp],
         "var_b200_embed": [C.POINTER(ModelDesc), vp, i32, i32, vp, i32, i32, i32, i32, vp, vp],

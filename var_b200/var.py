@@ -219,13 +219,14 @@ class VAR(nn.Module):
     @torch.no_grad()
     def autoregressive_infer_cfg(self, B: int, label_B: Optional[Union[int, torch.LongTensor]], g_seed: Optional[int] = None,
                                  cfg=1.5, top_k=0, top_p=0.0, more_smooth=False, *, forced_idx=None, return_trace=False,
-                                 decode=True):
+                                 decode=True, cuda_graph=False):
         """models/var.py:126-190: KV-cached CFG sampling; returns images [B,3,H,W] in [0,1].
-        Extras (keyword-only, for the parity harness): forced_idx = tokens to feed instead of the sampled ones,
-        return_trace = also return dict(idx, logits, f_hat); decode=False skips the CNN decoder (returns f_hat)."""
+        Extras (keyword-only): forced_idx = tokens to feed instead of the sampled ones and return_trace = also return
+        dict(idx, logits, f_hat) (parity harness); decode=False skips the CNN decoder (returns f_hat);
+        cuda_graph=True replays the whole 10-scale loop (~130 launches per scale and block) as one captured CUDA graph
+        per (B, cfg, top_k, top_p) — same tokens as the eager path for the same seed."""
         if more_smooth:
             raise NotImplementedError("more_smooth (Gumbel-softmax visualisation path, var.py:178-180) is out of scope")
-        pm = self._model()
         dev = self.lvl_1L.device
         if g_seed is None:
             rng = None
@@ -239,13 +240,29 @@ class VAR(nn.Module):
             label_B = torch.full((B,), fill_value=self.num_classes if label_B < 0 else label_B, device=dev)
         label_B = label_B.to(dev)
         labels = self._labels_i32(torch.cat((label_B, torch.full_like(label_B, self.num_classes))), 2 * B)
+        if cuda_graph:
+            if forced_idx is not None or return_trace:
+                raise ValueError("cuda_graph=True does not support forced_idx / return_trace")
+            f_hat = self._ar_graph_replay(B, labels, rng, float(cfg), int(top_k), float(top_p))
+            trace = None
+        else:
+            trace = dict(idx=[], logits=[]) if return_trace else None
+            f_hat = self._ar_loop(B, labels, rng, cfg, top_k, top_p, forced_idx, trace)
+        if return_trace:
+            trace["f_hat"] = f_hat
+        img = self.vae_proxy[0].fhat_to_img(f_hat).add_(1).mul_(0.5) if decode else f_hat
+        return (img, trace) if return_trace else img
+
+    def _ar_loop(self, B, labels, rng, cfg, top_k, top_p, forced_idx=None, trace=None):
+        """The 10 strictly sequential scale steps (var.py:160-187) on labels [2B] int32 (cond rows, then uncond)."""
+        pm = self._model()
+        dev = self.lvl_1L.device
         quant = self.vae_quant_proxy[0]
         S = len(self.patch_nums)
         ada = pm.ada_params(labels)
         kv = pm.kv_cache(2 * B)
         H = W = self.patch_nums[-1]
         f_hat = torch.zeros((B, self.Cvae, H, W), dtype=torch.float32, device=dev)
-        trace = dict(idx=[], logits=[]) if return_trace else None
         cur, nxt = 0, None
         for si, pn in enumerate(self.patch_nums):
             l = pn * pn
@@ -257,19 +274,46 @@ class VAR(nn.Module):
             logits = pm.head_logits(x, ada, 2 * B, l)
             q = torch.empty((B * l, self.V), dtype=torch.float32, device=dev).exponential_(1.0, generator=rng)
             t = cfg * (si / self.num_stages_minus_1) if self.num_stages_minus_1 > 0 else 0.0
-            mixed = torch.empty((B, l, self.V), dtype=torch.float32, device=dev) if return_trace else None
+            mixed = torch.empty((B, l, self.V), dtype=torch.float32, device=dev) if trace is not None else None
             idx = pm.sample(logits, B, l, t, q, top_k, top_p, mixed)
             if forced_idx is not None:
                 idx = forced_idx[si].to(dev).to(torch.int64).contiguous()
-            if return_trace:
+            if trace is not None:
                 trace["idx"].append(idx)
                 trace["logits"].append(mixed)
             _, nxt = quant.get_next_autoregressive_input(si, S, f_hat, idx_Bl=idx, token_major=True)
             cur += l
-        if return_trace:
-            trace["f_hat"] = f_hat
-        img = self.vae_proxy[0].fhat_to_img(f_hat).add_(1).mul_(0.5) if decode else f_hat
-        return (img, trace) if return_trace else img
+        return f_hat
+
+    def _ar_graph_replay(self, B, labels, rng, cfg, top_k, top_p):
+        """Capture-once / replay of _ar_loop. Static inputs: the label buffer; the generator state is registered with
+        the graph so a re-seeded generator drives the replayed Exp(1) draws."""
+        pm = self._model()
+        key = (id(pm), B, cfg, top_k, top_p, rng is not None)
+        if not hasattr(self, "_graphs"):
+            self._graphs = {}
+        ent = self._graphs.get(key)
+        if ent is None:
+            static_labels = labels.clone()
+            cur_stream = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur_stream)
+            with torch.cuda.stream(side):  # warm-up outside capture: workspaces, KV cache, kernel attributes
+                self._ar_loop(B, static_labels, rng, cfg, top_k, top_p)
+            cur_stream.wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            if rng is not None:
+                graph.register_generator_state(rng)
+            with torch.cuda.graph(graph):
+                f_hat = self._ar_loop(B, static_labels, rng, cfg, top_k, top_p)
+            ent = (graph, static_labels, f_hat)
+            self._graphs = {k: v for k, v in self._graphs.items() if k[0] == id(pm)}  # drop graphs of stale weights
+            self._graphs[key] = ent
+        graph, static_labels, f_hat = ent
+        static_labels.copy_(labels)
+        graph.replay()
+        return f_hat.clone()
 
     def extra_repr(self):
         return f"depth={self.depth}, C={self.C}, shared_aln={self.shared_aln}, drop_path_rate={self.drop_path_rate:g}"
