@@ -243,7 +243,7 @@ class VAR(nn.Module):
         if cuda_graph:
             if forced_idx is not None or return_trace:
                 raise ValueError("cuda_graph=True does not support forced_idx / return_trace")
-            f_hat = self._ar_graph_replay(B, labels, rng, float(cfg), int(top_k), float(top_p))
+            f_hat = self._ar_graph_replay(B, labels, rng, float(cfg), int(top_k), float(top_p), g_seed)
             trace = None
         else:
             trace = dict(idx=[], logits=[]) if return_trace else None
@@ -285,7 +285,7 @@ class VAR(nn.Module):
             cur += l
         return f_hat
 
-    def _ar_graph_replay(self, B, labels, rng, cfg, top_k, top_p):
+    def _ar_graph_replay(self, B, labels, rng, cfg, top_k, top_p, g_seed=None):
         """Capture-once / replay of _ar_loop. Static inputs: the label buffer; the generator state is registered with
         the graph so a re-seeded generator drives the replayed Exp(1) draws."""
         pm = self._model()
@@ -312,6 +312,8 @@ class VAR(nn.Module):
             self._graphs[key] = ent
         graph, static_labels, f_hat = ent
         static_labels.copy_(labels)
+        if rng is not None:
+            rng.manual_seed(g_seed)  # warm-up and capture advanced the generator: replay from the caller's seed
         graph.replay()
         return f_hat.clone()
 
