@@ -17,6 +17,7 @@ class VQVAE(nn.Module):
                  v_patch_nums=(1, 2, 3, 4, 5, 6, 8, 10, 13, 16), test_mode=True):
         super().__init__()
         self.test_mode = test_mode
+        self.decoder_dtype = None  # set to torch.bfloat16 / float16 to run fhat_to_img through a 16-bit decoder copy
         self.V, self.Cvae = vocab_size, z_channels
         cfg = dict(ch=ch, ch_mult=(1, 1, 2, 2, 4), num_res_blocks=2, in_channels=3, z_channels=z_channels)
         self.encoder = Encoder(**cfg)
@@ -38,7 +39,22 @@ class VQVAE(nn.Module):
 
     # ---- decode side (vqvae.py:62-63, 77-90)
     def fhat_to_img(self, f_hat: torch.Tensor):
+        if self.decoder_dtype is not None and f_hat.is_cuda:
+            post, dec = self._low_precision_decoder()
+            return dec(post(f_hat.to(self.decoder_dtype))).float().clamp_(-1, 1)
         return self.decoder(self.post_quant_conv(f_hat)).clamp_(-1, 1)
+
+    def _low_precision_decoder(self):
+        """bf16/fp16 copy of the CNN decoder (boundary helper, cuDNN): unlike autocast, GroupNorm/SiLU also read and
+        write 16-bit tensors, which halves the elementwise HBM traffic of the 256-px stages."""
+        import copy
+        key = (self.decoder_dtype, tuple(p._version for p in self.decoder.parameters()),
+               tuple(p._version for p in self.post_quant_conv.parameters()), self.decoder.conv_in.weight.data_ptr())
+        if getattr(self, "_lp_key", None) != key:
+            self._lp = (copy.deepcopy(self.post_quant_conv).to(self.decoder_dtype),
+                        copy.deepcopy(self.decoder).to(self.decoder_dtype))
+            self._lp_key = key
+        return self._lp
 
     def idxBl_to_img(self, ms_idx_Bl: List[torch.Tensor], same_shape: bool, last_one=False):
         if not same_shape:
