@@ -227,6 +227,13 @@ VAR_B200_API int var_b200_cfg_token_logprob(const float* logits_cond, const floa
 VAR_B200_API int var_b200_scale_sums(const float* tok_logp, int n_seq, int L, int n_scales, const int* level_end /* host */,
                                      int first_pos, float* per_scale, float* total, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * GroupNorm (+SiLU) on NHWC bf16 tensors: glue of the VQVAE CNN decoder/encoder around the cuDNN convolutions
+ * (models/basic_vae.py:18-19,57-58,159,225). x, y: bf16 [B, HW, C]; gamma, beta: fp32 [C]. Deterministic. */
+VAR_B200_API size_t var_b200_gn_workspace(int B, int HW, int C, int groups);
+VAR_B200_API int var_b200_gn_silu_nhwc(const void* x, const float* gamma, const float* beta, void* y, int B, int HW, int C,
+                                       int groups, float eps, int apply_silu, void* work, size_t work_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

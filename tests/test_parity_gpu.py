@@ -315,3 +315,31 @@ def test_ar_cuda_graph_matches_eager():
     eager2 = var.autoregressive_infer_cfg(3, labels + 7, g_seed=9, cfg=1.5, top_k=900, decode=False)
     graph2 = var.autoregressive_infer_cfg(3, labels + 7, g_seed=9, cfg=1.5, top_k=900, decode=False, cuda_graph=True)
     assert torch.equal(eager2, graph2) and not torch.equal(graph, graph2)
+
+
+def test_nhwc_decoder_matches_pytorch_decoder():
+    """The channels-last bf16 decoder plan (cuDNN NHWC convs + var_b200 GroupNorm/SiLU kernel) vs the fp32 PyTorch
+    decoder (models/basic_vae.py:163-226) and vs a plain bf16 copy of it."""
+    import copy
+    vae, _ = seeded_models(device=DEV)
+    g = golden("quant_forward_d2.npz")
+    f_hat = _t(g["fhat_last"])
+    torch.backends.cudnn.allow_tf32 = False
+    ref = vae.decoder(vae.post_quant_conv(f_hat)).clamp(-1, 1)
+    vae.decoder_dtype, vae.decoder_nhwc = torch.bfloat16, True
+    try:
+        got = vae.fhat_to_img(f_hat)
+        vae.decoder_nhwc = False
+        plain16 = vae.fhat_to_img(f_hat)
+    finally:
+        vae.decoder_dtype, vae.decoder_nhwc = None, True
+    assert got.shape == ref.shape == (3, 3, 256, 256) and got.dtype == torch.float32
+    e_plan, e_plain = (got - ref).abs(), (plain16 - ref).abs()
+    print(f"nhwc plan: max {e_plan.max():.4f} mean {e_plan.mean():.5f}; plain bf16: max {e_plain.max():.4f} mean {e_plain.mean():.5f}")
+    assert e_plan.mean().item() < 2.0 * e_plain.mean().item() + 1e-3 and e_plan.max().item() < 0.25
+    # deterministic (no atomics): two runs are bit-identical
+    vae.decoder_dtype = torch.bfloat16
+    try:
+        assert torch.equal(vae.fhat_to_img(f_hat), got)
+    finally:
+        vae.decoder_dtype = None

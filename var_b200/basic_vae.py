@@ -139,3 +139,81 @@ class Decoder(nn.Module):
             if hasattr(lvl, "upsample"):
                 h = lvl.upsample(h)
         return self.conv_out(F.silu(self.norm_out(h)))
+
+
+class NHWCDecoder:
+    """16-bit channels-last execution plan of a `Decoder` (+ post_quant_conv): the convolutions run on cuDNN's NHWC
+    tensor-core kernels without layout conversions, GroupNorm+SiLU runs as var_b200's two-pass NHWC kernel
+    (csrc/groupnorm.cu), residual adds stay 16-bit. Same function as Decoder.forward(post_quant_conv(f_hat)) up to
+    16-bit rounding (tests/test_parity_gpu.py::test_nhwc_decoder_matches_pytorch_decoder)."""
+
+    def __init__(self, decoder: Decoder, post_quant_conv: nn.Conv2d, dtype=torch.bfloat16):
+        if dtype != torch.bfloat16:
+            raise NotImplementedError("the NHWC GroupNorm kernel is bf16")
+        self.dtype = dtype
+        self.dec = decoder
+        self.post = post_quant_conv
+        self._w = {}
+
+    def _conv(self, x, m: nn.Conv2d, stride=1, padding=None):
+        w = self._w.get(id(m))
+        if w is None or w[2] != (m.weight._version, m.bias._version):
+            w = (m.weight.detach().to(self.dtype).contiguous(memory_format=torch.channels_last),
+                 m.bias.detach().to(self.dtype), (m.weight._version, m.bias._version))
+            self._w[id(m)] = w
+        pad = m.padding if padding is None else padding
+        return F.conv2d(x, w[0], w[1], stride=m.stride, padding=pad)
+
+    def _gn(self, x, m: nn.GroupNorm, silu: bool):
+        import ctypes as C
+        from . import lib as L
+        lib = L.load()
+        B, Cc, H, W = x.shape
+        assert x.is_contiguous(memory_format=torch.channels_last) and x.dtype == torch.bfloat16
+        p = self._w.get(id(m))
+        if p is None or p[2] != (m.weight._version, m.bias._version):
+            p = (m.weight.detach().float().contiguous(), m.bias.detach().float().contiguous(),
+                 (m.weight._version, m.bias._version))
+            self._w[id(m)] = p
+        y = torch.empty_like(x)  # preserves channels_last
+        ws = torch.empty(lib.var_b200_gn_workspace(B, H * W, Cc, m.num_groups), dtype=torch.uint8, device=x.device)
+        L.check(lib.var_b200_gn_silu_nhwc(x.data_ptr(), p[0].data_ptr(), p[1].data_ptr(), y.data_ptr(), B, H * W, Cc,
+                                          m.num_groups, m.eps, int(silu), ws.data_ptr(), ws.numel(), L.current_stream()),
+                "gn_silu_nhwc")
+        return y
+
+    def _res(self, x, blk: ResnetBlock):
+        h = self._conv(self._gn(x, blk.norm1, True), blk.conv1)
+        h = self._conv(self._gn(h, blk.norm2, True), blk.conv2)
+        sc = x if isinstance(blk.nin_shortcut, nn.Identity) else self._conv(x, blk.nin_shortcut)
+        return sc + h
+
+    def _attn(self, x, blk: AttnBlock):
+        B, Cc, H, W = x.shape
+        qkv = self._conv(self._gn(x, blk.norm, False), blk.qkv)               # [B,3C,H,W] channels_last
+        q, k, v = qkv.permute(0, 2, 3, 1).reshape(B, H * W, 3 * Cc).chunk(3, dim=-1)
+        o = F.scaled_dot_product_attention(q, k, v, scale=float(Cc) ** -0.5)   # [B,HW,C]
+        o = o.reshape(B, H, W, Cc).permute(0, 3, 1, 2)                         # channels_last view
+        return x + self._conv(o, blk.proj_out)
+
+    def _level(self, h, lvl):
+        for i, blk in enumerate(lvl.block):
+            h = self._res(h, blk)
+            if len(lvl.attn):
+                h = self._attn(h, lvl.attn[i])
+        return h
+
+    @torch.no_grad()
+    def __call__(self, f_hat: torch.Tensor) -> torch.Tensor:
+        d = self.dec
+        x = f_hat.to(self.dtype).contiguous(memory_format=torch.channels_last)
+        h = self._conv(self._conv(x, self.post), d.conv_in)
+        h = self._res(h, d.mid.block_1)
+        h = self._attn(h, d.mid.attn_1)
+        h = self._res(h, d.mid.block_2)
+        for lvl in reversed(d.up):
+            h = self._level(h, lvl)
+            if hasattr(lvl, "upsample"):
+                h = self._conv(F.interpolate(h, scale_factor=2, mode="nearest"), lvl.upsample.conv)
+        h = self._conv(self._gn(h, d.norm_out, True), d.conv_out)
+        return h.float().contiguous()

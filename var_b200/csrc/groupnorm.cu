@@ -1,0 +1,137 @@
+// GroupNorm (+ SiLU) on NHWC bf16 activations for the VQVAE CNN decoder/encoder glue
+// (reference: models/basic_vae.py:18-19 Normalize = GroupNorm(32, C, eps=1e-6, affine) followed by F.silu, :57-58,:159,:225).
+// PyTorch runs this as moments + several elementwise passes over fp32/NCHW tensors (plus layout conversions around the
+// cuDNN NHWC convolutions); here it is two HBM-bound passes over the bf16 NHWC tensor: (1) per-CTA partial sums in a
+// fixed order (deterministic, no atomics), (2) normalise * gamma + beta, SiLU, store.
+#include "common.cuh"
+#include "host.h"
+#include "../../include/var_b200.h"
+
+namespace vb {
+
+constexpr int GN_THREADS = 256;
+constexpr int GN_PIX_PER_CTA = 512;  // pixels reduced by one CTA of the statistics pass
+
+// x: [B, HW, C] bf16. part: [B, nchunk, G, 2] fp32 (sum, sum of squares) of the chunk's pixels.
+__global__ void __launch_bounds__(GN_THREADS)
+gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ part, int HW, int C, int G) {
+  __shared__ float red[GN_THREADS][8][2];  // per-thread (sum, sum of squares) of its 8 channels
+  const int b = blockIdx.y, chunk = blockIdx.x, nchunk = gridDim.x;
+  const int nv = C >> 3;                  // 16-byte vectors per pixel
+  const int ppp = GN_THREADS / nv;        // pixels per pass
+  const int vl = threadIdx.x % nv, pl = threadIdx.x / nv;
+  const int cpg = C / G;
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
+  const int p0 = chunk * GN_PIX_PER_CTA, p1 = min(HW, p0 + GN_PIX_PER_CTA);
+  if (pl < ppp) {
+    for (int p = p0 + pl; p < p1; p += ppp) {
+      const uint4 v = *reinterpret_cast<const uint4*>(x + ((size_t)b * HW + p) * C + vl * 8);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(h[i]);
+        s[2 * i] += f.x; q[2 * i] += f.x * f.x;
+        s[2 * i + 1] += f.y; q[2 * i + 1] += f.y * f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { red[threadIdx.x][i][0] = s[i]; red[threadIdx.x][i][1] = q[i]; }
+  __syncthreads();
+  if (threadIdx.x < G) {  // one thread per group, fixed summation order: deterministic
+    const int g = threadIdx.x;
+    float ss = 0.f, qq = 0.f;
+    for (int r = 0; r < ppp; ++r)
+      for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+        const int t = r * nv + (c >> 3), i = c & 7;
+        ss += red[t][i][0];
+        qq += red[t][i][1];
+      }
+    float* o = part + (((size_t)b * nchunk + chunk) * G + g) * 2;
+    o[0] = ss;
+    o[1] = qq;
+  }
+}
+
+__global__ void __launch_bounds__(GN_THREADS)
+gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ part, int nchunk, const float* __restrict__ gamma,
+                const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, int HW, int C, int G, float eps, int silu,
+                int pix_per_cta) {
+  __shared__ float mean_s[64], rstd_s[64];
+  const int b = blockIdx.y;
+  const int cpg = C / G;
+  if (threadIdx.x < G) {
+    float s = 0.f, q = 0.f;
+    for (int c = 0; c < nchunk; ++c) {  // fixed order
+      const float* pp = part + (((size_t)b * nchunk + c) * G + threadIdx.x) * 2;
+      s += pp[0]; q += pp[1];
+    }
+    const float n = (float)HW * (float)cpg;
+    const float m = s / n;
+    const float var = fmaxf(q / n - m * m, 0.f);
+    mean_s[threadIdx.x] = m;
+    rstd_s[threadIdx.x] = rsqrtf(var + eps);
+  }
+  __syncthreads();
+  const int nv = C >> 3;
+  const int ppp = GN_THREADS / nv;
+  const int vl = threadIdx.x % nv, pl = threadIdx.x / nv;
+  if (pl >= ppp) return;
+  float sc[8], sf[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = vl * 8 + i, g = c / cpg;
+    const float a = rstd_s[g] * __ldg(gamma + c);
+    sc[i] = a;
+    sf[i] = __ldg(beta + c) - mean_s[g] * a;
+  }
+  const int p0 = blockIdx.x * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
+  for (int p = p0 + pl; p < p1; p += ppp) {
+    const size_t off = ((size_t)b * HW + p) * C + vl * 8;
+    const uint4 v = *reinterpret_cast<const uint4*>(x + off);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+    uint4 o;
+    uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(h[i]);
+      float a = fmaf(f.x, sc[2 * i], sf[2 * i]), c = fmaf(f.y, sc[2 * i + 1], sf[2 * i + 1]);
+      if (silu) { a = a / (1.f + __expf(-a)); c = c / (1.f + __expf(-c)); }
+      ow[i] = pack_bf16x2(a, c);
+    }
+    *reinterpret_cast<uint4*>(y + off) = o;
+  }
+}
+
+}  // namespace vb
+
+extern "C" size_t var_b200_gn_workspace(int B, int HW, int C, int groups) {
+  if (B <= 0 || HW <= 0 || groups <= 0) return 0;
+  const int nchunk = (HW + vb::GN_PIX_PER_CTA - 1) / vb::GN_PIX_PER_CTA;
+  return (size_t)B * nchunk * groups * 2 * sizeof(float);
+}
+
+extern "C" int var_b200_gn_silu_nhwc(const void* x, const float* gamma, const float* beta, void* y, int B, int HW, int C,
+                                     int groups, float eps, int apply_silu, void* work, size_t work_bytes, void* stream) {
+  using namespace vb;
+  VB_REQUIRE(x && gamma && beta && y && work, "gn: null pointer");
+  VB_REQUIRE(B > 0 && HW > 0 && C > 0 && C % 8 == 0 && groups > 0 && groups <= 64 && C % groups == 0 && C / 8 <= GN_THREADS,
+             "gn: unsupported shape B=%d HW=%d C=%d groups=%d", B, HW, C, groups);
+  VB_REQUIRE(B <= 65535, "gn: batch too large");
+  VB_REQUIRE(work_bytes >= var_b200_gn_workspace(B, HW, C, groups), "gn: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nchunk = (HW + GN_PIX_PER_CTA - 1) / GN_PIX_PER_CTA;
+  vb::ProfScope prof_scope(vb::PK_OTHER, st);
+  gn_stats_kernel<<<dim3(nchunk, B), GN_THREADS, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                          reinterpret_cast<float*>(work), HW, C, groups);
+  VB_CUDA_CHECK(cudaGetLastError());
+  const int ppc = 256;
+  gn_apply_kernel<<<dim3((HW + ppc - 1) / ppc, B), GN_THREADS, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const float*>(work), nchunk, gamma, beta,
+      reinterpret_cast<__nv_bfloat16*>(y), HW, C, groups, eps, apply_silu, ppc);
+  VB_CUDA_CHECK(cudaGetLastError());
+  vb::count_launch(2);
+  return VB_OK;
+}

@@ -103,6 +103,8 @@ def _declare(lib: C.CDLL) -> None:
         fn = getattr(lib, name)
         fn.argtypes = [C.POINTER(ModelDesc), i32] if name == "var_b200_ada_workspace" else [C.POINTER(ModelDesc), i32, i32]
         fn.restype = C.c_size_t
+    lib.var_b200_gn_workspace.argtypes = [i32, i32, i32, i32]
+    lib.var_b200_gn_workspace.restype = C.c_size_t
     lib.var_b200_quant_encode_workspace.argtypes = [C.POINTER(QuantDesc), i32]
     lib.var_b200_quant_encode_workspace.restype = C.c_size_t
 
@@ -125,6 +127,7 @@ def _EXTRA_SIGS(vp, i32, i64, f32):
         "var_b200_cfg_topk_sample": [vp, i32, i32, i32, i32, dbl, vp, i32, f32, vp, vp, vp],
         "var_b200_cfg_token_logprob": [vp, vp, vp, vp, i32, i32, i32, vp, vp],
         "var_b200_scale_sums": [vp, i32, i32, i32, C.POINTER(C.c_int), i32, vp, vp, vp],
+        "var_b200_gn_silu_nhwc": [vp, vp, vp, vp, i32, i32, i32, i32, f32, i32, vp, sz, vp],
         "var_b200_ada_ld": [C.POINTER(ModelDesc)],
         "var_b200_ada_params": [C.POINTER(ModelDesc), vp, i32, vp, vp, sz, vp],
         "var_b200_embed": [C.POINTER(ModelDesc), vp, i32, i32, vp, i32, i32, i32, i32, vp, vp],

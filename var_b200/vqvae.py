@@ -18,6 +18,7 @@ class VQVAE(nn.Module):
         super().__init__()
         self.test_mode = test_mode
         self.decoder_dtype = None  # set to torch.bfloat16 / float16 to run fhat_to_img through a 16-bit decoder copy
+        self.decoder_nhwc = True   # with decoder_dtype=bfloat16: channels-last plan with the fused GroupNorm+SiLU kernel
         self.V, self.Cvae = vocab_size, z_channels
         cfg = dict(ch=ch, ch_mult=(1, 1, 2, 2, 4), num_res_blocks=2, in_channels=3, z_channels=z_channels)
         self.encoder = Encoder(**cfg)
@@ -39,6 +40,11 @@ class VQVAE(nn.Module):
 
     # ---- decode side (vqvae.py:62-63, 77-90)
     def fhat_to_img(self, f_hat: torch.Tensor):
+        if self.decoder_dtype is torch.bfloat16 and f_hat.is_cuda and self.decoder_nhwc:
+            if getattr(self, "_nhwc_dec", None) is None:
+                from .basic_vae import NHWCDecoder
+                self._nhwc_dec = NHWCDecoder(self.decoder, self.post_quant_conv)
+            return self._nhwc_dec(f_hat).clamp_(-1, 1)
         if self.decoder_dtype is not None and f_hat.is_cuda:
             post, dec = self._low_precision_decoder()
             return dec(post(f_hat.to(self.decoder_dtype))).float().clamp_(-1, 1)
