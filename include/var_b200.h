@@ -231,8 +231,16 @@ VAR_B200_API int var_b200_scale_sums(const float* tok_logp, int n_seq, int L, in
  * GroupNorm (+SiLU) on NHWC bf16 tensors: glue of the VQVAE CNN decoder/encoder around the cuDNN convolutions
  * (models/basic_vae.py:18-19,57-58,159,225). x, y: bf16 [B, HW, C]; gamma, beta: fp32 [C]. Deterministic. */
 VAR_B200_API size_t var_b200_gn_workspace(int B, int HW, int C, int groups);
-VAR_B200_API int var_b200_gn_silu_nhwc(const void* x, const float* gamma, const float* beta, void* y, int B, int HW, int C,
-                                       int groups, float eps, int apply_silu, void* work, size_t work_bytes, void* stream);
+/* pre_bias: NULL or fp32 [C], added to x before the statistics (folds the bias of the producing convolution). */
+VAR_B200_API int var_b200_gn_silu_nhwc(const void* x, const float* pre_bias, const float* gamma, const float* beta, void* y,
+                                       int B, int HW, int C, int groups, float eps, int apply_silu, void* work,
+                                       size_t work_bytes, void* stream);
+/* out = a (+ bias_a[c]) + b (+ bias_b[c]) on bf16 NHWC tensors of n_pixels x C; b, bias_a, bias_b may be NULL; out may
+ * alias a (residual add of ResnetBlock with the convolution biases folded in, basic_vae.py:60). */
+VAR_B200_API int var_b200_add_bias_nhwc(const void* a, const float* bias_a, const void* b, const float* bias_b, void* out,
+                                        long long n_pixels, int C, void* stream);
+/* y[B,2H,2W,C] = nearest-2x(x[B,H,W,C]) (+ bias[c]) (basic_vae.py:22-28). */
+VAR_B200_API int var_b200_upsample2x_nhwc(const void* x, const float* bias, void* y, int B, int H, int W, int C, void* stream);
 
 #ifdef __cplusplus
 }

@@ -142,32 +142,40 @@ class Decoder(nn.Module):
 
 
 class NHWCDecoder:
-    """16-bit channels-last execution plan of a `Decoder` (+ post_quant_conv): the convolutions run on cuDNN's NHWC
-    tensor-core kernels without layout conversions, GroupNorm+SiLU runs as var_b200's two-pass NHWC kernel
-    (csrc/groupnorm.cu), residual adds stay 16-bit. Same function as Decoder.forward(post_quant_conv(f_hat)) up to
-    16-bit rounding (tests/test_parity_gpu.py::test_nhwc_decoder_matches_pytorch_decoder)."""
+    """16-bit channels-last execution plan of a `Decoder` (+ post_quant_conv). The convolutions run bias-free on
+    cuDNN's NHWC tensor-core kernels (no layout conversions); everything between them is var_b200's NHWC glue
+    (csrc/groupnorm.cu): GroupNorm+SiLU in two passes with the producing convolution's bias folded in, the residual add
+    with both convolution biases folded in, nearest-2x up-sampling. Same function as
+    Decoder.forward(post_quant_conv(f_hat)) up to 16-bit rounding
+    (tests/test_parity_gpu.py::test_nhwc_decoder_matches_pytorch_decoder)."""
 
     def __init__(self, decoder: Decoder, post_quant_conv: nn.Conv2d, dtype=torch.bfloat16):
         if dtype != torch.bfloat16:
-            raise NotImplementedError("the NHWC GroupNorm kernel is bf16")
+            raise NotImplementedError("the NHWC glue kernels are bf16")
         self.dtype = dtype
         self.dec = decoder
         self.post = post_quant_conv
         self._w = {}
+        from . import lib as L
+        self.L, self.lib = L, L.load()
 
-    def _conv(self, x, m: nn.Conv2d, stride=1, padding=None):
+    # ---- cached 16-bit / fp32 parameter copies
+    def _cw(self, m: nn.Conv2d):
         w = self._w.get(id(m))
         if w is None or w[2] != (m.weight._version, m.bias._version):
             w = (m.weight.detach().to(self.dtype).contiguous(memory_format=torch.channels_last),
-                 m.bias.detach().to(self.dtype), (m.weight._version, m.bias._version))
+                 m.bias.detach().float().contiguous(), (m.weight._version, m.bias._version))
             self._w[id(m)] = w
-        pad = m.padding if padding is None else padding
-        return F.conv2d(x, w[0], w[1], stride=m.stride, padding=pad)
+        return w
 
-    def _gn(self, x, m: nn.GroupNorm, silu: bool):
-        import ctypes as C
-        from . import lib as L
-        lib = L.load()
+    def _conv(self, x, m: nn.Conv2d):
+        """bias-free convolution; the caller folds `self._cw(m)[1]` into the consumer kernel"""
+        return F.conv2d(x, self._cw(m)[0], None, stride=m.stride, padding=m.padding)
+
+    def _bias(self, m):
+        return self._cw(m)[1]
+
+    def _gn(self, x, m: nn.GroupNorm, silu: bool, pre_bias=None):
         B, Cc, H, W = x.shape
         assert x.is_contiguous(memory_format=torch.channels_last) and x.dtype == torch.bfloat16
         p = self._w.get(id(m))
@@ -176,25 +184,36 @@ class NHWCDecoder:
                  (m.weight._version, m.bias._version))
             self._w[id(m)] = p
         y = torch.empty_like(x)  # preserves channels_last
-        ws = torch.empty(lib.var_b200_gn_workspace(B, H * W, Cc, m.num_groups), dtype=torch.uint8, device=x.device)
-        L.check(lib.var_b200_gn_silu_nhwc(x.data_ptr(), p[0].data_ptr(), p[1].data_ptr(), y.data_ptr(), B, H * W, Cc,
-                                          m.num_groups, m.eps, int(silu), ws.data_ptr(), ws.numel(), L.current_stream()),
-                "gn_silu_nhwc")
+        ws = torch.empty(self.lib.var_b200_gn_workspace(B, H * W, Cc, m.num_groups), dtype=torch.uint8, device=x.device)
+        self.L.check(self.lib.var_b200_gn_silu_nhwc(x.data_ptr(), self.L.ptr(pre_bias), p[0].data_ptr(), p[1].data_ptr(),
+                                                    y.data_ptr(), B, H * W, Cc, m.num_groups, m.eps, int(silu),
+                                                    ws.data_ptr(), ws.numel(), self.L.current_stream()), "gn_silu_nhwc")
         return y
+
+    def _add(self, a, bias_a, b, bias_b, out=None):
+        B, Cc, H, W = a.shape
+        out = torch.empty_like(a) if out is None else out
+        self.L.check(self.lib.var_b200_add_bias_nhwc(a.data_ptr(), self.L.ptr(bias_a), self.L.ptr(b), self.L.ptr(bias_b),
+                                                     out.data_ptr(), B * H * W, Cc, self.L.current_stream()), "add_bias_nhwc")
+        return out
 
     def _res(self, x, blk: ResnetBlock):
         h = self._conv(self._gn(x, blk.norm1, True), blk.conv1)
-        h = self._conv(self._gn(h, blk.norm2, True), blk.conv2)
-        sc = x if isinstance(blk.nin_shortcut, nn.Identity) else self._conv(x, blk.nin_shortcut)
-        return sc + h
+        h = self._conv(self._gn(h, blk.norm2, True, pre_bias=self._bias(blk.conv1)), blk.conv2)
+        if isinstance(blk.nin_shortcut, nn.Identity):
+            return self._add(h, self._bias(blk.conv2), x, None, out=h)
+        sc = self._conv(x, blk.nin_shortcut)
+        return self._add(h, self._bias(blk.conv2), sc, self._bias(blk.nin_shortcut), out=h)
 
     def _attn(self, x, blk: AttnBlock):
         B, Cc, H, W = x.shape
-        qkv = self._conv(self._gn(x, blk.norm, False), blk.qkv)               # [B,3C,H,W] channels_last
+        qkv = self._conv(self._gn(x, blk.norm, False), blk.qkv)               # [B,3C,H,W] channels_last, no bias yet
+        qkv = self._add(qkv, self._bias(blk.qkv), None, None, out=qkv)
         q, k, v = qkv.permute(0, 2, 3, 1).reshape(B, H * W, 3 * Cc).chunk(3, dim=-1)
         o = F.scaled_dot_product_attention(q, k, v, scale=float(Cc) ** -0.5)   # [B,HW,C]
         o = o.reshape(B, H, W, Cc).permute(0, 3, 1, 2)                         # channels_last view
-        return x + self._conv(o, blk.proj_out)
+        p = self._conv(o, blk.proj_out)
+        return self._add(p, self._bias(blk.proj_out), x, None, out=p)
 
     def _level(self, h, lvl):
         for i, blk in enumerate(lvl.block):
@@ -203,17 +222,28 @@ class NHWCDecoder:
                 h = self._attn(h, lvl.attn[i])
         return h
 
+    def _upsample(self, h, conv: nn.Conv2d):
+        B, Cc, H, W = h.shape
+        up = torch.empty((B, Cc, 2 * H, 2 * W), dtype=h.dtype, device=h.device, memory_format=torch.channels_last)
+        self.L.check(self.lib.var_b200_upsample2x_nhwc(h.data_ptr(), None, up.data_ptr(), B, H, W, Cc,
+                                                       self.L.current_stream()), "upsample2x_nhwc")
+        y = self._conv(up, conv)
+        return self._add(y, self._bias(conv), None, None, out=y)
+
     @torch.no_grad()
     def __call__(self, f_hat: torch.Tensor) -> torch.Tensor:
         d = self.dec
         x = f_hat.to(self.dtype).contiguous(memory_format=torch.channels_last)
-        h = self._conv(self._conv(x, self.post), d.conv_in)
+        h = self._conv(x, self.post)
+        h = self._conv(self._add(h, self._bias(self.post), None, None, out=h), d.conv_in)
+        h = self._add(h, self._bias(d.conv_in), None, None, out=h)
         h = self._res(h, d.mid.block_1)
         h = self._attn(h, d.mid.attn_1)
         h = self._res(h, d.mid.block_2)
         for lvl in reversed(d.up):
             h = self._level(h, lvl)
             if hasattr(lvl, "upsample"):
-                h = self._conv(F.interpolate(h, scale_factor=2, mode="nearest"), lvl.upsample.conv)
-        h = self._conv(self._gn(h, d.norm_out, True), d.conv_out)
+                h = self._upsample(h, lvl.upsample.conv)
+        w, b, _ = self._cw(d.conv_out)
+        h = F.conv2d(self._gn(h, d.norm_out, True), w, b.to(self.dtype), padding=d.conv_out.padding)  # 3 channels: torch adds the bias
         return h.float().contiguous()
