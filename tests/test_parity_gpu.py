@@ -343,3 +343,25 @@ def test_nhwc_decoder_matches_pytorch_decoder():
         assert torch.equal(vae.fhat_to_img(f_hat), got)
     finally:
         vae.decoder_dtype = None
+
+
+def test_quant_search_paths_agree_fuzz():
+    """Tensor-core filter + exact re-rank vs the fused fp32 search on many random feature maps (scales from tiny to
+    huge, clustered values that create near-ties): every one of the 20 x 32 x 680 indices must agree."""
+    vae, _ = seeded_models(device=DEV)
+    g = torch.Generator(device=DEV).manual_seed(1234)
+    cb = vae.quantize.embedding.weight
+    try:
+        for trial in range(20):
+            sigma = [1e-3, 0.1, 0.5, 1.0, 2.0, 5.0, 20.0][trial % 7]
+            f = torch.randn(32, 32, 16, 16, device=DEV, generator=g) * sigma
+            if trial % 3 == 0:  # snap to codebook vectors plus small noise: the first scales land on near-ties
+                pick = torch.randint(0, cb.shape[0], (32, 16, 16), device=DEV, generator=g)
+                f = cb[pick].permute(0, 3, 1, 2).contiguous() + 1e-3 * f
+            vae.quantize.search_mode = 0
+            a = torch.cat(vae.quantize.f_to_idxBl_or_fhat(f, to_fhat=False), dim=1)
+            vae.quantize.search_mode = 1
+            b = torch.cat(vae.quantize.f_to_idxBl_or_fhat(f, to_fhat=False), dim=1)
+            assert torch.equal(a, b), f"trial {trial} sigma {sigma}: {(a != b).sum().item()} indices differ"
+    finally:
+        vae.quantize.search_mode = 0
