@@ -365,3 +365,22 @@ def test_quant_search_paths_agree_fuzz():
             assert torch.equal(a, b), f"trial {trial} sigma {sigma}: {(a != b).sum().item()} indices differ"
     finally:
         vae.quantize.search_mode = 0
+
+
+def test_nhwc_encoder_matches_pytorch_encoder():
+    """Channels-last bf16 encoder plan vs the fp32 PyTorch encoder (models/basic_vae.py:99-160 + quant_conv)."""
+    vae, _ = seeded_models(device=DEV)
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator().manual_seed(3)
+    img = (torch.rand(2, 3, 256, 256, generator=g) * 2 - 1).to(DEV)
+    ref = vae.img_to_post(img)
+    vae.encoder_dtype = torch.bfloat16
+    try:
+        got = vae.img_to_post(img)
+        again = vae.img_to_post(img)
+    finally:
+        vae.encoder_dtype = None
+    assert got.shape == ref.shape == (2, 32, 16, 16) and got.dtype == torch.float32
+    rel = ((got - ref).abs().max() / ref.abs().max()).item()
+    print(f"nhwc encoder rel err {rel:.4f}")
+    assert rel < 5e-2 and torch.equal(got, again)

@@ -247,3 +247,32 @@ class NHWCDecoder:
         w, b, _ = self._cw(d.conv_out)
         h = F.conv2d(self._gn(h, d.norm_out, True), w, b.to(self.dtype), padding=d.conv_out.padding)  # 3 channels: torch adds the bias
         return h.float().contiguous()
+
+
+class NHWCEncoder(NHWCDecoder):
+    """Channels-last 16-bit plan of `Encoder` (+ quant_conv): same glue kernels as NHWCDecoder; Downsample2x is the
+    reference's asymmetric (0,1,0,1) zero pad followed by a stride-2 convolution (models/basic_vae.py:31-37)."""
+
+    def __init__(self, encoder: Encoder, quant_conv: nn.Conv2d, dtype=torch.bfloat16):
+        super().__init__(encoder, quant_conv, dtype)
+        self.enc = encoder
+        self.qconv = quant_conv
+
+    @torch.no_grad()
+    def __call__(self, img: torch.Tensor) -> torch.Tensor:
+        e = self.enc
+        x = img.to(self.dtype).contiguous(memory_format=torch.channels_last)
+        w, b, _ = self._cw(e.conv_in)
+        h = F.conv2d(x, w, b.to(self.dtype), padding=e.conv_in.padding)  # 3 input channels: let torch add the bias
+        for lvl in e.down:
+            h = self._level(h, lvl)
+            if hasattr(lvl, "downsample"):
+                y = self._conv(F.pad(h, (0, 1, 0, 1)), lvl.downsample.conv)
+                h = self._add(y, self._bias(lvl.downsample.conv), None, None, out=y)
+        h = self._res(h, e.mid.block_1)
+        h = self._attn(h, e.mid.attn_1)
+        h = self._res(h, e.mid.block_2)
+        h = self._conv(self._gn(h, e.norm_out, True), e.conv_out)
+        h = self._conv(self._add(h, self._bias(e.conv_out), None, None, out=h), self.qconv)
+        h = self._add(h, self._bias(self.qconv), None, None, out=h)
+        return h.float().contiguous()  # fp32 NCHW features for the quantizer

@@ -19,6 +19,8 @@ class VQVAE(nn.Module):
         self.test_mode = test_mode
         self.decoder_dtype = None  # set to torch.bfloat16 / float16 to run fhat_to_img through a 16-bit decoder copy
         self.decoder_nhwc = True   # with decoder_dtype=bfloat16: channels-last plan with the fused GroupNorm+SiLU kernel
+        self.encoder_dtype = None  # torch.bfloat16: channels-last 16-bit encoder plan (token indices then depend on bf16
+        #                            rounding of the features; the default fp32 encoder keeps them reference-exact)
         self.V, self.Cvae = vocab_size, z_channels
         cfg = dict(ch=ch, ch_mult=(1, 1, 2, 2, 4), num_res_blocks=2, in_channels=3, z_channels=z_channels)
         self.encoder = Encoder(**cfg)
@@ -71,6 +73,11 @@ class VQVAE(nn.Module):
 
     # ---- encode side (vqvae.py:65-75, 92-98)
     def img_to_post(self, inp_img_no_grad: torch.Tensor, v_patch_nums=None):
+        if self.encoder_dtype is torch.bfloat16 and inp_img_no_grad.is_cuda:
+            if getattr(self, "_nhwc_enc", None) is None:
+                from .basic_vae import NHWCEncoder
+                self._nhwc_enc = NHWCEncoder(self.encoder, self.quant_conv)
+            return self._nhwc_enc(inp_img_no_grad)
         return self.quant_conv(self.encoder(inp_img_no_grad))
 
     def img_to_idxBl(self, inp_img_no_grad: torch.Tensor,
