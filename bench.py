@@ -348,6 +348,8 @@ def main():
     # (b) alone: fc1 at the step's largest shape, 20 launches, against the BURST measured peak.
     depth = wl["depth"]
     C_ = 64 * depth
+    ncu_path = ROOT / "profiles" / "r01_ncu_gemm_d30_fc1.json"
+    ncu_traffic = json.loads(ncu_path.read_text()) if ncu_path.exists() else {}
     n_seq_step = (2 * wl["batch"]) if wl["kind"] == "sample" else (shard_hi - shard_lo)
     gemm_flops = n_seq_step * (24.0 * C_ * C_ * depth * L_SEQ + 2.0 * C_ * V * L_SEQ + 12.0 * C_ * C_ * depth + 4.0 * C_ * C_)
     barrier()
@@ -363,7 +365,10 @@ def main():
     step_tf = value / world * fl_img / 1e12
     roofline = dict(bound="tensor", kernel="gemm_bf16_kernel<BN,EPI,2> (all fused epilogues of the step)",
                     achieved=gemm_tf_step, peak=pk["sustained"], unit="TFLOP/s", frac=gemm_tf_step / pk["sustained"],
-                    traffic=None,
+                    traffic=ncu_traffic.get("traffic_GB") if wl["kind"] == "sample" and depth == 30 else None,
+                    traffic_note=("GB per launch of the largest GEMM of the step (" + ncu_traffic.get("kernel", "") + "), ncu "
+                                  "--set full dram read+write, vs %.3f GB algorithmic (profiles/r01_ncu_gemm_d30_fc1.json)"
+                                  % ncu_traffic.get("algorithmic_GB", 0.0)) if ncu_traffic else None,
                     peak_source=f"{pk['src']} MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)",
                     gemm_share_of_kernel_time=gemm_ms / all_ms,
                     kernel_ms={k: round(v, 3) for k, v in sorted(kp.ms.items(), key=lambda kv: -kv[1])},
