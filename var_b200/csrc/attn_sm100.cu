@@ -29,7 +29,7 @@ namespace vb {
 constexpr int ATT_BM = 128;  // query rows per CTA
 constexpr int ATT_BN = 64;   // keys per tile
 constexpr int ATT_D = 64;    // head dim
-constexpr int ATT_THREADS = 160;   // 4 softmax warps + 1 issuer warp
+constexpr int ATT_THREADS = 192;   // 4 softmax warps + TMA producer warp + UMMA issuer warp
 constexpr int ATT_KST = 4;                        // K ring depth (QK runs two tiles ahead of the softmax)
 constexpr int ATT_VST = 3;                        // V ring depth
 constexpr int ATT_SST = 3;                        // S buffers in TMEM
@@ -38,6 +38,10 @@ constexpr int ATT_KV_BYTES = ATT_BN * ATT_D * 2;  // 8 KB
 constexpr int ATT_P_BYTES = ATT_BM * ATT_BN * 2;  // 16 KB
 constexpr int ATT_SMEM = 2 * ATT_Q_BYTES + (ATT_KST + ATT_VST) * ATT_KV_BYTES + ATT_P_BYTES + 1024;  // 2 Q buffers; sP: output staging
 constexpr float ATT_RESCALE_LOG2 = 80.f;
+constexpr int ATT_NBAR = 3 + ATT_KST + ATT_VST + 2 * ATT_SST + 2 + 2 + ATT_KST + ATT_VST;
+#ifndef ATT_POLY_EXP
+#define ATT_POLY_EXP 0
+#endif
 
 struct AttnLevels {
   int n;
@@ -54,8 +58,27 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128_attn(uint32_t smem_addr) 
   return d;
 }
 
+// 2^x for two values on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f with the 1.5*2^23 trick,
+// degree-3 minimax polynomial for 2^f on [-0.5, 0.5] (max relative error 7.5e-5, far below the bf16 rounding of P),
+// exponent patched in with one shift-add. Inputs are clamped at -126 (masked keys give 2^-126 ~ 1e-38 instead of 0).
+// Half of the exponentials of a tile take this path so that the 16-lane MUFU unit is no longer the per-warp limiter.
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -126.f);
+  x.y = fmaxf(x.y, -126.f);
+  const float2 t = __fadd2_rn(x, make_float2(12582912.f, 12582912.f));
+  const float2 nf = __fadd2_rn(t, make_float2(-12582912.f, -12582912.f));
+  const float2 f = __ffma2_rn(nf, make_float2(-1.f, -1.f), x);
+  float2 p = __ffma2_rn(f, make_float2(0.0551716685f, 0.0551716685f), make_float2(0.2426111251f, 0.2426111251f));
+  p = __ffma2_rn(p, f, make_float2(0.6932609677f, 0.6932609677f));
+  p = __ffma2_rn(p, f, make_float2(0.9999280572f, 0.9999280572f));
+  float2 r;
+  r.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
+  r.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
+  return r;
+}
+
 // Work item = (sequence, head, 128-row query tile). A CTA walks items blockIdx.x, blockIdx.x + gridDim.x, ... and
-// prefetches the K/V tile stream across item boundaries (the launcher currently gives every CTA exactly one item).
+// prefetches the K/V tile stream and the next Q tile across item boundaries.
 struct AttnItem {
   int item, j, n_kt, bh, row0;
 };
@@ -65,7 +88,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
             const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, int Lq, int H, int q_pos0,
             const __grid_constant__ AttnLevels lv, int n_qt, int total_items) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t bars[3 + ATT_KST + ATT_VST + ATT_SST + 4];  // q[2] | oread | k[] | v[] | s[] | p[2] | pv[2]
+  __shared__ uint64_t bars[ATT_NBAR];  // q[2] | oread | k[] | v[] | s[] | p[] | pv[2] | qfree[2] | kfree[] | vfree[]
   __shared__ uint32_t tmem_base_smem;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = base;
@@ -79,7 +102,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   auto bar_v = [&](int s) { return smem_u32(&bars[3 + ATT_KST + s]); };
   auto bar_s = [&](int s) { return smem_u32(&bars[3 + ATT_KST + ATT_VST + s]); };
   auto bar_p = [&](int s) { return smem_u32(&bars[3 + ATT_KST + ATT_VST + ATT_SST + s]); };
-  auto bar_pv = [&](int s) { return smem_u32(&bars[5 + ATT_KST + ATT_VST + ATT_SST + s]); };
+  auto bar_pv = [&](int s) { return smem_u32(&bars[3 + ATT_KST + ATT_VST + 2 * ATT_SST + s]); };
+  auto bar_qfree = [&](int s) { return smem_u32(&bars[5 + ATT_KST + ATT_VST + 2 * ATT_SST + s]); };
+  auto bar_kfree = [&](int s) { return smem_u32(&bars[7 + ATT_KST + ATT_VST + 2 * ATT_SST + s]); };
+  auto bar_vfree = [&](int s) { return smem_u32(&bars[7 + 2 * ATT_KST + ATT_VST + 2 * ATT_SST + s]); };
 
   auto kv_end_of = [&](int row) {  // visible keys of query row `row` of this call's query block
     // lv.end is padded with the sequence length up to VB_MAX_SCALES: fixed trip count, constant-bank operands
@@ -116,10 +142,15 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     for (int s = 0; s < ATT_KST; ++s) mbar_init(bar_k(s), 1);
     for (int s = 0; s < ATT_VST; ++s) mbar_init(bar_v(s), 1);
     for (int s = 0; s < ATT_SST; ++s) mbar_init(bar_s(s), 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(bar_p(s), 4); mbar_init(bar_pv(s), 1); }
+    // bar_p is a ring as deep as the S ring: the softmax may run up to two tiles ahead of the issuer's bar_p wait, and
+    // a two-deep ring would let tile g+2 complete a second phase of tile g's barrier before the issuer looked at it
+    for (int s = 0; s < ATT_SST; ++s) mbar_init(bar_p(s), 4);
+    for (int s = 0; s < 2; ++s) { mbar_init(bar_pv(s), 1); mbar_init(bar_qfree(s), 1); }
+    for (int s = 0; s < ATT_KST; ++s) mbar_init(bar_kfree(s), 1);
+    for (int s = 0; s < ATT_VST; ++s) mbar_init(bar_vfree(s), 1);
     mbar_fence_init();
   }
-  if (warp == 4) tmem_alloc(smem_u32(&tmem_base_smem), 256);
+  if (warp == 5) tmem_alloc(smem_u32(&tmem_base_smem), 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -127,87 +158,97 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   const uint32_t tmem_o = tmem + ATT_SST * 64;  // S ring in columns [0,192), O in [192,256)
 
   if (warp == 4) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_BM, ATT_BN);
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BM, ATT_D) | (1u << 16);  // B (V) is MN-major
-      AttnItem cur{(int)blockIdx.x, 0, 0, 0, 0};
-      decode(cur);
-      AttnItem kc = cur, vc = cur;  // K / V load cursors run ahead of the compute cursor along the tile stream
-      int kpos = 0, vpos = 0;
-      auto load_k = [&]() {
-        const int st = kpos % ATT_KST;
-        mbar_expect_tx(bar_k(st), ATT_KV_BYTES);
-        tma_load_3d(&tmK, bar_k(st), sK + st * ATT_KV_BYTES, 0, kc.j * ATT_BN, kc.bh);
-        next_tile(kc);
-        ++kpos;
-      };
-      auto load_v = [&]() {
-        const int st = vpos % ATT_VST;
-        mbar_expect_tx(bar_v(st), ATT_KV_BYTES);
-        tma_load_3d(&tmV, bar_v(st), sV + st * ATT_KV_BYTES, 0, vc.j * ATT_BN, vc.bh);
-        next_tile(vc);
-        ++vpos;
-      };
-      auto load_q = [&](const AttnItem& c, int it_) {  // Q tiles are double-buffered across items
-        mbar_expect_tx(bar_q(it_ & 1), ATT_Q_BYTES);
-        tma_load_3d(&tmQ, bar_q(it_ & 1), sQ + (it_ & 1) * ATT_Q_BYTES, 0, c.row0, c.bh);
-      };
-      if (cur.item < total_items) load_q(cur, 0);
-      for (int i = 0; i < ATT_KST; ++i)
-        if (kc.item < total_items) load_k();
-      for (int i = 0; i < ATT_VST; ++i)
-        if (vc.item < total_items) load_v();
-      uint64_t qd = 0;
-      auto issue_qk = [&](int g) {  // g: global key-tile index of this CTA
-        const int st = g % ATT_KST;
-        mbar_wait(bar_k(st), (g / ATT_KST) & 1);
-        tc_fence_after();
-        const uint64_t kd = umma_desc_k_sw128(sK + st * ATT_KV_BYTES);
-#pragma unroll
-        for (int k = 0; k < ATT_D / 16; ++k)
-          umma_bf16_ss(tmem + (g % ATT_SST) * 64, qd + 2 * k, kd + 2 * k, idesc_qk, k != 0);
-        umma_commit(bar_s(g % ATT_SST));
-      };
-      int G = 0, it = 0;
-      while (cur.item < total_items) {
-        const int n_kt = cur.n_kt;
-        {  // prefetch the next item's queries into the other Q buffer (its last reader, item it-1, has finished)
-          AttnItem nx = cur;
-          next_item(nx);
-          if (nx.item < total_items) load_q(nx, it + 1);
+    // ------------------------------ TMA producer warp (warp-uniform loop, one elected lane issues) ------------------
+    // Stream order: for every item [Q tile], then per key tile K, V. Ring slots are handed back by tcgen05.commit
+    // from the MMA warp (bar_kfree / bar_vfree / bar_qfree), so this warp never looks at the softmax barriers.
+    AttnItem c{(int)blockIdx.x, 0, 0, 0, 0};
+    decode(c);
+    int kst = 0, kph = 0, vst = 0, vph = 0, qit = 0;
+    while (c.item < total_items) {
+      if (c.j == 0) {
+        mbar_wait(bar_qfree(qit & 1), ((qit >> 1) & 1) ^ 1);
+        if (elect_one_sync()) {
+          mbar_expect_tx(bar_q(qit & 1), ATT_Q_BYTES);
+          tma_load_3d(&tmQ, bar_q(qit & 1), sQ + (qit & 1) * ATT_Q_BYTES, 0, c.row0, c.bh);
         }
-        mbar_wait(bar_q(it & 1), (it >> 1) & 1);
-        qd = umma_desc_k_sw128(sQ + (it & 1) * ATT_Q_BYTES);
-        // QK runs two tiles ahead of the softmax (the tcgen05 issue->commit->mbarrier round trip is ~1 us)
-        issue_qk(G);
-        if (n_kt > 1) issue_qk(G + 1);
-        for (int j = 0; j < n_kt; ++j) {
-          const int g = G + j;
-          // S[(g+2)%3] was last read by the softmax of tile g-1, whose bar_p this thread has already observed
-          if (j + 2 < n_kt) issue_qk(g + 2);
-          mbar_wait(bar_p(g & 1), (g >> 1) & 1);  // P_g written; QK_g therefore complete
-          tc_fence_after();
-          if (kc.item < total_items) load_k();  // stream position g + ATT_KST reuses the K stage of tile g
-          const int st = g % ATT_VST;
-          mbar_wait(bar_v(st), (g / ATT_VST) & 1);
-          if (j == 0 && it > 0) mbar_wait(bar_oread, (it - 1) & 1);  // previous item's output has left TMEM
-          tc_fence_after();
-          const uint32_t p_tmem = tmem + (g % ATT_SST) * 64;  // P_g sits in the first 32 columns of S_g's buffer
+        ++qit;
+      }
+      mbar_wait(bar_kfree(kst), kph ^ 1);
+      if (elect_one_sync()) {
+        mbar_expect_tx(bar_k(kst), ATT_KV_BYTES);
+        tma_load_3d(&tmK, bar_k(kst), sK + kst * ATT_KV_BYTES, 0, c.j * ATT_BN, c.bh);
+      }
+      if (++kst == ATT_KST) { kst = 0; kph ^= 1; }
+      mbar_wait(bar_vfree(vst), vph ^ 1);
+      if (elect_one_sync()) {
+        mbar_expect_tx(bar_v(vst), ATT_KV_BYTES);
+        tma_load_3d(&tmV, bar_v(vst), sV + vst * ATT_KV_BYTES, 0, c.j * ATT_BN, c.bh);
+      }
+      if (++vst == ATT_VST) { vst = 0; vph ^= 1; }
+      next_tile(c);
+    }
+  } else if (warp == 5) {
+    // ------------------------------ UMMA issuer warp (warp-uniform loop, one elected lane issues) -------------------
+    constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_BM, ATT_BN);
+    constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BM, ATT_D) | (1u << 16);  // B (V) is MN-major
+    AttnItem cur{(int)blockIdx.x, 0, 0, 0, 0};
+    decode(cur);
+    int kst = 0, kph = 0;            // K ring cursor of the next QK
+    int qs = 0, qsph = 0;            // S ring cursor of the next QK
+    int vst = 0, vph = 0;            // V ring cursor of the next P V
+    int ps = 0, pph = 0;             // S/P ring cursor of the next P V
+    int pvb = 0;                     // bar_pv slot of the next P V (tile parity)
+    int it = 0;
+    uint64_t qd = 0;
+    auto issue_qk = [&]() {
+      mbar_wait(bar_k(kst), kph);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint64_t kd = umma_desc_k_sw128(sK + kst * ATT_KV_BYTES);
+#pragma unroll
+        for (int k = 0; k < ATT_D / 16; ++k) umma_bf16_ss(tmem + qs * 64, qd + 2 * k, kd + 2 * k, idesc_qk, k != 0);
+        umma_commit(bar_s(qs));
+        umma_commit(bar_kfree(kst));  // the K stage returns to the producer when this QK has completed
+      }
+      __syncwarp();
+      if (++kst == ATT_KST) { kst = 0; kph ^= 1; }
+      if (++qs == ATT_SST) { qs = 0; qsph ^= 1; }
+    };
+    while (cur.item < total_items) {
+      const int n_kt = cur.n_kt;
+      mbar_wait(bar_q(it & 1), (it >> 1) & 1);
+      qd = umma_desc_k_sw128(sQ + (it & 1) * ATT_Q_BYTES);
+      // QK runs two tiles ahead of the softmax. S[(g+2)%3] was last read by the softmax of tile g-1 and by P V_{g-1},
+      // both ordered before this QK (bar_p observed / same in-order tensor pipe).
+      issue_qk();
+      if (n_kt > 1) issue_qk();
+      for (int j = 0; j < n_kt; ++j) {
+        if (j + 2 < n_kt) issue_qk();
+        if (j + 2 == n_kt - 1 || (n_kt <= 2 && j == 0)) {  // last QK of this item issued: Q buffer may be refilled
+          if (elect_one_sync()) umma_commit(bar_qfree(it & 1));
+          __syncwarp();
+        }
+        mbar_wait(bar_p(ps), pph);  // P_g written; QK_g therefore complete
+        mbar_wait(bar_v(vst), vph);
+        if (j == 0 && it > 0) mbar_wait(bar_oread, (it - 1) & 1);  // previous item's output has left TMEM
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const uint32_t p_tmem = tmem + ps * 64;  // P_g sits in the first 32 columns of S_g's buffer
 #pragma unroll
           for (int k = 0; k < ATT_BN / 16; ++k) {  // 16 keys = 8 packed columns per K-step
-            const uint64_t vd = umma_desc_mn_sw128_attn(sV + st * ATT_KV_BYTES + k * 2048);
+            const uint64_t vd = umma_desc_mn_sw128_attn(sV + vst * ATT_KV_BYTES + k * 2048);
             umma_bf16_ts(tmem_o, p_tmem + 8 * k, vd, idesc_pv, (j | k) != 0);
           }
-          umma_commit(bar_pv(g & 1));
-          if (g >= 1 && vc.item < total_items) {  // stream position g + 2 reuses the V stage of tile g - 1
-            mbar_wait(bar_pv((g - 1) & 1), ((g - 1) >> 1) & 1);
-            load_v();
-          }
+          umma_commit(bar_pv(pvb));
+          umma_commit(bar_vfree(vst));
         }
-        G += n_kt;
-        ++it;
-        next_item(cur);
+        __syncwarp();
+        if (++vst == ATT_VST) { vst = 0; vph ^= 1; }
+        if (++ps == ATT_SST) { ps = 0; pph ^= 1; }
+        pvb ^= 1;
       }
+      ++it;
+      next_item(cur);
     }
   } else {
     // ------------------------------ softmax / output warps ------------------------------
@@ -217,17 +258,67 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     AttnItem cur{(int)blockIdx.x, 0, 0, 0, 0};
     decode(cur);
     int G = 0;
-    while (cur.item < total_items) {
-      const int n_kt = cur.n_kt;
-      const int row = cur.row0 + warp * 32 + lane;
-      const int kv_end = kv_end_of(row);
-      const int head = cur.bh % H, seq = cur.bh / H;
-      float m_ref2 = 0.f;  // reference maximum, pre-multiplied by log2(e)
-      float l_run = 0.f;
-      for (int j = 0; j < n_kt; ++j) {
+    // ---- item epilogue: O / l -> bf16, staged through this warp's own rows of sP for coalesced 128-byte rows. It runs
+    // one tile late: after the softmax of the next item's first key tile, when the last P V of the item has long
+    // completed, so the softmax warps never sit out the P V latency at an item boundary. ----
+    bool pend_valid = false;
+    int pend_row0 = 0, pend_bh = 0, pend_g = 0;
+    float pend_inv = 0.f;
+    auto write_out = [&]() {
+      mbar_wait(bar_pv(pend_g & 1), (pend_g >> 1) & 1);  // all P V of that item (and everything before) complete
+      tc_fence_after();
+      const float inv = pend_inv;
+      const int head = pend_bh % H, seq = pend_bh / H;
+      float o[64];
+      __syncwarp();
+      tmem_ld_32x32(tmem_o + lane_off, o);
+      tmem_ld_32x32(tmem_o + lane_off + 32, o + 32);
+      tmem_ld_wait_dep(o);
+      tmem_ld_wait_dep(o + 32);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_oread);  // the issuer may overwrite O with the next item's first P V
+      const uint32_t stg = sP + (uint32_t)(warp * 32) * 128;  // rows of this warp: no other warp touches them
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint32_t addr = stg + (uint32_t)lane * 128 + (uint32_t)((c ^ sw) << 4);
+        const uint32_t w0 = pack_bf16x2(o[8 * c + 0] * inv, o[8 * c + 1] * inv);
+        const uint32_t w1 = pack_bf16x2(o[8 * c + 2] * inv, o[8 * c + 3] * inv);
+        const uint32_t w2 = pack_bf16x2(o[8 * c + 4] * inv, o[8 * c + 5] * inv);
+        const uint32_t w3 = pack_bf16x2(o[8 * c + 6] * inv, o[8 * c + 7] * inv);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+      }
+      __syncwarp();
+      const int rsub = lane >> 3, ch = lane & 7;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = rsub + 4 * i;
+        const int rg = pend_row0 + warp * 32 + r;
+        uint32_t w0, w1, w2, w3;
+        const uint32_t addr = stg + (uint32_t)r * 128 + (uint32_t)((ch ^ (r & 7)) << 4);
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(addr) : "memory");
+        if (rg < Lq) {
+          uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)seq * Lq + rg) * (size_t)(H * ATT_D) + head * ATT_D);
+          dst[ch] = make_uint4(w0, w1, w2, w3);
+        }
+      }
+      __syncwarp();  // staging reads done before the next use of the staging rows
+      pend_valid = false;
+    };
+    // Flattened (item, key tile) loop so that the deferred epilogue has a single call site (instruction cache).
+    int kv_end = 0;
+    float m_ref2 = 0.f;  // reference maximum, pre-multiplied by log2(e)
+    float l_run = 0.f;
+    for (;;) {
+      const bool have = cur.item < total_items;
+      if (have) {
+        const int j = cur.j;
         const int g = G + j;
         const int k0 = j * ATT_BN;
-        const int b = g & 1;
+        if (j == 0) {
+          kv_end = kv_end_of(cur.row0 + warp * 32 + lane);
+          l_run = 0.f;
+        }
         const int sb = g % ATT_SST;
         mbar_wait(bar_s(sb), (g / ATT_SST) & 1);
         tc_fence_after();
@@ -257,7 +348,12 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
           for (int i = 0; i < 64; i += 4) {
             float2 a = __ffma2_rn(make_float2(s[i], s[i + 1]), l2e, nm);
             float2 c2 = __ffma2_rn(make_float2(s[i + 2], s[i + 3]), l2e, nm);
-            a.x = fast_exp2(a.x); a.y = fast_exp2(a.y); c2.x = fast_exp2(c2.x); c2.y = fast_exp2(c2.y);
+            a.x = fast_exp2(a.x); a.y = fast_exp2(a.y);
+            if (ATT_POLY_EXP && ((i >> 2) % ATT_POLY_EXP) == 0) {
+              c2 = exp2_poly2(c2);
+            } else {
+              c2.x = fast_exp2(c2.x); c2.y = fast_exp2(c2.y);
+            }
             acc0 = __fadd2_rn(acc0, a);
             acc1 = __fadd2_rn(acc1, c2);
             s[i] = a.x; s[i + 1] = a.y; s[i + 2] = c2.x; s[i + 3] = c2.y;
@@ -317,54 +413,21 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_p(b));
+        if (lane == 0) mbar_arrive(bar_p(sb));
       }
-      // ---- item epilogue: O / l -> bf16, staged through this warp's own rows of P[0] for coalesced 128-byte rows ----
-      const int g_last = G + n_kt - 1;
-      mbar_wait(bar_pv(g_last & 1), (g_last >> 1) & 1);  // all P V of this item (and everything before) complete
-      tc_fence_after();
-      const float inv = 1.f / l_run;
-      float o[64];
-      __syncwarp();
-      tmem_ld_32x32(tmem_o + lane_off, o);
-      tmem_ld_32x32(tmem_o + lane_off + 32, o + 32);
-      tmem_ld_wait_dep(o);
-      tmem_ld_wait_dep(o + 32);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_oread);  // the issuer may overwrite O with the next item's first P V
-      const uint32_t stg = sP + (uint32_t)(warp * 32) * 128;  // rows of this warp inside P[0]: no other warp writes them
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const uint32_t addr = stg + (uint32_t)lane * 128 + (uint32_t)((c ^ sw) << 4);
-        const uint32_t w0 = pack_bf16x2(o[8 * c + 0] * inv, o[8 * c + 1] * inv);
-        const uint32_t w1 = pack_bf16x2(o[8 * c + 2] * inv, o[8 * c + 3] * inv);
-        const uint32_t w2 = pack_bf16x2(o[8 * c + 4] * inv, o[8 * c + 5] * inv);
-        const uint32_t w3 = pack_bf16x2(o[8 * c + 6] * inv, o[8 * c + 7] * inv);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+      if (pend_valid) write_out();  // pend_valid was set after the last tile of the previous item: here cur.j == 0 or no item
+      if (!have) break;
+      // The epilogue of this item is deferred until after the first key tile of the CTA's next item (see write_out)
+      if (cur.j + 1 == cur.n_kt) {
+        pend_valid = true; pend_row0 = cur.row0; pend_bh = cur.bh; pend_inv = 1.f / l_run; pend_g = G + cur.n_kt - 1;
+        G += cur.n_kt;
       }
-      __syncwarp();
-      const int rsub = lane >> 3, ch = lane & 7;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = rsub + 4 * i;
-        const int rg = cur.row0 + warp * 32 + r;
-        uint32_t w0, w1, w2, w3;
-        const uint32_t addr = stg + (uint32_t)r * 128 + (uint32_t)((ch ^ (r & 7)) << 4);
-        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(addr) : "memory");
-        if (rg < Lq) {
-          uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)seq * Lq + rg) * (size_t)(H * ATT_D) + head * ATT_D);
-          dst[ch] = make_uint4(w0, w1, w2, w3);
-        }
-      }
-      __syncwarp();  // staging reads done before this warp's next P writes
-      G += n_kt;
-      next_item(cur);
+      next_tile(cur);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 5) {
     tc_fence_after();
     tmem_dealloc(tmem, 256);
   }
@@ -408,17 +471,19 @@ int attn_launch(const AttnArgs& a, cudaStream_t st) {
   const int n_qt = (a.Lq + ATT_BM - 1) / ATT_BM;
   const long long total = (long long)n_qt * a.H * a.n_seq;
   VB_REQUIRE(total < (1ll << 31), "attn: too many work items");
-  // One work item per CTA by default. Persistent CTAs (2 per SM, stride = 1 mod n_qt so every CTA walks through all
-  // q tiles, next item's Q prefetched into the second buffer) are supported by the kernel and selectable with
-  // VAR_B200_ATTN_GRID=<n>: measured 94 ms vs 78 ms of attention time per d16 scoring step (item costs vary 3..11 key
-  // tiles and the hardware CTA scheduler balances them better than a static stride).
-  int grid = (int)total;
-  if (const char* e = getenv("VAR_B200_ATTN_GRID")) {  // measurement hook
-    int g = atoi(e);
-    if (g > 0 && g < total) {
-      while (g > 1 && g % n_qt != 1 % n_qt) --g;
-      grid = g;
-    }
+  // Persistent CTAs, two per SM, walking items with a stride that is 1 mod n_qt so every CTA visits all q-tile
+  // positions (3..11 key tiles each) in turn; consecutive items of one (sequence, head) run at the same time on
+  // neighbouring CTAs, which keeps their shared K/V tiles in L2 (DRAM traffic == one pass over Q, K, V).
+  // VAR_B200_ATTN_GRID=<n> overrides the grid for measurements (n >= number of items: one item per CTA).
+  int grid = 2 * vb::sm_count();
+  if (const char* e = getenv("VAR_B200_ATTN_GRID")) {
+    const int g = atoi(e);
+    if (g > 0) grid = g;
+  }
+  if (grid >= total) {
+    grid = (int)total;
+  } else {
+    while (grid > 1 && grid % n_qt != 1 % n_qt) --grid;
   }
   vb::ProfScope prof_scope(vb::PK_ATTN, st);
   attn_kernel<<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, reinterpret_cast<__nv_bfloat16*>(a.out), a.Lq, a.H,

@@ -141,6 +141,14 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
 }
 // All previously issued UMMAs of this thread arrive on the mbarrier when complete
 // (implies tcgen05.fence::before_thread_sync).
+// True in exactly one lane of a fully converged warp (elect.sync): lets warp-uniform loops keep descriptors and
+// addresses in uniform registers and predicate only the single-thread tcgen05 / TMA instruction.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred)::"memory");
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
