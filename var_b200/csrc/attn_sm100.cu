@@ -40,7 +40,7 @@ constexpr int ATT_SMEM = 2 * ATT_Q_BYTES + (ATT_KST + ATT_VST) * ATT_KV_BYTES + 
 constexpr float ATT_RESCALE_LOG2 = 80.f;
 constexpr int ATT_NBAR = 3 + ATT_KST + ATT_VST + 2 * ATT_SST + 2 + 2 + ATT_KST + ATT_VST;
 #ifndef ATT_POLY_EXP
-#define ATT_POLY_EXP 0
+#define ATT_POLY_EXP 2
 #endif
 
 struct AttnLevels {
@@ -163,16 +163,20 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     // from the MMA warp (bar_kfree / bar_vfree / bar_qfree), so this warp never looks at the softmax barriers.
     AttnItem c{(int)blockIdx.x, 0, 0, 0, 0};
     decode(c);
+    AttnItem qc = c;  // Q cursor: runs one item ahead of the K/V stream (the Q tile is a cold 16 KB read from DRAM)
     int kst = 0, kph = 0, vst = 0, vph = 0, qit = 0;
-    while (c.item < total_items) {
-      if (c.j == 0) {
-        mbar_wait(bar_qfree(qit & 1), ((qit >> 1) & 1) ^ 1);
-        if (elect_one_sync()) {
-          mbar_expect_tx(bar_q(qit & 1), ATT_Q_BYTES);
-          tma_load_3d(&tmQ, bar_q(qit & 1), sQ + (qit & 1) * ATT_Q_BYTES, 0, c.row0, c.bh);
-        }
-        ++qit;
+    auto load_q = [&]() {
+      mbar_wait(bar_qfree(qit & 1), ((qit >> 1) & 1) ^ 1);
+      if (elect_one_sync()) {
+        mbar_expect_tx(bar_q(qit & 1), ATT_Q_BYTES);
+        tma_load_3d(&tmQ, bar_q(qit & 1), sQ + (qit & 1) * ATT_Q_BYTES, 0, qc.row0, qc.bh);
       }
+      __syncwarp();
+      ++qit;
+      next_item(qc);
+    };
+    if (qc.item < total_items) load_q();
+    while (c.item < total_items) {
       mbar_wait(bar_kfree(kst), kph ^ 1);
       if (elect_one_sync()) {
         mbar_expect_tx(bar_k(kst), ATT_KV_BYTES);
@@ -185,22 +189,31 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         tma_load_3d(&tmV, bar_v(vst), sV + vst * ATT_KV_BYTES, 0, c.j * ATT_BN, c.bh);
       }
       if (++vst == ATT_VST) { vst = 0; vph ^= 1; }
+      if (c.j == 0 && qc.item < total_items) load_q();  // next item's Q, once this item's first K/V tiles are in flight
       next_tile(c);
     }
   } else if (warp == 5) {
     // ------------------------------ UMMA issuer warp (warp-uniform loop, one elected lane issues) -------------------
     constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_BM, ATT_BN);
     constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BM, ATT_D) | (1u << 16);  // B (V) is MN-major
-    AttnItem cur{(int)blockIdx.x, 0, 0, 0, 0};
-    decode(cur);
+    // The tile stream is flat across items: the QK cursor runs two key tiles ahead of the P V cursor also over item
+    // boundaries (next item's Q tile is already resident), so the softmax warps find S ready when they change items.
+    AttnItem qc{(int)blockIdx.x, 0, 0, 0, 0};
+    decode(qc);
+    AttnItem pc = qc;
     int kst = 0, kph = 0;            // K ring cursor of the next QK
-    int qs = 0, qsph = 0;            // S ring cursor of the next QK
+    int qs = 0;                      // S ring slot of the next QK
     int vst = 0, vph = 0;            // V ring cursor of the next P V
     int ps = 0, pph = 0;             // S/P ring cursor of the next P V
     int pvb = 0;                     // bar_pv slot of the next P V (tile parity)
-    int it = 0;
+    int q_it = 0, p_it = 0;          // items started by the QK cursor / finished by the P V cursor
     uint64_t qd = 0;
     auto issue_qk = [&]() {
+      if (qc.j == 0) {
+        mbar_wait(bar_q(q_it & 1), (q_it >> 1) & 1);
+        qd = umma_desc_k_sw128(sQ + (q_it & 1) * ATT_Q_BYTES);
+      }
+      const bool last = qc.j + 1 == qc.n_kt;
       mbar_wait(bar_k(kst), kph);
       tc_fence_after();
       if (elect_one_sync()) {
@@ -208,47 +221,41 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
 #pragma unroll
         for (int k = 0; k < ATT_D / 16; ++k) umma_bf16_ss(tmem + qs * 64, qd + 2 * k, kd + 2 * k, idesc_qk, k != 0);
         umma_commit(bar_s(qs));
-        umma_commit(bar_kfree(kst));  // the K stage returns to the producer when this QK has completed
+        umma_commit(bar_kfree(kst));               // the K stage returns to the producer when this QK has completed
+        if (last) umma_commit(bar_qfree(q_it & 1));  // ... and so does the Q buffer after the item's last QK
       }
       __syncwarp();
       if (++kst == ATT_KST) { kst = 0; kph ^= 1; }
-      if (++qs == ATT_SST) { qs = 0; qsph ^= 1; }
+      if (++qs == ATT_SST) qs = 0;
+      if (last) ++q_it;
+      next_tile(qc);
     };
-    while (cur.item < total_items) {
-      const int n_kt = cur.n_kt;
-      mbar_wait(bar_q(it & 1), (it >> 1) & 1);
-      qd = umma_desc_k_sw128(sQ + (it & 1) * ATT_Q_BYTES);
-      // QK runs two tiles ahead of the softmax. S[(g+2)%3] was last read by the softmax of tile g-1 and by P V_{g-1},
-      // both ordered before this QK (bar_p observed / same in-order tensor pipe).
-      issue_qk();
-      if (n_kt > 1) issue_qk();
-      for (int j = 0; j < n_kt; ++j) {
-        if (j + 2 < n_kt) issue_qk();
-        if (j + 2 == n_kt - 1 || (n_kt <= 2 && j == 0)) {  // last QK of this item issued: Q buffer may be refilled
-          if (elect_one_sync()) umma_commit(bar_qfree(it & 1));
-          __syncwarp();
-        }
-        mbar_wait(bar_p(ps), pph);  // P_g written; QK_g therefore complete
-        mbar_wait(bar_v(vst), vph);
-        if (j == 0 && it > 0) mbar_wait(bar_oread, (it - 1) & 1);  // previous item's output has left TMEM
-        tc_fence_after();
-        if (elect_one_sync()) {
-          const uint32_t p_tmem = tmem + ps * 64;  // P_g sits in the first 32 columns of S_g's buffer
+    // S[(g+2)%3] was last read by the softmax of tile g-1 and by P V_{g-1}, both ordered before QK_{g+2}
+    // (bar_p(g-1) observed by this warp / same in-order tensor pipe).
+    if (qc.item < total_items) issue_qk();
+    if (qc.item < total_items) issue_qk();
+    while (pc.item < total_items) {
+      if (qc.item < total_items) issue_qk();
+      mbar_wait(bar_p(ps), pph);  // P_g written; QK_g therefore complete
+      mbar_wait(bar_v(vst), vph);
+      if (pc.j == 0 && p_it > 0) mbar_wait(bar_oread, (p_it - 1) & 1);  // previous item's output has left TMEM
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint32_t p_tmem = tmem + ps * 64;  // P_g sits in the first 32 columns of S_g's buffer
 #pragma unroll
-          for (int k = 0; k < ATT_BN / 16; ++k) {  // 16 keys = 8 packed columns per K-step
-            const uint64_t vd = umma_desc_mn_sw128_attn(sV + vst * ATT_KV_BYTES + k * 2048);
-            umma_bf16_ts(tmem_o, p_tmem + 8 * k, vd, idesc_pv, (j | k) != 0);
-          }
-          umma_commit(bar_pv(pvb));
-          umma_commit(bar_vfree(vst));
+        for (int k = 0; k < ATT_BN / 16; ++k) {  // 16 keys = 8 packed columns per K-step
+          const uint64_t vd = umma_desc_mn_sw128_attn(sV + vst * ATT_KV_BYTES + k * 2048);
+          umma_bf16_ts(tmem_o, p_tmem + 8 * k, vd, idesc_pv, (pc.j | k) != 0);
         }
-        __syncwarp();
-        if (++vst == ATT_VST) { vst = 0; vph ^= 1; }
-        if (++ps == ATT_SST) { ps = 0; pph ^= 1; }
-        pvb ^= 1;
+        umma_commit(bar_pv(pvb));
+        umma_commit(bar_vfree(vst));
       }
-      ++it;
-      next_item(cur);
+      __syncwarp();
+      if (++vst == ATT_VST) { vst = 0; vph ^= 1; }
+      if (++ps == ATT_SST) { ps = 0; pph ^= 1; }
+      pvb ^= 1;
+      if (pc.j + 1 == pc.n_kt) ++p_it;
+      next_tile(pc);
     }
   } else {
     // ------------------------------ softmax / output warps ------------------------------
