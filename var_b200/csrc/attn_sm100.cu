@@ -37,8 +37,11 @@ constexpr int ATT_Q_BYTES = ATT_BM * ATT_D * 2;   // 16 KB
 constexpr int ATT_KV_BYTES = ATT_BN * ATT_D * 2;  // 8 KB
 constexpr int ATT_P_BYTES = ATT_BM * ATT_BN * 2;  // 16 KB
 constexpr int ATT_SMEM = 2 * ATT_Q_BYTES + (ATT_KST + ATT_VST) * ATT_KV_BYTES + ATT_P_BYTES + 1024;  // 2 Q buffers; sP: output staging
-constexpr float ATT_RESCALE_LOG2 = 80.f;
-constexpr int ATT_NBAR = 3 + ATT_KST + ATT_VST + 2 * ATT_SST + 2 + 2 + ATT_KST + ATT_VST;
+// bar_pv ring depth. When the softmax has finished tile t, P V_{t-3} is known complete (QK_t was queued behind it on
+// the in-order tensor pipe) but P V_{t-2} and P V_{t-1} may still be in flight: with fewer than three slots a wait for
+// tile t's phase would alias the already completed phase of an older tile on the same slot and pass early.
+constexpr int ATT_PVST = 4;
+constexpr int ATT_NBAR = 3 + ATT_KST + ATT_VST + 2 * ATT_SST + ATT_PVST + 2 + ATT_KST + ATT_VST;
 #ifndef ATT_POLY_EXP
 #define ATT_POLY_EXP 2
 #endif
@@ -77,6 +80,62 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
   return r;
 }
 
+// Slow path of the lazy-reference softmax, out of line and rolled (8 columns at a time straight from TMEM) so that
+// it does not sit in the hot instruction stream: the tile's row maximum exceeds the reference by more than the
+// representable range. Rebase the accumulator O and the running sum on the new maximum (exact, like the usual online
+// softmax recurrence), then compute this tile's P against it and write it over S. Warp-collective.
+struct AttnRebase {
+  float m_ref2, l_run, l_tile;
+};
+static __device__ __noinline__ AttnRebase attn_rebase_tile(uint32_t s_addr, uint32_t o_addr, int lim, bool rescale_o,
+                                                           uint32_t bar_pv_prev, uint32_t pv_parity, float m_ref2,
+                                                           float l_run) {
+  constexpr float LOG2E = 1.4426950408889634f;
+  float mx = -INFINITY;
+#pragma unroll 1
+  for (int c = 0; c < 8; ++c) {
+    float v[8];
+    tmem_ld_32x8_sync(s_addr + 8 * c, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mx = fmaxf(mx, (8 * c + i < lim) ? v[i] : -INFINITY);
+  }
+  const float mx2 = mx * LOG2E;
+  const bool need = mx2 > m_ref2;
+  const float f = need ? exp2f(m_ref2 - mx2) : 1.f;
+  if (rescale_o) {
+    mbar_wait(bar_pv_prev, pv_parity);  // every earlier P V of this item has landed in TMEM
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < 8; ++c) {
+      float o[8];
+      tmem_ld_32x8_sync(o_addr + 8 * c, o);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] *= f;
+      tmem_st_32x8(o_addr + 8 * c, o);
+    }
+    tmem_st_wait();
+  }
+  AttnRebase r;
+  r.m_ref2 = need ? mx2 : m_ref2;
+  r.l_run = l_run * f;
+  r.l_tile = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < 8; ++c) {  // P chunk c (4 packed columns) lands on S columns that have already been consumed
+    float v[8];
+    tmem_ld_32x8_sync(s_addr + 8 * c, v);
+    uint32_t pw[4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v[i] = (8 * c + i < lim) ? fast_exp2(fmaf(v[i], LOG2E, -r.m_ref2)) : 0.f;
+      r.l_tile += v[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pw[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+    tmem_st_32x4(s_addr + 4 * c, pw);
+  }
+  return r;
+}
+
 // Work item = (sequence, head, 128-row query tile). A CTA walks items blockIdx.x, blockIdx.x + gridDim.x, ... and
 // prefetches the K/V tile stream and the next Q tile across item boundaries.
 struct AttnItem {
@@ -88,7 +147,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
             const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, int Lq, int H, int q_pos0,
             const __grid_constant__ AttnLevels lv, int n_qt, int total_items) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t bars[ATT_NBAR];  // q[2] | oread | k[] | v[] | s[] | p[] | pv[2] | qfree[2] | kfree[] | vfree[]
+  __shared__ uint64_t bars[ATT_NBAR];  // q[2] | oread | k[] | v[] | s[] | p[] | pv[] | qfree[2] | kfree[] | vfree[]
   __shared__ uint32_t tmem_base_smem;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = base;
@@ -103,9 +162,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   auto bar_s = [&](int s) { return smem_u32(&bars[3 + ATT_KST + ATT_VST + s]); };
   auto bar_p = [&](int s) { return smem_u32(&bars[3 + ATT_KST + ATT_VST + ATT_SST + s]); };
   auto bar_pv = [&](int s) { return smem_u32(&bars[3 + ATT_KST + ATT_VST + 2 * ATT_SST + s]); };
-  auto bar_qfree = [&](int s) { return smem_u32(&bars[5 + ATT_KST + ATT_VST + 2 * ATT_SST + s]); };
-  auto bar_kfree = [&](int s) { return smem_u32(&bars[7 + ATT_KST + ATT_VST + 2 * ATT_SST + s]); };
-  auto bar_vfree = [&](int s) { return smem_u32(&bars[7 + 2 * ATT_KST + ATT_VST + 2 * ATT_SST + s]); };
+  auto bar_qfree = [&](int s) { return smem_u32(&bars[3 + ATT_PVST + ATT_KST + ATT_VST + 2 * ATT_SST + s]); };
+  auto bar_kfree = [&](int s) { return smem_u32(&bars[5 + ATT_PVST + ATT_KST + ATT_VST + 2 * ATT_SST + s]); };
+  auto bar_vfree = [&](int s) { return smem_u32(&bars[5 + ATT_PVST + 2 * ATT_KST + ATT_VST + 2 * ATT_SST + s]); };
 
   auto kv_end_of = [&](int row) {  // visible keys of query row `row` of this call's query block
     // lv.end is padded with the sequence length up to VB_MAX_SCALES: fixed trip count, constant-bank operands
@@ -145,7 +204,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     // bar_p is a ring as deep as the S ring: the softmax may run up to two tiles ahead of the issuer's bar_p wait, and
     // a two-deep ring would let tile g+2 complete a second phase of tile g's barrier before the issuer looked at it
     for (int s = 0; s < ATT_SST; ++s) mbar_init(bar_p(s), 4);
-    for (int s = 0; s < 2; ++s) { mbar_init(bar_pv(s), 1); mbar_init(bar_qfree(s), 1); }
+    for (int s = 0; s < ATT_PVST; ++s) mbar_init(bar_pv(s), 1);
+    for (int s = 0; s < 2; ++s) mbar_init(bar_qfree(s), 1);
     for (int s = 0; s < ATT_KST; ++s) mbar_init(bar_kfree(s), 1);
     for (int s = 0; s < ATT_VST; ++s) mbar_init(bar_vfree(s), 1);
     mbar_fence_init();
@@ -205,7 +265,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     int qs = 0;                      // S ring slot of the next QK
     int vst = 0, vph = 0;            // V ring cursor of the next P V
     int ps = 0, pph = 0;             // S/P ring cursor of the next P V
-    int pvb = 0;                     // bar_pv slot of the next P V (tile parity)
+    int pvb = 0;                     // bar_pv slot of the next P V (tile index mod ATT_PVST)
     int q_it = 0, p_it = 0;          // items started by the QK cursor / finished by the P V cursor
     uint64_t qd = 0;
     auto issue_qk = [&]() {
@@ -253,7 +313,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       __syncwarp();
       if (++vst == ATT_VST) { vst = 0; vph ^= 1; }
       if (++ps == ATT_SST) { ps = 0; pph ^= 1; }
-      pvb ^= 1;
+      pvb = (pvb + 1) & (ATT_PVST - 1);
       if (pc.j + 1 == pc.n_kt) ++p_it;
       next_tile(pc);
     }
@@ -272,7 +332,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     int pend_row0 = 0, pend_bh = 0, pend_g = 0;
     float pend_inv = 0.f;
     auto write_out = [&]() {
-      mbar_wait(bar_pv(pend_g & 1), (pend_g >> 1) & 1);  // all P V of that item (and everything before) complete
+      mbar_wait(bar_pv(pend_g & (ATT_PVST - 1)), (pend_g / ATT_PVST) & 1);  // all P V of that item (and everything before) complete
       tc_fence_after();
       const float inv = pend_inv;
       const int head = pend_bh % H, seq = pend_bh / H;
@@ -366,58 +426,25 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
             s[i] = a.x; s[i + 1] = a.y; s[i + 2] = c2.x; s[i + 3] = c2.y;
           }
         }
-        float l_tile = (acc0.x + acc0.y) + (acc1.x + acc1.y);
+        const float l_tile = (acc0.x + acc0.y) + (acc1.x + acc1.y);
         // Overflow guard: a tile whose scores exceed the reference by more than 2^80 shows up as a huge (or inf) row
         // sum. Rare (needs a per-head scale > 27): rebase the TMEM accumulator on this tile's maximum and redo the tile.
         if (__any_sync(0xffffffffu, !(l_tile < 1.2e24f))) {
           __syncwarp();
-          tmem_ld_32x32(tmem + lane_off + sb * 64, s);
-          tmem_ld_32x32(tmem + lane_off + sb * 64 + 32, s + 32);
-          tmem_ld_wait_dep(s);
-          tmem_ld_wait_dep(s + 32);
-          if (partial) {
-#pragma unroll
-            for (int i = 0; i < 64; ++i) s[i] = (i < lim) ? s[i] : -INFINITY;
-          }
-          float mx = s[0];
-#pragma unroll
-          for (int i = 1; i < 64; ++i) mx = fmaxf(mx, s[i]);
-          const float mx2 = mx * LOG2E;
-          const bool need = mx2 > m_ref2;
-          const float f = need ? exp2f(m_ref2 - mx2) : 1.f;
-          if (j > 0) {
-            mbar_wait(bar_pv((g - 1) & 1), ((g - 1) >> 1) & 1);  // every earlier P V of this item has landed in TMEM
-            tc_fence_after();
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              float o[32];
-              __syncwarp();
-              tmem_ld_32x32(tmem_o + lane_off + c * 32, o);
-              tmem_ld_wait_dep(o);
-#pragma unroll
-              for (int i = 0; i < 32; ++i) o[i] *= f;
-              tmem_st_32x32(tmem_o + lane_off + c * 32, o);
-            }
-            tmem_st_wait();
-          }
-          l_run *= f;
-          if (need) m_ref2 = mx2;
-          l_tile = 0.f;
-#pragma unroll
-          for (int i = 0; i < 64; ++i) {
-            s[i] = fast_exp2(fmaf(s[i], LOG2E, -m_ref2));
-            l_tile += s[i];
-          }
-        }
-        l_run += l_tile;
-        {  // P_g (bf16, two keys per 32-bit column) overwrites this thread's row of S_g: columns [sb*64, sb*64+32)
+          const AttnRebase r = attn_rebase_tile(tmem + lane_off + sb * 64, tmem_o + lane_off, lim, j > 0,
+                                                bar_pv((g - 1) & (ATT_PVST - 1)), ((g - 1) / ATT_PVST) & 1, m_ref2, l_run);
+          m_ref2 = r.m_ref2;
+          l_run = r.l_run + r.l_tile;
+        } else {
+          // P_g (bf16, two keys per 32-bit column) overwrites this thread's row of S_g: columns [sb*64, sb*64+32)
+          l_run += l_tile;
           float pk[32];
           uint32_t* pw = reinterpret_cast<uint32_t*>(pk);
 #pragma unroll
           for (int c = 0; c < 32; ++c) pw[c] = pack_bf16x2(s[2 * c], s[2 * c + 1]);
           tmem_st_32x32(tmem + lane_off + sb * 64, pk);
-          tmem_st_wait();
         }
+        tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_p(sb));
