@@ -1,4 +1,7 @@
-"""Measurement aid: run the fc1 GEMM (GELU epilogue) alone at a given shape (default: d30, B=256, last scale)."""
+"""Measurement aid: run each GEMM flavour of a transformer block alone at the d30 (or a given) shape.
+
+usage: python tools/gemm_one.py [depth=30] [n_seq=512] [l=256]      (last AR scale of a B=256 CFG batch by default)
+"""
 import ctypes as C
 import sys
 from pathlib import Path
@@ -8,23 +11,57 @@ import torch
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from var_b200 import lib as L  # noqa: E402
 
-M, N, K = (int(a) for a in sys.argv[1:4]) if len(sys.argv) > 3 else (131072, 7680, 1920)
+depth, n_seq, l = (int(a) for a in sys.argv[1:4]) if len(sys.argv) > 3 else (30, 512, 256)
+Cd, H, Lmax = 64 * depth, depth, 680
+M = n_seq * l
 lib = L.load()
-A = (torch.randn(M, K, device="cuda") * 0.05).bfloat16()
-W = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
-bias = torch.zeros(N, device="cuda")
-out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-a = L.GemmArgs()
-a.A, a.W, a.M, a.N, a.K, a.epilogue = A.data_ptr(), W.data_ptr(), M, N, K, L.EPI_GELU_BF16
-a.bias, a.out = bias.data_ptr(), out.data_ptr()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-for _ in range(3):
-    L.check(lib.var_b200_gemm_bf16(C.byref(a), L.current_stream()))
-torch.cuda.synchronize()
-e0.record()
-for _ in range(10):
-    L.check(lib.var_b200_gemm_bf16(C.byref(a), L.current_stream()))
-e1.record()
-torch.cuda.synchronize()
-t = e0.elapsed_time(e1) / 10 * 1e-3
-print(f"M={M} N={N} K={K}: {t * 1e6:.1f} us, {2.0 * M * N * K / t / 1e12:.1f} TFLOP/s, algorithmic bytes {(M * K + N * K + M * N) * 2 / 1e9:.3f} GB")
+
+
+def timed(a, flops, label):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        L.check(lib.var_b200_gemm_bf16(C.byref(a), L.current_stream()))
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(10):
+        L.check(lib.var_b200_gemm_bf16(C.byref(a), L.current_stream()))
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) / 10 * 1e-3
+    print(f"{label:28s} M={a.M} N={a.N} K={a.K}: {t * 1e6:8.1f} us  {flops / t / 1e12:7.1f} TFLOP/s")
+
+
+def base(N, K, epi):
+    A = (torch.randn(M, K, device="cuda") * 0.05).bfloat16()
+    W = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+    bias = torch.zeros(N, device="cuda")
+    a = L.GemmArgs()
+    a.A, a.W, a.M, a.N, a.K, a.epilogue = A.data_ptr(), W.data_ptr(), M, N, K, epi
+    a.bias = bias.data_ptr()
+    return a, (A, W, bias)
+
+
+# fc1 (GELU)
+a, keep = base(4 * Cd, Cd, L.EPI_GELU_BF16)
+out = torch.empty(M, 4 * Cd, device="cuda", dtype=torch.bfloat16)
+a.out = out.data_ptr()
+timed(a, 2.0 * M * 4 * Cd * Cd, "fc1  (GELU -> bf16)")
+del out
+# qkv
+a, keep = base(3 * Cd, Cd, L.EPI_QKV)
+q = torch.empty(n_seq, H, l, 64, device="cuda", dtype=torch.bfloat16)
+kc = torch.empty(n_seq, H, Lmax, 64, device="cuda", dtype=torch.bfloat16)
+vc = torch.empty_like(kc)
+scale = torch.full((H,), 4.0, device="cuda")
+a.q_out, a.k_cache, a.v_cache, a.q_scale = q.data_ptr(), kc.data_ptr(), vc.data_ptr(), scale.data_ptr()
+a.C, a.H, a.pos0, a.Lmax, a.rows_per_seq = Cd, H, Lmax - l, Lmax, l
+timed(a, 2.0 * M * 3 * Cd * Cd, "qkv  (norm/scale/scatter)")
+del q, kc, vc
+# proj / fc2 (gate + residual, fp32 in place)
+for K, name in ((Cd, "proj (resid + g*acc, fp32)"), (4 * Cd, "fc2  (resid + g*acc, fp32)")):
+    a, keep = base(Cd, K, L.EPI_GATE_RESID)
+    x = torch.zeros(M, Cd, device="cuda")
+    gate = torch.ones(n_seq, Cd, device="cuda")
+    a.out, a.resid, a.gate, a.gate_ld, a.rows_per_seq = x.data_ptr(), x.data_ptr(), gate.data_ptr(), Cd, l
+    timed(a, 2.0 * M * Cd * K, name)
+    del x

@@ -295,6 +295,16 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   float u = k0 * (x + k1 * x * x * x);
   return 0.5f * x * (1.f + tanh_approx(u));
 }
+// two GELUs at once on the packed f32x2 pipes (5 FMA-pipe instructions + 2 MUFU per pair instead of 7 + 1 each)
+__device__ __forceinline__ float2 gelu_tanh2(float2 x) {
+  const float2 x2 = __fmul2_rn(x, x);
+  float2 u = __ffma2_rn(x2, make_float2(0.7978845608028654f * 0.044715f, 0.7978845608028654f * 0.044715f),
+                        make_float2(0.7978845608028654f, 0.7978845608028654f));
+  u = __fmul2_rn(u, x);
+  const float2 t = make_float2(tanh_approx(u.x), tanh_approx(u.y));
+  const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+  return __ffma2_rn(hx, t, hx);
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -162,6 +162,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int row_w0 = m_blk * TILE_M + rank * GEMM_BM + quarter * 32;  // first row of this warp
 
       if constexpr (EPI == EPI_QKV) {
+        // destination row offsets of the four row groups this lane stores (fixed for the whole tile)
+        size_t q_off[4], kv_off[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int rg = row_w0 + rsub + 8 * i;
+          const int sq = rg / p.rows_per_seq, tt = rg - sq * p.rows_per_seq;
+          q_off[i] = ((size_t)sq * p.H * p.rows_per_seq + tt) * 64;
+          kv_off[i] = ((size_t)sq * p.H * p.Lmax + p.pos0 + tt) * 64;
+        }
 #pragma unroll 1
         for (int c = half; c < BN / 64; c += 2) {
           const int n0 = n_base + c * 64;
@@ -170,48 +179,50 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           __syncwarp();
           tmem_ld_32x32(taddr + c * 64, v);
           tmem_ld_32x32(taddr + c * 64 + 32, v + 32);
-          tmem_ld_wait_dep(v);
-          tmem_ld_wait_dep(v + 32);
           const int which = n0 / p.C;  // 0 q, 1 k, 2 v
           const int head = (n0 - which * p.C) >> 6;
-          float ss = 0.f;
+          const float qs = which == 0 ? __ldg(p.q_scale + head) : 1.f;
+          tmem_ld_wait_dep(v);
+          tmem_ld_wait_dep(v + 32);
+          float2 ss2 = make_float2(0.f, 0.f);
 #pragma unroll
-          for (int j = 0; j < 64; ++j) {
-            v[j] += __ldg(p.bias + n0 + j);
-            ss += v[j] * v[j];
+          for (int j = 0; j < 64; j += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+            const float2 a0 = __fadd2_rn(make_float2(v[j], v[j + 1]), make_float2(b.x, b.y));
+            const float2 a1 = __fadd2_rn(make_float2(v[j + 2], v[j + 3]), make_float2(b.z, b.w));
+            ss2 = __ffma2_rn(a0, a0, ss2);
+            ss2 = __ffma2_rn(a1, a1, ss2);
+            v[j] = a0.x; v[j + 1] = a0.y; v[j + 2] = a1.x; v[j + 3] = a1.y;
           }
           float mul = 1.f;
-          if (which < 2) {
-            mul = 1.f / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize(dim=-1), eps 1e-12
-            if (which == 0) mul *= __ldg(p.q_scale + head);
-          }
+          if (which < 2) mul = qs / fmaxf(sqrtf(ss2.x + ss2.y), 1e-12f);  // F.normalize(dim=-1), eps 1e-12
+          const float2 mul2 = make_float2(mul, mul);
+          const size_t head_off = (size_t)head * (which == 0 ? p.rows_per_seq : p.Lmax) * 64;
+          __nv_bfloat16* const dst_base = (which == 0 ? p.q_out : (which == 1 ? p.k_cache : p.v_cache)) + head_off;
 #pragma unroll
           for (int h2 = 0; h2 < 2; ++h2) {  // 64-byte halves of the 128-byte head row
             uint4* srow = reinterpret_cast<uint4*>(stg + lane * EPI_STG_LD);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int e = 32 * h2 + 8 * j;
+              const float2 p0 = __fmul2_rn(make_float2(v[e + 0], v[e + 1]), mul2);
+              const float2 p1 = __fmul2_rn(make_float2(v[e + 2], v[e + 3]), mul2);
+              const float2 p2 = __fmul2_rn(make_float2(v[e + 4], v[e + 5]), mul2);
+              const float2 p3 = __fmul2_rn(make_float2(v[e + 6], v[e + 7]), mul2);
               uint4 o;
-              o.x = pack_bf16x2(v[e + 0] * mul, v[e + 1] * mul);
-              o.y = pack_bf16x2(v[e + 2] * mul, v[e + 3] * mul);
-              o.z = pack_bf16x2(v[e + 4] * mul, v[e + 5] * mul);
-              o.w = pack_bf16x2(v[e + 6] * mul, v[e + 7] * mul);
+              o.x = pack_bf16x2(p0.x, p0.y);
+              o.y = pack_bf16x2(p1.x, p1.y);
+              o.z = pack_bf16x2(p2.x, p2.y);
+              o.w = pack_bf16x2(p3.x, p3.y);
               srow[j] = o;
             }
             __syncwarp();
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int r = rsub + 8 * i;
-              const int rg = row_w0 + r;
-              if (rg < p.M) {
-                const int sq = rg / p.rows_per_seq, tt = rg - sq * p.rows_per_seq;
-                __nv_bfloat16* dst;
-                if (which == 0)
-                  dst = p.q_out + (((size_t)sq * p.H + head) * p.rows_per_seq + tt) * 64;
-                else
-                  dst = (which == 1 ? p.k_cache : p.v_cache) + (((size_t)sq * p.H + head) * p.Lmax + p.pos0 + tt) * 64;
-                *reinterpret_cast<uint4*>(dst + 32 * h2 + cg * 8) = *reinterpret_cast<const uint4*>(stg + r * EPI_STG_LD + cg * 4);
-              }
+              if (row_w0 + r < p.M)
+                *reinterpret_cast<uint4*>(dst_base + (which == 0 ? q_off[i] : kv_off[i]) + 32 * h2 + cg * 8) =
+                    *reinterpret_cast<const uint4*>(stg + r * EPI_STG_LD + cg * 4);
             }
             __syncwarp();
           }
@@ -250,7 +261,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (row_ok) p.part[((size_t)row * n_tiles + n_blk) * 2 + half] = make_float2(run_max, run_sum);
       } else if constexpr (EPI == EPI_GATE_RESID) {
         // Residual update needs coalesced reads of resid/gate: transpose 32x16 accumulator pieces through a private
-        // smem tile so that each warp instruction touches 8 rows x 64 contiguous bytes.
+        // smem tile so that each warp instruction touches 8 rows x 64 contiguous bytes. (Issuing the residual reads a
+        // chunk ahead / before the accumulator barrier was measured 3-10 % SLOWER in an A/B on one box: the extra
+        // loads in flight compete with the TMA operand stream for the SM's L2 ingress.)
         int seqs[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) seqs[i] = (row_w0 + rsub + 8 * i) / p.rows_per_seq;
@@ -271,13 +284,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             __syncwarp();
             const int col = n0 + 16 * h2 + 4 * cg;
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-            float4 rs[4], g4[4];
+            float4 g4[4], rs4[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {  // all loads first: resid may alias out, so the compiler cannot hoist them
+            for (int i = 0; i < 4; ++i) {  // all loads before the stores: resid may alias out
               const int rg = row_w0 + rsub + 8 * i;
               if (rg < p.M) {
-                rs[i] = *reinterpret_cast<const float4*>(p.resid + (size_t)rg * p.N + col);
                 g4[i] = __ldg(reinterpret_cast<const float4*>(p.gate + (size_t)seqs[i] * p.gate_ld + col));
+                rs4[i] = *reinterpret_cast<const float4*>(p.resid + (size_t)rg * p.N + col);
               }
             }
 #pragma unroll
@@ -286,9 +299,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const int rg = row_w0 + r;
               if (rg < p.M) {
                 const float4 a = *reinterpret_cast<const float4*>(stg + r * EPI_STG_LD + 4 * cg);
+                const float4 rs = rs4[i];
                 *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)rg * p.N + col) =
-                    make_float4(fmaf(a.x + b4.x, g4[i].x, rs[i].x), fmaf(a.y + b4.y, g4[i].y, rs[i].y),
-                                fmaf(a.z + b4.z, g4[i].z, rs[i].z), fmaf(a.w + b4.w, g4[i].w, rs[i].w));
+                    make_float4(fmaf(a.x + b4.x, g4[i].x, rs.x), fmaf(a.y + b4.y, g4[i].y, rs.y),
+                                fmaf(a.z + b4.z, g4[i].z, rs.z), fmaf(a.w + b4.w, g4[i].w, rs.w));
               }
             }
             __syncwarp();
@@ -331,7 +345,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           } else if constexpr (EPI == EPI_GELU_BF16) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
+            for (int j = 0; j < 32; j += 2) {
+              const float2 g = gelu_tanh2(make_float2(v[j], v[j + 1]));
+              v[j] = g.x;
+              v[j + 1] = g.y;
+            }
           }
           if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_GELU_BF16) {
             // transpose the 32 rows x 64 B of this chunk through the warp's staging tile: each store instruction then
