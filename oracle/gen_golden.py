@@ -151,6 +151,46 @@ def main():
                         img_sub=img_ar[:, :, ::8, ::8].numpy(),
                         logit_max=np.stack([lg_.amax(-1).numpy().reshape(-1)[:2] for lg_, _ in rec]),
                         kept=np.array([int(torch.isfinite(lg_).sum()) for lg_, _ in rec]))
+    # ---------------------------------------------------------------- G5: VAR.inpainting (var.py:236-364), depth 2
+    # keep mask: scales 0-2 entirely (exercises the skip branch, which consumes no noise), then the left half of
+    # every later token map. gt tokens = the quantizer's tokens of the random feature map above.
+    gt_tok = torch.cat(idx, dim=1)[:2].clone()
+    keep = torch.zeros_like(gt_tok, dtype=torch.bool)
+    off = 0
+    for si_, pn_ in enumerate(var.patch_nums):
+        m_ = torch.zeros(pn_, pn_, dtype=torch.bool)
+        if si_ <= 2:
+            m_[:] = True
+        else:
+            m_[:, : pn_ // 2] = True
+        keep[:, off:off + pn_ * pn_] = m_.reshape(-1)
+        off += pn_ * pn_
+    rec2 = []
+
+    def spy2(logits_BlV, **kw):
+        r = orig(logits_BlV, **kw)
+        rec2.append((logits_BlV.detach().clone(), r[:, :, 0].clone()))
+        return r
+    ref_var.sample_with_top_k_top_p_ = spy2
+    emb_calls = []
+    emb_orig = q.embedding.forward
+
+    def emb_spy(t):
+        emb_calls.append(t.detach().clone())
+        return emb_orig(t)
+    q.embedding.forward = emb_spy
+    with torch.no_grad():
+        img_inp = var.inpainting(gt_tok, keep, label=labels_ar, g_seed=321, cfg=1.5, top_k=900, top_p=0.0)
+    q.embedding.forward = emb_orig
+    ref_var.sample_with_top_k_top_p_ = orig
+    final_tok = np.concatenate([t.numpy().astype(np.int16) for t in emb_calls], axis=1)
+    with torch.no_grad():
+        f_hat_inp = q.embed_to_fhat([q.embedding(t).transpose(1, 2).reshape(2, 32, pn, pn) for t, pn in zip(emb_calls, var.patch_nums)],
+                                    all_to_max_scale=True, last_one=True)
+    np.savez_compressed(OUT / "inpaint_d2.npz", labels=labels_ar.numpy(), gt_tokens=gt_tok.numpy().astype(np.int16),
+                        keep=keep.numpy(), final_tokens=final_tok, f_hat=f_hat_inp.numpy(),
+                        img_sub=img_inp[:, :, ::8, ::8].numpy(), n_sampled_scales=np.array(len(rec2)),
+                        logit_max=np.stack([lg_.amax(-1).numpy().reshape(-1)[:2] for lg_, _ in rec2]))
     print("golden fixtures written to", OUT)
     for p in sorted(OUT.iterdir()):
         print(f"  {p.name}: {p.stat().st_size / 1024:.0f} KB")

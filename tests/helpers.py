@@ -62,7 +62,9 @@ def sd_cpu(var):
     return {k: v.detach().cpu().float() if v.is_floating_point() else v.detach().cpu() for k, v in var.state_dict().items()}
 
 
-def replay_noise(seed: int, B: int, V: int = 4096, patch_nums=PATCH_NUMS, device="cpu"):
-    """The Exp(1) draws torch.multinomial makes inside sample_with_top_k_top_p_."""
+def replay_noise(seed: int, B: int, V: int = 4096, patch_nums=PATCH_NUMS, device="cpu", skip_scales=()):
+    """The Exp(1) draws torch.multinomial makes inside sample_with_top_k_top_p_. Scales listed in
+    skip_scales draw nothing (VAR.inpainting skips the sampler where every token is kept, var.py:313-314)."""
     g = torch.Generator(device=device).manual_seed(seed)
-    return [torch.empty(B * pn * pn, V, device=device).exponential_(1, generator=g) for pn in patch_nums]
+    return [None if si in skip_scales else torch.empty(B * pn * pn, V, device=device).exponential_(1, generator=g)
+            for si, pn in enumerate(patch_nums)]

@@ -124,3 +124,22 @@ def test_ar_oracle_matches_reference_golden():
     ref = g["idx"].astype(np.int64)
     assert (got != ref).sum() == 0, f"{(got != ref).sum()} sampled tokens differ from the reference"
     assert (out["f_hat"] - torch.from_numpy(g["f_hat"])).abs().max() < 5e-5
+
+
+def test_inpainting_oracle_matches_reference_golden():
+    """VAR.inpainting (var.py:236-364): kept tokens override the samples, fully kept scales skip the sampler."""
+    g = golden("inpaint_d2.npz")
+    vae, var = seeded_models()
+    sd, cfg = sd_cpu(var), var_cfg_of(var)
+    keep = torch.from_numpy(g["keep"])
+    gt = torch.from_numpy(g["gt_tokens"].astype(np.int64))
+    assert int(g["n_sampled_scales"]) == 7
+    noise = replay_noise(321, B=2, skip_scales=(0, 1, 2))
+    out = VO.ar_infer(sd, cfg, quant_oracle_of(vae), torch.from_numpy(g["labels"]), noise, cfg_scale=1.5, top_k=900,
+                      gt_tokens=gt, keep_mask=keep)
+    got = torch.cat(out["idx"], dim=1).numpy()
+    ref = g["final_tokens"].astype(np.int64)
+    assert (got != ref).sum() == 0, f"{(got != ref).sum()} tokens differ from the reference"
+    assert (got[g["keep"]] == g["gt_tokens"].astype(np.int64)[g["keep"]]).all()
+    assert all(l is None for l in out["logits"][:3]) and all(l is not None for l in out["logits"][3:])
+    assert (out["f_hat"] - torch.from_numpy(g["f_hat"])).abs().max() < 5e-5

@@ -384,3 +384,51 @@ def test_nhwc_encoder_matches_pytorch_encoder():
     rel = ((got - ref).abs().max() / ref.abs().max()).item()
     print(f"nhwc encoder rel err {rel:.4f}")
     assert rel < 5e-2 and torch.equal(got, again)
+
+
+def test_inpainting_vs_oracle_and_reference_golden():
+    """VAR.inpainting (var.py:236-364) on the GPU path: with the reference's final tokens forced, the mixed logits of
+    the sampled scales match the oracle and f_hat is bit-exact; unforced, kept positions carry the gt tokens, fully
+    kept scales draw no noise and the image equals the decode of the returned tokens."""
+    g = golden("inpaint_d2.npz")
+    vae, var = seeded_models(device=DEV)
+    sd, cfg = sd_cpu(var), var_cfg_of(var)
+    keep = torch.from_numpy(g["keep"])
+    gt = torch.from_numpy(g["gt_tokens"].astype(np.int64))
+    labels = torch.from_numpy(g["labels"])
+    forced = [torch.from_numpy(i) for i in split_scales(g["final_tokens"])]
+    noise = replay_noise(321, B=2, skip_scales=(0, 1, 2))
+    ref = VO.ar_infer(sd, cfg, quant_oracle_of(vae), labels, noise, cfg_scale=1.5, top_k=900, forced_idx=forced,
+                      gt_tokens=gt, keep_mask=keep)
+    _, tr = var.inpainting(gt.to(DEV), keep.to(DEV), label=labels.to(DEV), g_seed=321, cfg=1.5, top_k=900,
+                           forced_idx=forced, return_trace=True, decode=False)
+    for si in range(10):
+        if si <= 2:
+            assert tr["logits"][si] is None and ref["logits"][si] is None
+            continue
+        err = (tr["logits"][si].cpu() - ref["logits"][si]).abs().max().item()
+        assert err < 2.5 * LOGIT_TOL, f"scale {si}: mixed-logit err {err}"
+    assert torch.equal(tr["f_hat"].cpu(), ref["f_hat"])
+    assert (tr["f_hat"].cpu() - torch.from_numpy(g["f_hat"])).abs().max() < 5e-5
+    # unforced run: merge semantics + determinism + skipped scales consume no noise
+    torch.backends.cudnn.allow_tf32 = False
+    img, tr2 = var.inpainting(gt.to(DEV), keep.to(DEV), label=labels.to(DEV), g_seed=5, cfg=1.5, top_k=900, return_trace=True)
+    tok = torch.cat(tr2["idx"], dim=1).cpu()
+    assert torch.equal(tok[keep], gt[keep])
+    assert img.shape == (2, 3, 256, 256)
+    img_dec = vae.idxBl_to_img(tr2["idx"], same_shape=True, last_one=True).add(1).mul(0.5)
+    assert (img - img_dec).abs().max().item() == 0.0
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    q3 = torch.empty(2 * 16, 4096, device=DEV).exponential_(1.0, generator=gen)  # first draw belongs to scale 3 (4x4)
+    lg3 = tr2["logits"][3].view(-1, 4096)
+    thr = lg3.topk(900, dim=-1)[0][:, -1:]
+    p3 = torch.softmax(lg3.masked_fill(lg3 < thr, float("-inf")), dim=-1)
+    samp3 = (p3 / q3).argmax(-1).view(2, 16).cpu()
+    exp3 = torch.where(keep[:, 14:30], gt[:, 14:30], samp3)
+    assert (exp3 != tr2["idx"][3].cpu()).sum().item() <= 1  # softmax rounding may move one near-tie
+    with pytest.raises(ValueError):
+        var.inpainting(gt.to(DEV), keep[:, :10].to(DEV), label=labels.to(DEV))
+    # all tokens kept -> exact reconstruction of the gt tokens, no sampling at all
+    _, tr3 = var.inpainting(gt.to(DEV), torch.ones_like(keep).to(DEV), label=labels.to(DEV), g_seed=1, return_trace=True,
+                            decode=False)
+    assert torch.equal(torch.cat(tr3["idx"], dim=1).cpu(), gt) and all(l is None for l in tr3["logits"])

@@ -253,8 +253,49 @@ class VAR(nn.Module):
         img = self.vae_proxy[0].fhat_to_img(f_hat).add_(1).mul_(0.5) if decode else f_hat
         return (img, trace) if return_trace else img
 
-    def _ar_loop(self, B, labels, rng, cfg, top_k, top_p, forced_idx=None, trace=None):
-        """The 10 strictly sequential scale steps (var.py:160-187) on labels [2B] int32 (cond rows, then uncond)."""
+    @torch.no_grad()
+    def inpainting(self, gt_tokens: torch.Tensor, mask: torch.Tensor, label: Optional[Union[int, torch.LongTensor]] = None,
+                   g_seed: Optional[int] = None, cfg: float = 1.5, top_k: int = 0, top_p: float = 0.0,
+                   more_smooth: bool = False, *, forced_idx=None, return_trace=False, decode=True):
+        """models/var.py:236-364: KV-cached CFG sampling that keeps the tokens where `mask` [B, L] is True (they are
+        taken from `gt_tokens` [B, L], the output of vae.img_to_idxBl concatenated over scales) and samples the rest;
+        a scale whose tokens are all kept runs the blocks (its K/V must enter the cache) but neither the head nor the
+        sampler, and draws no noise (var.py:313-314). Returns images [B,3,H,W] in [0,1]. Keyword extras as in
+        autoregressive_infer_cfg."""
+        if mask.shape != gt_tokens.shape:
+            raise ValueError("Mask shape must match the latent token shape obtained from vae.img_to_idxBl")
+        if more_smooth:
+            raise NotImplementedError("more_smooth (Gumbel-softmax visualisation path, var.py:333-341) is out of scope")
+        dev = self.lvl_1L.device
+        B = gt_tokens.shape[0]
+        if gt_tokens.shape[1] != self.L:
+            raise ValueError(f"gt_tokens must hold {self.L} tokens per image, got {gt_tokens.shape[1]}")
+        if label is None:  # var.py:274: the reference draws from the global generator here
+            uniform = torch.full((1, self.num_classes), 1.0 / self.num_classes, dtype=torch.float32, device=dev)
+            label = torch.multinomial(uniform, num_samples=B, replacement=True).reshape(B)
+        elif isinstance(label, int):
+            label = torch.full((B,), fill_value=label, device=dev)
+        label = label.to(dev)
+        if g_seed is None:
+            rng = None
+        else:
+            self.rng.manual_seed(g_seed)
+            rng = self.rng
+        labels = self._labels_i32(torch.cat((label, torch.full_like(label, self.num_classes))), 2 * B)
+        gt = gt_tokens.to(dev).to(torch.int64).contiguous()
+        keep = mask.to(dev).bool().contiguous()
+        if int(gt.min()) < 0 or int(gt.max()) >= self.V:
+            raise ValueError(f"gt_tokens out of range [0, {self.V})")
+        trace = dict(idx=[], logits=[]) if return_trace else None
+        f_hat = self._ar_loop(B, labels, rng, cfg, top_k, top_p, forced_idx, trace, gt, keep)
+        if return_trace:
+            trace["f_hat"] = f_hat
+        img = self.vae_proxy[0].fhat_to_img(f_hat).add_(1).mul_(0.5) if decode else f_hat
+        return (img, trace) if return_trace else img
+
+    def _ar_loop(self, B, labels, rng, cfg, top_k, top_p, forced_idx=None, trace=None, gt_tokens=None, keep_mask=None):
+        """The 10 strictly sequential scale steps (var.py:160-187) on labels [2B] int32 (cond rows, then uncond).
+        gt_tokens / keep_mask [B, L]: inpainting (var.py:303-328)."""
         pm = self._model()
         dev = self.lvl_1L.device
         quant = self.vae_quant_proxy[0]
@@ -264,6 +305,12 @@ class VAR(nn.Module):
         H = W = self.patch_nums[-1]
         f_hat = torch.zeros((B, self.Cvae, H, W), dtype=torch.float32, device=dev)
         cur, nxt = 0, None
+        all_kept = None
+        if keep_mask is not None:  # one host read for the whole loop: which scales keep every token
+            offs = [0]
+            for p_ in self.patch_nums:
+                offs.append(offs[-1] + p_ * p_)
+            all_kept = torch.stack([keep_mask[:, a:b].all() for a, b in zip(offs[:-1], offs[1:])]).tolist()
         for si, pn in enumerate(self.patch_nums):
             l = pn * pn
             if si == 0:
@@ -271,11 +318,16 @@ class VAR(nn.Module):
             else:
                 x = pm.embed(nxt, B, labels, 2 * B, l, 0, cur)
             pm.blocks_cached(x, ada, 2 * B, l, cur, kv)
-            logits = pm.head_logits(x, ada, 2 * B, l)
-            q = torch.empty((B * l, self.V), dtype=torch.float32, device=dev).exponential_(1.0, generator=rng)
-            t = cfg * (si / self.num_stages_minus_1) if self.num_stages_minus_1 > 0 else 0.0
-            mixed = torch.empty((B, l, self.V), dtype=torch.float32, device=dev) if trace is not None else None
-            idx = pm.sample(logits, B, l, t, q, top_k, top_p, mixed)
+            if all_kept is not None and all_kept[si]:
+                idx, mixed = gt_tokens[:, cur:cur + l].contiguous(), None
+            else:
+                logits = pm.head_logits(x, ada, 2 * B, l)
+                q = torch.empty((B * l, self.V), dtype=torch.float32, device=dev).exponential_(1.0, generator=rng)
+                t = cfg * (si / self.num_stages_minus_1) if self.num_stages_minus_1 > 0 else 0.0
+                mixed = torch.empty((B, l, self.V), dtype=torch.float32, device=dev) if trace is not None else None
+                idx = pm.sample(logits, B, l, t, q, top_k, top_p, mixed)
+                if keep_mask is not None:
+                    idx = torch.where(keep_mask[:, cur:cur + l], gt_tokens[:, cur:cur + l], idx).contiguous()
             if forced_idx is not None:
                 idx = forced_idx[si].to(dev).to(torch.int64).contiguous()
             if trace is not None:
