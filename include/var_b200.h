@@ -224,6 +224,13 @@ VAR_B200_API int var_b200_head_score(const var_b200_model_t* m, const float* x, 
  * var_b200_scale_sums: per_scale[s,i] = sum of tok_logp over level i (t >= first_pos), total[s] = sum over levels. */
 VAR_B200_API int var_b200_cfg_token_logprob(const float* logits_cond, const float* logits_uncond, const int32_t* gt,
                                             const float* t_row, int n_seq, int L, int V, float* tok_logp, void* stream);
+/* Expected codebook distance score (var_analysis.py:468-490, --mode l2_dist): tok_dist[s,t] =
+ * sum_v p_v * dists[gt[t], v] with p = softmax of the mixed logits (logits_uncond NULL: no mixing), optionally
+ * restricted to the top_k most probable tokens and renormalised (:476-486). dists: device fp32 [V, V] =
+ * torch.cdist(codebook, codebook) (:256). The caller negates and sums per scale (var_b200_scale_sums). */
+VAR_B200_API int var_b200_cfg_token_expected_dist(const float* logits_cond, const float* logits_uncond, const int32_t* gt,
+                                                  const float* t_row, const float* dists, int n_seq, int L, int V,
+                                                  int top_k, float* tok_dist, void* stream);
 VAR_B200_API int var_b200_scale_sums(const float* tok_logp, int n_seq, int L, int n_scales, const int* level_end /* host */,
                                      int first_pos, float* per_scale, float* total, void* stream);
 

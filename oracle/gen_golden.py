@@ -116,6 +116,22 @@ def main():
         img_sub=img[:, :, ::8, ::8].numpy(), f_enc_sub=f_enc[:, :, ::2, ::2].numpy(),
         cfg_scale_sums=cfg_scale_sums.numpy(), cfg_tok_logp=glp.numpy())
 
+    # ---------------------------------------------------------------- G2b: --mode l2_dist scores (var_analysis.py:252-256,468-524)
+    # computed from the reference model's own logits with the script's statements (the script has no importable function)
+    with torch.no_grad():
+        dists_ref = torch.cdist(q.embedding.weight, q.embedding.weight, p=2)
+        probs_ref = torch.nn.functional.softmax(mixed, dim=-1)
+        gt_d_ref = dists_ref[gt[:1].expand(3, -1)]
+        avg_all = (gt_d_ref * probs_ref).sum(dim=-1)
+        tkp, tki = torch.topk(probs_ref, k=50, dim=-1)
+        tkd = torch.gather(gt_d_ref, dim=-1, index=tki)
+        tkp = tkp / tkp.sum(dim=-1, keepdim=True)
+        avg_k50 = (tkd * tkp).sum(dim=-1)
+        probs_nocfg = torch.nn.functional.softmax(lg_c, dim=-1)
+        avg_nocfg = (gt_d_ref * probs_nocfg).sum(dim=-1)
+    np.savez_compressed(OUT / "l2dist_d2.npz", neg_all=(-avg_all).numpy(), neg_k50=(-avg_k50).numpy(),
+                        neg_nocfg=(-avg_nocfg).numpy())
+
     # ---------------------------------------------------------------- G3: sampler op (helpers.py:6-19) with replayed noise
     gs = torch.Generator().manual_seed(5)
     lg = (torch.randn(2, 9, 4096, generator=gs) * 2.0)

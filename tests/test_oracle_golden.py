@@ -143,3 +143,19 @@ def test_inpainting_oracle_matches_reference_golden():
     assert (got[g["keep"]] == g["gt_tokens"].astype(np.int64)[g["keep"]]).all()
     assert all(l is None for l in out["logits"][:3]) and all(l is not None for l in out["logits"][3:])
     assert (out["f_hat"] - torch.from_numpy(g["f_hat"])).abs().max() < 5e-5
+
+
+def test_expected_dist_oracle_matches_reference_golden():
+    """var_analysis.py --mode l2_dist (:252-256,468-524): expected codebook distance scores, full and top-k renormalised."""
+    g, g2 = golden("quant_forward_d2.npz"), golden("l2dist_d2.npz")
+    vae, var = seeded_models()
+    sd, cfg = sd_cpu(var), var_cfg_of(var)
+    vin = torch.from_numpy(g["var_input"][:1])
+    gt = torch.from_numpy(g["idx"][:1].astype(np.int64))
+    E = vae.quantize.embedding.weight.detach()
+    unc = VO.var_forward(sd, cfg, torch.tensor([1000]), vin)
+    lc = VO.var_forward(sd, cfg, torch.tensor([3, 999, 17]), vin.expand(3, -1, -1))
+    for key, kw, c in (("neg_all", {}, 1.5), ("neg_k50", dict(top_k=50), 1.5), ("neg_nocfg", {}, 0.0)):
+        total, per_scale, tok = VO.expected_dist_scores(lc, unc, gt, c, PATCH_NUMS, E, **kw)
+        assert (tok - torch.from_numpy(g2[key])).abs().max() < 2e-3, key
+        assert (total - per_scale.sum(1)).abs().max() < 1e-2

@@ -432,3 +432,26 @@ def test_inpainting_vs_oracle_and_reference_golden():
     _, tr3 = var.inpainting(gt.to(DEV), torch.ones_like(keep).to(DEV), label=labels.to(DEV), g_seed=1, return_trace=True,
                             decode=False)
     assert torch.equal(torch.cat(tr3["idx"], dim=1).cpu(), gt) and all(l is None for l in tr3["logits"])
+
+
+def test_expected_dist_scores_vs_oracle():
+    """--mode l2_dist scores (var_analysis.py:468-524) on the GPU path vs the fp32 oracle and the reference golden."""
+    from var_b200.scoring import class_expected_distances
+    g, g2 = golden("quant_forward_d2.npz"), golden("l2dist_d2.npz")
+    vae, var = seeded_models(device=DEV)
+    sd, cfg = sd_cpu(var), var_cfg_of(var)
+    idx_np = split_scales(g["idx"][:1])
+    labels = torch.tensor([3, 999, 17])
+    vin = torch.from_numpy(g["var_input"][:1])
+    gt = torch.from_numpy(g["idx"][:1].astype(np.int64))
+    E = vae.quantize.embedding.weight.detach().cpu()
+    unc = VO.var_forward(sd, cfg, torch.tensor([1000]), vin)
+    lc = VO.var_forward(sd, cfg, labels, vin.expand(3, -1, -1))
+    for key, kw, c in (("neg_all", {}, 1.5), ("neg_k50", dict(top_k=50), 1.5), ("neg_nocfg", {}, 0.0)):
+        ref_total, ref_ps, ref_tok = VO.expected_dist_scores(lc, unc, gt, c, PATCH_NUMS, E, **kw)
+        total, ps, tok = class_expected_distances(var, [_t(i) for i in idx_np], labels, c, class_batch=2, **kw)
+        scale = ref_tok.abs().max().item()
+        assert (tok.cpu() - ref_tok).abs().max().item() < 0.05 * scale, key   # bf16 logits move the softmax weights
+        assert (tok.cpu() - torch.from_numpy(g2[key])).abs().max().item() < 0.05 * scale, key
+        assert (total.cpu() - ref_total).abs().max().item() < 0.01 * ref_total.abs().max().item(), key
+        assert (total - ps.sum(1)).abs().max().item() < 1e-2 * scale

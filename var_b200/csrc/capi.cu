@@ -368,6 +368,13 @@ extern "C" int var_b200_cfg_token_logprob(const float* logits_cond, const float*
   return cfg_token_logprob(logits_cond, logits_uncond, gt, t_row, n_seq, L, V, tok_logp, (cudaStream_t)stream);
 }
 
+extern "C" int var_b200_cfg_token_expected_dist(const float* logits_cond, const float* logits_uncond, const int32_t* gt,
+                                                const float* t_row, const float* dists, int n_seq, int L, int V, int top_k,
+                                                float* tok_dist, void* stream) {
+  return cfg_token_expected_dist(logits_cond, logits_uncond, gt, t_row, dists, n_seq, L, V, top_k, tok_dist,
+                                 (cudaStream_t)stream);
+}
+
 extern "C" int var_b200_scale_sums(const float* tok_logp, int n_seq, int L, int n_scales, const int* level_end,
                                    int first_pos, float* per_scale, float* total, void* stream) {
   VB_REQUIRE(level_end != nullptr, "scale_sums: null level table");

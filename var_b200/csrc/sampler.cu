@@ -62,6 +62,36 @@ __device__ void bitonic_sort(float* key, int* val, int n) {
   }
 }
 
+// Exact k-th largest of xs[0..V) by a 4-pass radix select on order-preserving keys (whole CTA; hist[256] and the two
+// scalars live in shared memory). Ends with a barrier.
+__device__ float block_kth_largest(const float* xs, int V, int k, int* hist, uint32_t* sel_prefix, int* sel_k) {
+  const int tid = threadIdx.x;
+  if (tid == 0) { *sel_prefix = 0; *sel_k = k; }
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    hist[tid] = 0;
+    __syncthreads();
+    const uint32_t prefix = *sel_prefix;
+    const uint32_t mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+    for (int v = tid; v < V; v += ST) {
+      const uint32_t key = f2key(xs[v]);
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int need = *sel_k, bin = 255;
+      for (; bin > 0; --bin) {
+        if (hist[bin] >= need) break;
+        need -= hist[bin];
+      }
+      *sel_k = need;
+      *sel_prefix = prefix | ((uint32_t)bin << shift);
+    }
+    __syncthreads();
+  }
+  return key2f(*sel_prefix);
+}
+
 __global__ void __launch_bounds__(ST)
 sample_kernel(const float* __restrict__ logits, int B, int l, int V, int use_cfg, float one_plus_t, float t,
               const float* __restrict__ q, int top_k, float top_p, float p_lim, long long* __restrict__ idx_out,
@@ -89,31 +119,7 @@ sample_kernel(const float* __restrict__ logits, int B, int l, int V, int use_cfg
   __syncthreads();
 
   if (top_k > 0 && top_k < V) {
-    // exact k-th largest by 4-pass radix select on order-preserving keys
-    if (tid == 0) { sel_prefix = 0; sel_k = top_k; }
-    for (int pass = 0; pass < 4; ++pass) {
-      const int shift = 24 - 8 * pass;
-      hist[tid] = 0;
-      __syncthreads();
-      const uint32_t prefix = sel_prefix;
-      const uint32_t mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
-      for (int v = tid; v < V; v += ST) {
-        const uint32_t k = f2key(xs[v]);
-        if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 255], 1);
-      }
-      __syncthreads();
-      if (tid == 0) {
-        int need = sel_k, bin = 255;
-        for (; bin > 0; --bin) {
-          if (hist[bin] >= need) break;
-          need -= hist[bin];
-        }
-        sel_k = need;
-        sel_prefix = prefix | ((uint32_t)bin << shift);
-      }
-      __syncthreads();
-    }
-    const float thr = key2f(sel_prefix);
+    const float thr = block_kth_largest(xs, V, top_k, hist, &sel_prefix, &sel_k);
     for (int v = tid; v < V; v += ST)
       if (xs[v] < thr) xs[v] = -INFINITY;
     __syncthreads();
@@ -191,6 +197,65 @@ int sample_launch(const SampleArgs& a, cudaStream_t st) {
   vb::ProfScope prof_scope(vb::PK_SAMPLE, st);
   sample_kernel<<<a.B * a.l, ST, smem, st>>>(a.logits, a.B, a.l, a.V, a.use_cfg, opt, tf, a.q, a.top_k, a.top_p, (float)(1.0 - (double)a.top_p),
                                              reinterpret_cast<long long*>(a.idx_out), a.mixed_out, use_p ? vp2 : 0);
+  VB_CUDA_CHECK(cudaGetLastError());
+  vb::count_launch();
+  return VB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Expected codebook distance of the (optionally CFG-mixed, optionally top-k-renormalised) next-token distribution to
+// the ground-truth token: out[s,t] = sum_v p_v * dists[gt_t, v]   (var_analysis.py:468-490, mode l2_dist; dists =
+// torch.cdist(E, E)). One CTA per (class sequence, position) row. Ties with the k-th probability are all kept.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ST)
+expected_dist_kernel(const float* __restrict__ lc, const float* __restrict__ lu, const int* __restrict__ gt,
+                     const float* __restrict__ t_row, const float* __restrict__ dists, int L, int V, int top_k,
+                     float* __restrict__ out) {
+  extern __shared__ float sm[];
+  float* xs = sm;  // [V]
+  __shared__ float red[ST / 32];
+  __shared__ int hist[256];
+  __shared__ uint32_t sel_prefix;
+  __shared__ int sel_k;
+  const int t = blockIdx.x, s = blockIdx.y, tid = threadIdx.x;
+  const float* c = lc + ((size_t)s * L + t) * V;
+  const float* u = lu ? lu + (size_t)t * V : nullptr;
+  const float tr = u ? __ldg(t_row + t) : 0.f, opt = 1.f + tr;
+  float m = -INFINITY;
+  for (int v = tid; v < V; v += ST) {
+    float x = c[v];
+    if (u) x = __fsub_rn(__fmul_rn(opt, x), __fmul_rn(tr, u[v]));
+    xs[v] = x;
+    m = fmaxf(m, x);
+  }
+  m = block_max(m, red);  // includes the barrier that publishes xs
+  float thr = -INFINITY;
+  if (top_k > 0 && top_k < V) thr = block_kth_largest(xs, V, top_k, hist, &sel_prefix, &sel_k);
+  const float* d = dists + (size_t)__ldg(gt + t) * V;
+  float se = 0.f, sd = 0.f;
+  for (int v = tid; v < V; v += ST) {
+    const float x = xs[v];
+    if (x >= thr) {
+      const float e = expf(x - m);
+      se += e;
+      sd = fmaf(e, __ldg(d + v), sd);
+    }
+  }
+  se = block_sum(se, red);
+  sd = block_sum(sd, red);
+  if (tid == 0) out[(size_t)s * L + t] = sd / se;
+}
+
+int cfg_token_expected_dist(const float* lc, const float* lu, const int* gt, const float* t_row, const float* dists,
+                            int n_seq, int L, int V, int top_k, float* out, cudaStream_t st) {
+  VB_REQUIRE(lc && gt && dists && out && n_seq > 0 && L > 0 && V > 0, "cfg_token_expected_dist: bad arguments");
+  VB_REQUIRE(lu == nullptr || t_row != nullptr, "cfg_token_expected_dist: t_row is required with uncond logits");
+  VB_REQUIRE(n_seq <= 65535 && top_k >= 0 && (size_t)V * 4 <= 200 * 1024, "cfg_token_expected_dist: n_seq/top_k/V out of range");
+  const size_t smem = (size_t)V * sizeof(float);
+  if (smem > 40 * 1024)
+    VB_CUDA_CHECK(cudaFuncSetAttribute(expected_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  vb::ProfScope prof_scope(vb::PK_SCORE_FIN, st);
+  expected_dist_kernel<<<dim3(L, n_seq), ST, smem, st>>>(lc, lu, gt, t_row, dists, L, V, top_k, out);
   VB_CUDA_CHECK(cudaGetLastError());
   vb::count_launch();
   return VB_OK;

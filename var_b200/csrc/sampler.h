@@ -18,4 +18,8 @@ struct SampleArgs {
 
 int sample_launch(const SampleArgs& a, cudaStream_t st);
 
+// out[s,t] = sum_v softmax(mix(lc[s,t,:], lu[t,:]))_v * dists[gt[t], v]; lu may be null (no mixing); top_k 0 = all
+int cfg_token_expected_dist(const float* lc, const float* lu, const int* gt, const float* t_row, const float* dists,
+                            int n_seq, int L, int V, int top_k, float* out, cudaStream_t st);
+
 }  // namespace vb

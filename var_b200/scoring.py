@@ -95,6 +95,54 @@ def class_log_likelihoods_cfg(var: VAR, gt_idx_list: Sequence[torch.Tensor], lab
 
 
 @torch.no_grad()
+def class_expected_distances(var: VAR, gt_idx_list: Sequence[torch.Tensor], labels: torch.Tensor, cfg: float = 0.0, *,
+                             top_k: Optional[int] = None, class_batch: int = 64, first_pos: int = 0):
+    """--mode l2_dist of var_analysis.py (:252-256,468-524): per candidate class the negated expected codebook distance
+    -sum_v p_v * ||E_gt - E_v||_2 of every position, p = softmax of the teacher-forced logits (CFG-mixed with the
+    label-1000 logits when cfg > 0, :336-342; restricted to the top_k most probable tokens and renormalised when top_k
+    is given, :476-486). Returns (total [K], per_scale [K, S], tok [K, L]); larger is better, as in the reference."""
+    import ctypes as C
+    from . import lib as L
+    lib = L.load()
+    assert gt_idx_list[0].shape[0] == 1
+    pm = var._model()
+    dev = pm.dev
+    quant = var.vae_quant_proxy[0]
+    x_in = quant.idxBl_to_var_input(list(gt_idx_list))
+    gt = torch.cat([g.reshape(-1) for g in gt_idx_list]).to(device=dev, dtype=torch.int32).contiguous()
+    S = len(var.patch_nums)
+    E = quant.embedding.weight.detach().float()
+    dists = torch.cdist(E, E, p=2).contiguous()  # var_analysis.py:256, once per call (V x V fp32 = 64 MB, L2 resident)
+    t_row = torch.cat([torch.full((pn * pn,), cfg * (si / (S - 1))) for si, pn in enumerate(var.patch_nums)]).to(dev).float()
+    ends = (C.c_int * S)(*[e for _, e in var.begin_ends])
+
+    def logits_of(lab):
+        n = lab.numel()
+        x = pm.embed(x_in, 1, lab, n, var.L, var.first_l, 0)
+        ada = pm.ada_params(lab)
+        pm.blocks_teacher(x, ada, n)
+        return pm.head_logits(x, ada, n, var.L)
+
+    lu = logits_of(torch.tensor([var.num_classes], device=dev, dtype=torch.int32)) if cfg > 0 else None
+    labels = labels.reshape(-1).to(device=dev, dtype=torch.int32).contiguous()
+    K = labels.numel()
+    tok = torch.empty((K, var.L), dtype=torch.float32, device=dev)
+    for lo in range(0, K, class_batch):
+        lab = labels[lo:lo + class_batch].contiguous()
+        lc = logits_of(lab)
+        L.check(lib.var_b200_cfg_token_expected_dist(lc.data_ptr(), lu.data_ptr() if lu is not None else None, gt.data_ptr(),
+                                                     t_row.data_ptr(), dists.data_ptr(), lab.numel(), var.L, var.V,
+                                                     int(top_k or 0), tok[lo:].data_ptr(), L.current_stream()),
+                "cfg_token_expected_dist")
+    tok.neg_()
+    per_scale = torch.empty((K, S), dtype=torch.float32, device=dev)
+    total = torch.empty(K, dtype=torch.float32, device=dev)
+    L.check(lib.var_b200_scale_sums(tok.data_ptr(), K, var.L, S, ends, first_pos, per_scale.data_ptr(), total.data_ptr(),
+                                    L.current_stream()), "scale_sums")
+    return total, per_scale, tok
+
+
+@torch.no_grad()
 def classify_image(var: VAR, vae: VQVAE, img: torch.Tensor, num_classes: Optional[int] = None, *, class_batch: int = 125,
                    first_pos: int = 0, group: Optional[dist.ProcessGroup] = None):
     """eval_prob.py:417-465,600-601 for one image [1,3,H,W] in [-1,1]: tokenise, score every class, argmax.
