@@ -224,6 +224,17 @@ VAR_B200_API int var_b200_head_score(const var_b200_model_t* m, const float* x, 
  * var_b200_scale_sums: per_scale[s,i] = sum of tok_logp over level i (t >= first_pos), total[s] = sum over levels. */
 VAR_B200_API int var_b200_cfg_token_logprob(const float* logits_cond, const float* logits_uncond, const int32_t* gt,
                                             const float* t_row, int n_seq, int L, int V, float* tok_logp, void* stream);
+/* Token selection of VAR.smooth_sampling (models/var.py:483-536): logits fp32 [2B, l, V] (cond rows, then uncond) are
+ * CFG-mixed with guidance t; per row the token is the arg-max of log_softmax(mixed) among the codebook neighbours of
+ * the ground-truth token gt[B*l] (neighbors: device int32 [V, n_nb] = argsort(dists, 1)[:, :n_nb]; dists: fp32 [V, V]).
+ * Count mode (thr_mode 0): the first cand_count neighbours; threshold mode: those with distance <= d_0 + (thr - d_0) *
+ * ratio. Outputs: idx_out int64 [B*l], logp_out (selected log-probability), dlogp_out (log_softmax(-d) of the selected
+ * candidate over all n_nb candidates). */
+VAR_B200_API int var_b200_neighbor_select(const float* logits, int B, int l, int V, double t, const int32_t* gt,
+                                          const int32_t* neighbors, const float* dists, int n_nb, int cand_count,
+                                          int thr_mode, float thr, float ratio, void* idx_out, float* logp_out,
+                                          float* dlogp_out, void* stream);
+
 /* Expected codebook distance score (var_analysis.py:468-490, --mode l2_dist): tok_dist[s,t] =
  * sum_v p_v * dists[gt[t], v] with p = softmax of the mixed logits (logits_uncond NULL: no mixing), optionally
  * restricted to the top_k most probable tokens and renormalised (:476-486). dists: device fp32 [V, V] =

@@ -207,6 +207,19 @@ def main():
                         keep=keep.numpy(), final_tokens=final_tok, f_hat=f_hat_inp.numpy(),
                         img_sub=img_inp[:, :, ::8, ::8].numpy(), n_sampled_scales=np.array(len(rec2)),
                         logit_max=np.stack([lg_.amax(-1).numpy().reshape(-1)[:2] for lg_, _ in rec2]))
+    # ---------------------------------------------------------------- G6: VAR.smooth_sampling (var.py:366-575), depth 2
+    sm = {}
+    for tag, kw in (("cnt", dict(n=8)), ("thr", dict(n=8, neighbor_threshold=0.9))):
+        emb_calls = []
+        q.embedding.forward = lambda t, _c=emb_calls: (_c.append(t.detach().clone()), emb_orig(t))[1]
+        with torch.no_grad():
+            img_s, sll, sdll = var.smooth_sampling(gt_tok, label=labels_ar, g_seed=1, cfg=1.5, **kw)
+        q.embedding.forward = emb_orig
+        sm[f"tok_{tag}"] = np.concatenate([t.numpy().astype(np.int16) for t in emb_calls], axis=1)
+        sm[f"sum_ll_{tag}"] = np.array(float(sll))
+        sm[f"sum_dll_{tag}"] = np.array(float(sdll))
+        sm[f"img_sub_{tag}"] = img_s[:, :, ::8, ::8].numpy()
+    np.savez_compressed(OUT / "smooth_d2.npz", labels=labels_ar.numpy(), gt_tokens=gt_tok.numpy().astype(np.int16), **sm)
     print("golden fixtures written to", OUT)
     for p in sorted(OUT.iterdir()):
         print(f"  {p.name}: {p.stat().st_size / 1024:.0f} KB")

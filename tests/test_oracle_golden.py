@@ -159,3 +159,19 @@ def test_expected_dist_oracle_matches_reference_golden():
         total, per_scale, tok = VO.expected_dist_scores(lc, unc, gt, c, PATCH_NUMS, E, **kw)
         assert (tok - torch.from_numpy(g2[key])).abs().max() < 2e-3, key
         assert (total - per_scale.sum(1)).abs().max() < 1e-2
+
+
+@pytest.mark.parametrize("tag,kw", [("cnt", {}), ("thr", dict(neighbor_threshold=0.9))])
+def test_smooth_sampling_oracle_matches_reference_golden(tag, kw):
+    """VAR.smooth_sampling (var.py:366-575): neighbour-restricted arg-max tokens and both accumulated likelihoods."""
+    g = golden("smooth_d2.npz")
+    vae, var = seeded_models()
+    sd, cfg = sd_cpu(var), var_cfg_of(var)
+    gt = torch.from_numpy(g["gt_tokens"].astype(np.int64))
+    out = VO.smooth_infer(sd, cfg, quant_oracle_of(vae), torch.from_numpy(g["labels"]), gt, 8,
+                          vae.quantize.embedding.weight.detach(), cfg_scale=1.5, **kw)
+    got = torch.cat(out["idx"], dim=1).numpy()
+    ref = g[f"tok_{tag}"].astype(np.int64)
+    assert (got != ref).sum() == 0, f"{(got != ref).sum()} tokens differ from the reference"
+    assert float(out["sum_ll"]) == float(g[f"sum_ll_{tag}"])          # integer-truncated terms (var.py:536)
+    assert abs(float(out["sum_dll"]) - float(g[f"sum_dll_{tag}"])) < 1e-2 * max(1.0, abs(float(g[f"sum_dll_{tag}"])))

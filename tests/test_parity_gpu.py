@@ -455,3 +455,36 @@ def test_expected_dist_scores_vs_oracle():
         assert (tok.cpu() - torch.from_numpy(g2[key])).abs().max().item() < 0.05 * scale, key
         assert (total.cpu() - ref_total).abs().max().item() < 0.01 * ref_total.abs().max().item(), key
         assert (total - ps.sum(1)).abs().max().item() < 1e-2 * scale
+
+
+@pytest.mark.parametrize("tag,kw", [("cnt", {}), ("thr", dict(neighbor_threshold=0.9))])
+def test_smooth_sampling_vs_oracle_and_reference_golden(tag, kw):
+    """VAR.smooth_sampling (var.py:366-575): with the reference's tokens forced, the per-position selections agree with
+    the oracle wherever the oracle's decision margin exceeds the bf16 logit tolerance, the selected log-probabilities
+    match within tolerance, and f_hat is bit-exact."""
+    g = golden("smooth_d2.npz")
+    vae, var = seeded_models(device=DEV)
+    sd, cfg = sd_cpu(var), var_cfg_of(var)
+    gt = torch.from_numpy(g["gt_tokens"].astype(np.int64))
+    labels = torch.from_numpy(g["labels"])
+    forced = [torch.from_numpy(i) for i in split_scales(g[f"tok_{tag}"])]
+    E = vae.quantize.embedding.weight.detach().cpu()
+    ref = VO.smooth_infer(sd, cfg, quant_oracle_of(vae), labels, gt, 8, E, cfg_scale=1.5, forced_idx=forced, **kw)
+    _, sll, sdll, tr = var.smooth_sampling(gt.to(DEV), 8, label=labels.to(DEV), g_seed=1, cfg=1.5, forced_idx=forced,
+                                           return_trace=True, decode=False, **kw)
+    assert torch.equal(tr["f_hat"].cpu(), ref["f_hat"])
+    n_diff = 0
+    for si in range(10):
+        assert (tr["logp"][si].cpu() - ref["logp"][si]).abs().max().item() < 4 * LOGIT_TOL, f"scale {si}"
+        same = tr["sel"][si].cpu() == ref["sel"][si]   # near-tied decisions may flip under the bf16 logit error
+        n_diff += int((~same).sum())
+        assert ((tr["dlogp"][si].cpu() - ref["dlogp"][si]).abs() * same).max().item() < 1e-2  # cdist: GPU matmul path vs CPU
+    assert n_diff <= 0.02 * gt.numel(), f"{n_diff} selections differ from the oracle"
+    # unforced: our own selections vs the reference's tokens (decisions with sub-tolerance margins may flip)
+    img, sll2, sdll2, tr2 = var.smooth_sampling(gt.to(DEV), 8, label=labels.to(DEV), g_seed=1, cfg=1.5, return_trace=True, **kw)
+    tok = torch.cat(tr2["idx"], dim=1).cpu().numpy()
+    n_diff = int((tok != g[f"tok_{tag}"].astype(np.int64)).sum())
+    assert n_diff <= 0.02 * tok.size, f"{n_diff} of {tok.size} selections differ from the reference"
+    assert img.shape == (2, 3, 256, 256) and sll2.dtype == torch.int64
+    assert torch.equal(tr2["idx"][0].cpu(), gt[:, :1])  # candidate_count = 1 at scale 0: the gt token itself (d = 0)
+    assert abs(float(sdll2) - float(g[f"sum_dll_{tag}"])) < 0.05 * abs(float(g[f"sum_dll_{tag}"])) + 1.0

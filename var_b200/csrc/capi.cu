@@ -368,6 +368,14 @@ extern "C" int var_b200_cfg_token_logprob(const float* logits_cond, const float*
   return cfg_token_logprob(logits_cond, logits_uncond, gt, t_row, n_seq, L, V, tok_logp, (cudaStream_t)stream);
 }
 
+extern "C" int var_b200_neighbor_select(const float* logits, int B, int l, int V, double t, const int32_t* gt,
+                                        const int32_t* neighbors, const float* dists, int n_nb, int cand_count, int thr_mode,
+                                        float thr, float ratio, void* idx_out, float* logp_out, float* dlogp_out,
+                                        void* stream) {
+  return neighbor_select(logits, B, l, V, t, gt, neighbors, dists, n_nb, cand_count, thr_mode, thr, ratio, idx_out, logp_out,
+                         dlogp_out, (cudaStream_t)stream);
+}
+
 extern "C" int var_b200_cfg_token_expected_dist(const float* logits_cond, const float* logits_uncond, const int32_t* gt,
                                                 const float* t_row, const float* dists, int n_seq, int L, int V, int top_k,
                                                 float* tok_dist, void* stream) {

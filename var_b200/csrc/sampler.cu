@@ -261,4 +261,96 @@ int cfg_token_expected_dist(const float* lc, const float* lu, const int* gt, con
   return VB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Neighbour-restricted arg-max token selection of VAR.smooth_sampling (models/var.py:483-536): one CTA per
+// (image, position) row. x = CFG mix of the row's logits, lp = log_softmax(x); candidates are the first n_nb codebook
+// neighbours of the ground-truth token (ascending L2 distance, table `neighbors` [V, n_nb]); a candidate j takes
+// part if j < cand_count (count mode) or dists[gt, cand_j] <= d_0 + (thr - d_0) * ratio (threshold mode, thr_mode=1).
+// Outputs the selected token, its log-probability and log_softmax(-d)[j*] over all n_nb candidates.
+// First maximal candidate wins (torch.max on CPU); no candidate left -> candidate 0 (:521-527).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ST)
+neighbor_select_kernel(const float* __restrict__ logits, int B, int l, int V, float one_plus_t, float t,
+                       const int* __restrict__ gt, const int* __restrict__ neighbors, const float* __restrict__ dists,
+                       int n_nb, int cand_count, int thr_mode, float thr, float ratio, long long* __restrict__ tok_out,
+                       float* __restrict__ lp_out, float* __restrict__ dlp_out) {
+  extern __shared__ float sm[];
+  float* xs = sm;  // [V]
+  __shared__ float red[ST / 32];
+  __shared__ float bval[ST / 32];
+  __shared__ int bidx[ST / 32];
+  const int r = blockIdx.x, tid = threadIdx.x;
+  const float* lc = logits + (size_t)r * V;
+  const float* lu = logits + ((size_t)B * l + r) * V;
+  float m = -INFINITY;
+  for (int v = tid; v < V; v += ST) {
+    const float x = __fsub_rn(__fmul_rn(one_plus_t, lc[v]), __fmul_rn(t, lu[v]));
+    xs[v] = x;
+    m = fmaxf(m, x);
+  }
+  m = block_max(m, red);
+  float se = 0.f;
+  for (int v = tid; v < V; v += ST) se += expf(xs[v] - m);
+  const float lse = m + logf(block_sum(se, red));
+  const int g = __ldg(gt + r);
+  const int* nb = neighbors + (size_t)g * n_nb;
+  const float* dg = dists + (size_t)g * V;
+  const float d0 = __ldg(dg + __ldg(nb));
+  const float eff = d0 + (thr - d0) * ratio;
+  // distance log-softmax over all n_nb candidates + masked arg-max of the token log-probabilities
+  float dm = -INFINITY;
+  for (int j = tid; j < n_nb; j += ST) dm = fmaxf(dm, -__ldg(dg + __ldg(nb + j)));
+  dm = block_max(dm, red);
+  float ds = 0.f, best = -INFINITY;
+  int best_j = 0x7fffffff;
+  for (int j = tid; j < n_nb; j += ST) {
+    const int c = __ldg(nb + j);
+    const float d = __ldg(dg + c);
+    ds += expf(-d - dm);
+    const bool in = thr_mode ? (d <= eff) : (j < cand_count);
+    const float lp = in ? xs[c] - lse : -INFINITY;
+    if (in && (lp > best || best_j == 0x7fffffff)) { best = lp; best_j = j; }  // j ascending per thread: first max kept
+  }
+  const float dlse = dm + logf(block_sum(ds, red));
+  // block arg-max, ties -> smallest j
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oj = __shfl_xor_sync(0xffffffffu, best_j, o);
+    if (oj != 0x7fffffff && (best_j == 0x7fffffff || ov > best || (ov == best && oj < best_j))) { best = ov; best_j = oj; }
+  }
+  if ((tid & 31) == 0) { bval[tid >> 5] = best; bidx[tid >> 5] = best_j; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < ST / 32; ++w) {
+      const float ov = bval[w];
+      const int oj = bidx[w];
+      if (oj != 0x7fffffff && (best_j == 0x7fffffff || ov > best || (ov == best && oj < best_j))) { best = ov; best_j = oj; }
+    }
+    if (best_j == 0x7fffffff) { best_j = 0; best = -INFINITY; }
+    const int c = __ldg(nb + best_j);
+    tok_out[r] = c;
+    lp_out[r] = best;
+    dlp_out[r] = -__ldg(dg + c) - dlse;
+  }
+}
+
+int neighbor_select(const float* logits, int B, int l, int V, double t, const int* gt, const int* neighbors,
+                    const float* dists, int n_nb, int cand_count, int thr_mode, float thr, float ratio, void* tok_out,
+                    float* lp_out, float* dlp_out, cudaStream_t st) {
+  VB_REQUIRE(logits && gt && neighbors && dists && tok_out && lp_out && dlp_out, "neighbor_select: null pointer");
+  VB_REQUIRE(B > 0 && l > 0 && V > 0 && n_nb > 0 && n_nb <= V && (size_t)V * 4 <= 200 * 1024, "neighbor_select: bad shape");
+  VB_REQUIRE(thr_mode || (cand_count >= 1 && cand_count <= n_nb), "neighbor_select: cand_count=%d out of [1,%d]", cand_count, n_nb);
+  const size_t smem = (size_t)V * sizeof(float);
+  if (smem > 40 * 1024)
+    VB_CUDA_CHECK(cudaFuncSetAttribute(neighbor_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  vb::ProfScope prof_scope(vb::PK_SAMPLE, st);
+  neighbor_select_kernel<<<B * l, ST, smem, st>>>(logits, B, l, V, (float)(1.0 + t), (float)t, gt, neighbors, dists, n_nb,
+                                                 cand_count, thr_mode, thr, ratio, reinterpret_cast<long long*>(tok_out),
+                                                 lp_out, dlp_out);
+  VB_CUDA_CHECK(cudaGetLastError());
+  vb::count_launch();
+  return VB_OK;
+}
+
 }  // namespace vb

@@ -22,4 +22,9 @@ int sample_launch(const SampleArgs& a, cudaStream_t st);
 int cfg_token_expected_dist(const float* lc, const float* lu, const int* gt, const float* t_row, const float* dists,
                             int n_seq, int L, int V, int top_k, float* out, cudaStream_t st);
 
+// VAR.smooth_sampling token selection (models/var.py:483-536); see sampler.cu
+int neighbor_select(const float* logits, int B, int l, int V, double t, const int* gt, const int* neighbors,
+                    const float* dists, int n_nb, int cand_count, int thr_mode, float thr, float ratio, void* tok_out,
+                    float* lp_out, float* dlp_out, cudaStream_t st);
+
 }  // namespace vb

@@ -126,6 +126,7 @@ def _EXTRA_SIGS(vp, i32, i64, f32):
         "var_b200_quant_next_input": [C.POINTER(QuantDesc), i32, vp, vp, i32, vp, vp, vp],
         "var_b200_cfg_topk_sample": [vp, i32, i32, i32, i32, dbl, vp, i32, f32, vp, vp, vp],
         "var_b200_cfg_token_logprob": [vp, vp, vp, vp, i32, i32, i32, vp, vp],
+        "var_b200_neighbor_select": [vp, i32, i32, i32, dbl, vp, vp, vp, i32, i32, i32, f32, f32, vp, vp, vp, vp],
         "var_b200_cfg_token_expected_dist": [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp],
         "var_b200_scale_sums": [vp, i32, i32, i32, C.POINTER(C.c_int), i32, vp, vp, vp],
         "var_b200_gn_silu_nhwc": [vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, i32, vp, sz, vp],

@@ -293,6 +293,81 @@ class VAR(nn.Module):
         img = self.vae_proxy[0].fhat_to_img(f_hat).add_(1).mul_(0.5) if decode else f_hat
         return (img, trace) if return_trace else img
 
+    @torch.no_grad()
+    def smooth_sampling(self, gt_tokens: torch.Tensor, n: int, label: Optional[Union[int, torch.LongTensor]] = None,
+                        g_seed: Optional[int] = None, cfg: float = 1.5, more_smooth: bool = False,
+                        neighbor_threshold: Optional[float] = None, *, forced_idx=None, return_trace=False, decode=True):
+        """models/var.py:366-575: KV-cached CFG loop in which every token is the arg-max of the mixed log-probabilities
+        among the codebook neighbours of the ground-truth token (`1 + int((n-1)*ratio)` nearest, or those within
+        d_min + (neighbor_threshold - d_min)*ratio). Returns (images [B,3,H,W] in [0,1], sum_log_likelihood,
+        sum_distance_log_likelihood); as in the reference the first sum adds the log-probabilities truncated to
+        integers (int64 `new_tensor`, var.py:536). No randomness is consumed (g_seed only reseeds self.rng)."""
+        if more_smooth:
+            raise NotImplementedError("more_smooth (Gumbel-softmax visualisation path, var.py:543-551) is out of scope")
+        import ctypes as C
+        from . import lib as L
+        lib = L.load()
+        dev = self.lvl_1L.device
+        B = gt_tokens.shape[0]
+        if gt_tokens.shape[1] != self.L:
+            raise ValueError(f"gt_tokens must hold {self.L} tokens per image, got {gt_tokens.shape[1]}")
+        if not 1 <= int(n) <= self.V:
+            raise ValueError(f"n must be in [1, {self.V}]")
+        if label is None:
+            uniform = torch.full((1, self.num_classes), 1.0 / self.num_classes, dtype=torch.float32, device=dev)
+            label = torch.multinomial(uniform, num_samples=B, replacement=True).reshape(B)
+        elif isinstance(label, int):
+            label = torch.full((B,), fill_value=label, device=dev)
+        label = label.to(dev)
+        if g_seed is not None:
+            self.rng.manual_seed(g_seed)
+        labels = self._labels_i32(torch.cat((label, torch.full_like(label, self.num_classes))), 2 * B)
+        gt = gt_tokens.to(dev).to(torch.int32).contiguous()
+        if int(gt.min()) < 0 or int(gt.max()) >= self.V:
+            raise ValueError(f"gt_tokens out of range [0, {self.V})")
+        quant = self.vae_quant_proxy[0]
+        E = quant.embedding.weight.detach().float()
+        dists = torch.cdist(E, E, p=2).contiguous()                                   # var.py:459-460
+        neighbors = torch.argsort(dists, dim=1)[:, :n].to(torch.int32).contiguous()   # var.py:461-462
+        pm = self._model()
+        S = len(self.patch_nums)
+        ada = pm.ada_params(labels)
+        kv = pm.kv_cache(2 * B)
+        H = W = self.patch_nums[-1]
+        f_hat = torch.zeros((B, self.Cvae, H, W), dtype=torch.float32, device=dev)
+        sum_ll = torch.zeros((), dtype=torch.int64, device=dev)
+        sum_dll = torch.zeros((), dtype=torch.float32, device=dev)
+        trace = dict(idx=[], sel=[], logp=[], dlogp=[]) if return_trace else None
+        cur, nxt = 0, None
+        for si, pn in enumerate(self.patch_nums):
+            l = pn * pn
+            ratio = si / self.num_stages_minus_1 if self.num_stages_minus_1 > 0 else 0.0
+            x = pm.embed(None, 0, labels, 2 * B, l, self.first_l, 0) if si == 0 else pm.embed(nxt, B, labels, 2 * B, l, 0, cur)
+            pm.blocks_cached(x, ada, 2 * B, l, cur, kv)
+            logits = pm.head_logits(x, ada, 2 * B, l)
+            idx = torch.empty((B, l), dtype=torch.int64, device=dev)
+            lp = torch.empty((B, l), dtype=torch.float32, device=dev)
+            dlp = torch.empty((B, l), dtype=torch.float32, device=dev)
+            gt_seg = gt[:, cur:cur + l].contiguous()
+            L.check(lib.var_b200_neighbor_select(
+                logits.data_ptr(), B, l, self.V, float(cfg * ratio), gt_seg.data_ptr(), neighbors.data_ptr(), dists.data_ptr(),
+                int(n), 1 + int((n - 1) * ratio), int(neighbor_threshold is not None),
+                float(neighbor_threshold if neighbor_threshold is not None else 0.0), float(ratio), idx.data_ptr(),
+                lp.data_ptr(), dlp.data_ptr(), L.current_stream()), "neighbor_select")
+            sum_ll = sum_ll + lp.to(torch.int64).sum()
+            sum_dll = sum_dll + dlp.sum()
+            sel = idx
+            if forced_idx is not None:
+                idx = forced_idx[si].to(dev).to(torch.int64).contiguous()
+            if trace is not None:
+                trace["idx"].append(idx); trace["sel"].append(sel); trace["logp"].append(lp); trace["dlogp"].append(dlp)
+            _, nxt = quant.get_next_autoregressive_input(si, S, f_hat, idx_Bl=idx, token_major=True)
+            cur += l
+        if trace is not None:
+            trace["f_hat"] = f_hat
+        img = self.vae_proxy[0].fhat_to_img(f_hat).add_(1).mul_(0.5) if decode else f_hat
+        return (img, sum_ll, sum_dll, trace) if return_trace else (img, sum_ll, sum_dll)
+
     def _ar_loop(self, B, labels, rng, cfg, top_k, top_p, forced_idx=None, trace=None, gt_tokens=None, keep_mask=None):
         """The 10 strictly sequential scale steps (var.py:160-187) on labels [2B] int32 (cond rows, then uncond).
         gt_tokens / keep_mask [B, L]: inpainting (var.py:303-328)."""
