@@ -144,6 +144,13 @@ VAR_B200_API int var_b200_quant_next_input(const var_b200_quant_t* qz, int si, f
  * ---------------------------------------------------------------------------------------------- */
 VAR_B200_API int var_b200_cfg_topk_sample(const float* logits, int B, int l, int V, int use_cfg, double t, const float* q,
                                           int top_k, float top_p, int64_t* idx_out, float* mixed_out, void* stream);
+/* The same sampler plus the more_smooth soft embedding (models/var.py:178-180, helpers.py:22-36):
+ * h_out[B*l, Cvae] = softmax((x * logit_mul - log(q_gumbel)) / tau) @ codebook over the top-k/top-p filtered row x,
+ * q_gumbel [B*l, V] ~ Exp(1) drawn after q (the reference's order of generator use). */
+VAR_B200_API int var_b200_cfg_topk_sample_smooth(const float* logits, int B, int l, int V, int use_cfg, double t,
+                                                 const float* q, int top_k, float top_p, int64_t* idx_out,
+                                                 float* mixed_out, const float* q_gumbel, float tau, float logit_mul,
+                                                 const float* codebook, int Cvae, float* h_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * VAR transformer (models/var.py, models/basic_var.py). Weights are caller-owned device buffers packed once:

@@ -220,6 +220,21 @@ def main():
         sm[f"sum_dll_{tag}"] = np.array(float(sdll))
         sm[f"img_sub_{tag}"] = img_s[:, :, ::8, ::8].numpy()
     np.savez_compressed(OUT / "smooth_d2.npz", labels=labels_ar.numpy(), gt_tokens=gt_tok.numpy().astype(np.int16), **sm)
+    # ---------------------------------------------------------------- G7: more_smooth sampling (var.py:178-180), depth 2
+    with torch.no_grad():
+        f_hats = []
+        gni = q.get_next_autoregressive_input
+
+        def gni_spy(si_, SN_, f_hat_, h_):
+            r = gni(si_, SN_, f_hat_, h_)
+            if si_ == SN_ - 1:
+                f_hats.append(r[0].detach().clone())
+            return r
+        q.get_next_autoregressive_input = gni_spy
+        img_ms = var.autoregressive_infer_cfg(B=2, label_B=labels_ar, g_seed=77, cfg=1.5, top_k=900, top_p=0.0, more_smooth=True)
+        q.get_next_autoregressive_input = gni
+    np.savez_compressed(OUT / "more_smooth_d2.npz", labels=labels_ar.numpy(), f_hat=f_hats[0].numpy(),
+                        img_sub=img_ms[:, :, ::8, ::8].numpy())
     print("golden fixtures written to", OUT)
     for p in sorted(OUT.iterdir()):
         print(f"  {p.name}: {p.stat().st_size / 1024:.0f} KB")

@@ -130,11 +130,19 @@ class QuantOracle:
         assert rc == 0, rc
         return fh[-1] if last_one else [fh[i] for i in range(fh.shape[0])]
 
-    def get_next_autoregressive_input(self, si: int, f_hat: np.ndarray, idx_Bl: np.ndarray) -> Optional[np.ndarray]:
-        """quant.py:187-196 with h_BChw = codebook[idx]; f_hat updated in place; returns area(f_hat) or None."""
+    def get_next_autoregressive_input(self, si: int, f_hat: np.ndarray, idx_Bl: Optional[np.ndarray],
+                                      h: Optional[np.ndarray] = None) -> Optional[np.ndarray]:
+        """quant.py:187-196 with h_BChw = codebook[idx] (or an arbitrary h [B,C,ph,pw], the more_smooth soft embeddings of
+        var.py:178-182, fed through a virtual codebook with an identity index); f_hat updated in place; returns
+        area(f_hat) or None."""
         assert f_hat.dtype == np.float32 and f_hat.flags.c_contiguous
         B = f_hat.shape[0]
         cfg = self._cfg(B)
+        if h is not None:
+            ph, pw = self.patch_hws[si]
+            h_tok = np.ascontiguousarray(h.reshape(B, self.Cv, ph * pw).transpose(0, 2, 1), dtype=np.float32)
+            cfg.codebook, cfg.V = h_tok.ctypes.data, B * ph * pw
+            idx_Bl = np.arange(B * ph * pw, dtype=np.int64).reshape(B, ph * pw)
         idx = np.ascontiguousarray(idx_Bl, dtype=np.int64)
         nxt = None
         if si != len(self.patch_hws) - 1:

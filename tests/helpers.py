@@ -19,6 +19,17 @@ def golden(name: str):
     return np.load(GOLDEN / name)
 
 
+def replay_noise_more_smooth(seed: int, B: int, V: int = 4096, patch_nums=PATCH_NUMS, device="cpu"):
+    """Generator use of autoregressive_infer_cfg(more_smooth=True): per scale the sampler's Exp(1) draw, then the
+    Gumbel draw of gumbel_softmax_with_rng (helpers.py:26). Returns (q list, g list)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    qs, gs = [], []
+    for pn in patch_nums:
+        qs.append(torch.empty(B * pn * pn, V, device=device).exponential_(1, generator=g))
+        gs.append(torch.empty(B * pn * pn, V, device=device).exponential_(1, generator=g))
+    return qs, gs
+
+
 def split_scales(flat_BL: np.ndarray, patch_hws=None):
     hws = patch_hws or [(p, p) for p in PATCH_NUMS]
     out, off = [], 0

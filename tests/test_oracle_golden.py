@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import (GOLDEN, PATCH_NUMS, golden, quant_oracle_of, replay_noise, sd_cpu, seeded_models, split_scales,
+from helpers import (replay_noise_more_smooth, GOLDEN, PATCH_NUMS, golden, quant_oracle_of, replay_noise, sd_cpu, seeded_models, split_scales,
                      var_cfg_of)
 from oracle import var_oracle as VO
 
@@ -175,3 +175,15 @@ def test_smooth_sampling_oracle_matches_reference_golden(tag, kw):
     assert (got != ref).sum() == 0, f"{(got != ref).sum()} tokens differ from the reference"
     assert float(out["sum_ll"]) == float(g[f"sum_ll_{tag}"])          # integer-truncated terms (var.py:536)
     assert abs(float(out["sum_dll"]) - float(g[f"sum_dll_{tag}"])) < 1e-2 * max(1.0, abs(float(g[f"sum_dll_{tag}"])))
+
+
+def test_more_smooth_oracle_matches_reference_golden():
+    """autoregressive_infer_cfg(more_smooth=True) (var.py:178-180): the Gumbel soft embeddings drive f_hat."""
+    g = golden("more_smooth_d2.npz")
+    vae, var = seeded_models()
+    sd, cfg = sd_cpu(var), var_cfg_of(var)
+    qs, gs = replay_noise_more_smooth(77, B=2)
+    out = VO.ar_infer(sd, cfg, quant_oracle_of(vae), torch.from_numpy(g["labels"]), qs, cfg_scale=1.5, top_k=900,
+                      g_noise=gs, codebook=vae.quantize.embedding.weight.detach())
+    err = (out["f_hat"] - torch.from_numpy(g["f_hat"])).abs().max().item()
+    assert err < 2e-3 * float(np.abs(g["f_hat"]).max()), err

@@ -488,3 +488,39 @@ def test_smooth_sampling_vs_oracle_and_reference_golden(tag, kw):
     assert img.shape == (2, 3, 256, 256) and sll2.dtype == torch.int64
     assert torch.equal(tr2["idx"][0].cpu(), gt[:, :1])  # candidate_count = 1 at scale 0: the gt token itself (d = 0)
     assert abs(float(sdll2) - float(g[f"sum_dll_{tag}"])) < 0.05 * abs(float(g[f"sum_dll_{tag}"])) + 1.0
+
+
+def test_more_smooth_soft_embedding_op_and_end_to_end():
+    """more_smooth (var.py:178-180): the Gumbel soft-embedding tail of the sampler kernel vs the oracle on identical fp32
+    logits and noise; then the public call (finite image, f_hat = running sum driven by the soft embeddings, seeded)."""
+    g = golden("sampler.npz")
+    vae, var = seeded_models(device=DEV)
+    E = vae.quantize.embedding.weight.detach().float().contiguous()
+    lg = torch.from_numpy(g["logits"])                      # [2, 9, 4096]; as cond rows, uncond rows = zeros, t = 0
+    B, l, V = lg.shape
+    logits = torch.cat((lg, torch.zeros_like(lg))).to(DEV).contiguous()
+    q = torch.from_numpy(g["q"]).to(DEV).contiguous()
+    gen = torch.Generator().manual_seed(3)
+    q2 = torch.empty(B * l, V).exponential_(1, generator=gen)
+    pm = var._model()
+    for tau, mul, k, p in ((0.27, 1.0, 900, 0.0), (0.05, 1.5, 900, 0.0), (0.0135, 2.0, 0, 0.5), (0.27, 1.3, 0, 0.0)):
+        idx, h = pm.sample_smooth(logits, B, l, 0.0, q, k, p, q2.to(DEV), tau, mul, E)
+        ref_h = VO.gumbel_soft_embed(VO.filter_top_k_top_p(lg, k, p), q2, tau, mul, E.cpu())
+        ref_idx = VO.sample_top_k_top_p(lg, torch.from_numpy(g["q"]), k, p)
+        assert torch.equal(idx.cpu(), ref_idx)
+        assert (h.cpu() - ref_h).abs().max().item() < 2e-4 * max(1.0, ref_h.abs().max().item()), (tau, mul, k, p)
+    torch.backends.cudnn.allow_tf32 = False
+    labels = torch.tensor([5, 6], device=DEV)
+    img, tr = var.autoregressive_infer_cfg(2, labels, g_seed=9, cfg=1.5, top_k=900, more_smooth=True, return_trace=True)
+    img2 = var.autoregressive_infer_cfg(2, labels, g_seed=9, cfg=1.5, top_k=900, more_smooth=True)
+    assert img.shape == (2, 3, 256, 256) and bool(torch.isfinite(img).all()) and torch.equal(img, img2)
+    assert len(tr["h"]) == 10 and tr["h"][3].shape == (2, 16, 32)
+    # f_hat is reproduced by the oracle quantizer from the traced soft embeddings (bit-exact, same op order)
+    qo = quant_oracle_of(vae)
+    f = np.zeros((2, 32, 16, 16), dtype=np.float32)
+    for si, pn in enumerate(PATCH_NUMS):
+        qo.get_next_autoregressive_input(si, f, None, h=tr["h"][si].cpu().transpose(1, 2).reshape(2, 32, pn, pn).contiguous().numpy())
+    assert np.array_equal(f, tr["f_hat"].cpu().numpy())
+    with pytest.raises(NotImplementedError):
+        var.inpainting(torch.zeros(2, 680, dtype=torch.long, device=DEV), torch.ones(2, 680, dtype=torch.bool, device=DEV),
+                       label=labels, more_smooth=True)

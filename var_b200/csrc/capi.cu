@@ -362,6 +362,18 @@ extern "C" int var_b200_quant_next_input(const var_b200_quant_t* qz, int si, flo
   return quant_launch(a, (cudaStream_t)stream);
 }
 
+extern "C" int var_b200_cfg_topk_sample_smooth(const float* logits, int B, int l, int V, int use_cfg, double t,
+                                               const float* q, int top_k, float top_p, int64_t* idx_out, float* mixed_out,
+                                               const float* q_gumbel, float tau, float logit_mul, const float* codebook,
+                                               int Cvae, float* h_out, void* stream) {
+  SampleArgs a{};
+  a.logits = logits; a.B = B; a.l = l; a.V = V; a.use_cfg = use_cfg; a.t = t; a.q = q; a.top_k = top_k; a.top_p = top_p;
+  a.idx_out = idx_out; a.mixed_out = mixed_out;
+  a.q_gumbel = q_gumbel; a.tau = tau; a.logit_mul = logit_mul; a.codebook = codebook; a.Cvae = Cvae; a.h_out = h_out;
+  VB_REQUIRE(q_gumbel != nullptr, "cfg_topk_sample_smooth: q_gumbel is required (use var_b200_cfg_topk_sample otherwise)");
+  return sample_launch(a, (cudaStream_t)stream);
+}
+
 // ------------------------------------------------------------------------------------------------ CFG scoring
 extern "C" int var_b200_cfg_token_logprob(const float* logits_cond, const float* logits_uncond, const int32_t* gt,
                                           const float* t_row, int n_seq, int L, int V, float* tok_logp, void* stream) {

@@ -95,7 +95,8 @@ __device__ float block_kth_largest(const float* xs, int V, int k, int* hist, uin
 __global__ void __launch_bounds__(ST)
 sample_kernel(const float* __restrict__ logits, int B, int l, int V, int use_cfg, float one_plus_t, float t,
               const float* __restrict__ q, int top_k, float top_p, float p_lim, long long* __restrict__ idx_out,
-              float* __restrict__ mixed_out, int Vpow2) {
+              float* __restrict__ mixed_out, int Vpow2, const float* __restrict__ q_gumbel, float tau, float logit_mul,
+              const float* __restrict__ codebook, int Cvae, float* __restrict__ h_out) {
   extern __shared__ float sm[];
   float* xs = sm;                                   // [V]
   float* sk = xs + V;                               // [Vpow2] sort keys (top-p only)
@@ -177,6 +178,42 @@ sample_kernel(const float* __restrict__ logits, int B, int l, int V, int use_cfg
       if (bval[w] > best || (bval[w] == best && bidx[w] < bi)) { best = bval[w]; bi = bidx[w]; }
     idx_out[r] = bi == 0x7fffffff ? 0 : bi;
   }
+  if (q_gumbel == nullptr) return;
+  // ---- more_smooth (models/var.py:178-180, helpers.py:22-36): soft embedding of the filtered row,
+  //      h = softmax((x * (1 + ratio) - log(q_gumbel)) / tau) @ codebook, q_gumbel ~ Exp(1) drawn after the sampler noise
+  __syncthreads();
+  const float* qg = q_gumbel + (size_t)r * V;
+  float zm = -INFINITY;
+  for (int v = tid; v < V; v += ST) zm = fmaxf(zm, (xs[v] * logit_mul - logf(qg[v])) / tau);
+  zm = block_max(zm, red);
+  float acc[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+  float es = 0.f;
+  for (int v = tid; v < V; v += ST) {
+    const float e = expf((xs[v] * logit_mul - logf(qg[v])) / tau - zm);
+    es += e;
+    if (e != 0.f) {
+      const float* er = codebook + (size_t)v * Cvae;
+#pragma unroll
+      for (int c = 0; c < 32; ++c)
+        if (c < Cvae) acc[c] = fmaf(e, __ldg(er + c), acc[c]);
+    }
+  }
+  es = block_sum(es, red);
+  float* hacc = xs;  // the row is no longer needed: reuse its first (ST/32)*32 floats for the cross-warp reduction
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    const float w = warp_sum(acc[c]);
+    if ((tid & 31) == 0) hacc[(tid >> 5) * 32 + c] = w;
+  }
+  __syncthreads();
+  if (tid < Cvae) {
+    float h = 0.f;
+    for (int w = 0; w < ST / 32; ++w) h += hacc[w * 32 + tid];
+    h_out[(size_t)r * Cvae + tid] = h / es;
+  }
 }
 
 int sample_launch(const SampleArgs& a, cudaStream_t st) {
@@ -188,6 +225,10 @@ int sample_launch(const SampleArgs& a, cudaStream_t st) {
   const bool use_p = a.top_p > 0.f;
   const size_t smem = (size_t)a.V * 4 + (use_p ? (size_t)vp2 * 8 : 0);
   VB_REQUIRE(smem <= 200 * 1024, "sample: V=%d too large for the shared-memory sampler", a.V);
+  if (a.q_gumbel != nullptr) {
+    VB_REQUIRE(a.codebook && a.h_out && a.Cvae > 0 && a.Cvae <= 32 && a.tau > 0.f && a.V >= 256,
+               "sample: more_smooth needs codebook, h_out, 0 < Cvae <= 32, tau > 0 (Cvae=%d tau=%f)", a.Cvae, a.tau);
+  }
   static size_t attr = 0;
   if (smem > attr && smem > 40 * 1024) {  // static smem (~1.2 KB) counts against the 48 KB default limit
     VB_CUDA_CHECK(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -196,7 +237,8 @@ int sample_launch(const SampleArgs& a, cudaStream_t st) {
   const float opt = (float)(1.0 + a.t), tf = (float)a.t;
   vb::ProfScope prof_scope(vb::PK_SAMPLE, st);
   sample_kernel<<<a.B * a.l, ST, smem, st>>>(a.logits, a.B, a.l, a.V, a.use_cfg, opt, tf, a.q, a.top_k, a.top_p, (float)(1.0 - (double)a.top_p),
-                                             reinterpret_cast<long long*>(a.idx_out), a.mixed_out, use_p ? vp2 : 0);
+                                             reinterpret_cast<long long*>(a.idx_out), a.mixed_out, use_p ? vp2 : 0, a.q_gumbel, a.tau, a.logit_mul,
+                                             a.codebook, a.Cvae, a.h_out);
   VB_CUDA_CHECK(cudaGetLastError());
   vb::count_launch();
   return VB_OK;

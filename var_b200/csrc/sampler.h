@@ -14,6 +14,12 @@ struct SampleArgs {
   float top_p;     // 0 = off
   void* idx_out;   // int64 [B, l]
   float* mixed_out;  // optional [B, l, V]: the mixed logits (before filtering)
+  // more_smooth (models/var.py:178-180): optional Gumbel soft embedding of the filtered row
+  const float* q_gumbel;  // NULL = off; [B*l, V] Exp(1) noise (gumbel = -log q)
+  float tau, logit_mul;   // softmax((x * logit_mul + gumbel) / tau)
+  const float* codebook;  // [V, Cvae]
+  int Cvae;
+  float* h_out;           // [B*l, Cvae]
 };
 
 int sample_launch(const SampleArgs& a, cudaStream_t st);

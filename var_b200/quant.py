@@ -184,14 +184,21 @@ class VectorQuantizer2(nn.Module):
         """quant.py:187-196. The kernel path takes the sampled indices (h = embedding[idx], models/var.py:177,182);
         f_hat is updated in place. Returns (f_hat, next) with next = area(f_hat) as NCHW (reference layout) or
         [B, l_next, Cvae] when token_major."""
-        if idx_Bl is None:
-            raise NotImplementedError("pass idx_Bl= (sampled token indices); arbitrary h_BChw (the more_smooth Gumbel "
-                                      "path, var.py:178-180) is outside the hot path")
         hws = [_hw(pn) for pn in self.v_patch_nums]
         assert SN == len(hws)
         d = self._desc(hws)
         B = f_hat.shape[0]
         assert f_hat.dtype == torch.float32 and f_hat.is_contiguous()
+        if idx_Bl is None:
+            # arbitrary h map (the more_smooth soft embeddings, var.py:178-182): the same kernel reads h through a
+            # "virtual codebook" whose row b*l + t is h[b, :, t] and an identity index
+            if h_BChw is None:
+                raise ValueError("get_next_autoregressive_input needs h_BChw or idx_Bl")
+            ph, pw = hws[si]
+            h_tok = h_BChw.detach().float().reshape(B, self.Cvae, ph * pw).transpose(1, 2).contiguous()
+            d.codebook, d.V = h_tok.data_ptr(), B * ph * pw
+            d._keep = d._keep + (h_tok,)
+            idx_Bl = torch.arange(B * ph * pw, device=f_hat.device, dtype=torch.int64).view(B, ph * pw)
         idx = idx_Bl.to(torch.int64).contiguous()
         nxt = None
         if si != SN - 1:

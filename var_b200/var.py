@@ -225,9 +225,9 @@ class VAR(nn.Module):
         dict(idx, logits, f_hat) (parity harness); decode=False skips the CNN decoder (returns f_hat);
         cuda_graph=True replays the whole 10-scale loop (~130 launches per scale and block) as one captured CUDA graph
         per (B, cfg, top_k, top_p) — same tokens as the eager path for the same seed."""
-        if more_smooth:
-            raise NotImplementedError("more_smooth (Gumbel-softmax visualisation path, var.py:178-180) is out of scope")
         dev = self.lvl_1L.device
+        if more_smooth and (cuda_graph or forced_idx is not None):
+            raise ValueError("more_smooth does not combine with cuda_graph / forced_idx")
         if g_seed is None:
             rng = None
         else:
@@ -247,7 +247,7 @@ class VAR(nn.Module):
             trace = None
         else:
             trace = dict(idx=[], logits=[]) if return_trace else None
-            f_hat = self._ar_loop(B, labels, rng, cfg, top_k, top_p, forced_idx, trace)
+            f_hat = self._ar_loop(B, labels, rng, cfg, top_k, top_p, forced_idx, trace, more_smooth=more_smooth)
         if return_trace:
             trace["f_hat"] = f_hat
         img = self.vae_proxy[0].fhat_to_img(f_hat).add_(1).mul_(0.5) if decode else f_hat
@@ -265,7 +265,8 @@ class VAR(nn.Module):
         if mask.shape != gt_tokens.shape:
             raise ValueError("Mask shape must match the latent token shape obtained from vae.img_to_idxBl")
         if more_smooth:
-            raise NotImplementedError("more_smooth (Gumbel-softmax visualisation path, var.py:333-341) is out of scope")
+            raise NotImplementedError("more_smooth inside inpainting (var.py:333-341) reads the logits of a possibly skipped "
+                                      "scale in the reference; use autoregressive_infer_cfg(more_smooth=True)")
         dev = self.lvl_1L.device
         B = gt_tokens.shape[0]
         if gt_tokens.shape[1] != self.L:
@@ -368,7 +369,8 @@ class VAR(nn.Module):
         img = self.vae_proxy[0].fhat_to_img(f_hat).add_(1).mul_(0.5) if decode else f_hat
         return (img, sum_ll, sum_dll, trace) if return_trace else (img, sum_ll, sum_dll)
 
-    def _ar_loop(self, B, labels, rng, cfg, top_k, top_p, forced_idx=None, trace=None, gt_tokens=None, keep_mask=None):
+    def _ar_loop(self, B, labels, rng, cfg, top_k, top_p, forced_idx=None, trace=None, gt_tokens=None, keep_mask=None,
+                 more_smooth=False):
         """The 10 strictly sequential scale steps (var.py:160-187) on labels [2B] int32 (cond rows, then uncond).
         gt_tokens / keep_mask [B, L]: inpainting (var.py:303-328)."""
         pm = self._model()
@@ -400,7 +402,16 @@ class VAR(nn.Module):
                 q = torch.empty((B * l, self.V), dtype=torch.float32, device=dev).exponential_(1.0, generator=rng)
                 t = cfg * (si / self.num_stages_minus_1) if self.num_stages_minus_1 > 0 else 0.0
                 mixed = torch.empty((B, l, self.V), dtype=torch.float32, device=dev) if trace is not None else None
-                idx = pm.sample(logits, B, l, t, q, top_k, top_p, mixed)
+                h_soft = None
+                if more_smooth:  # var.py:178-180: soft embedding from Gumbel noise drawn after the sampler's noise
+                    q2 = torch.empty((B * l, self.V), dtype=torch.float32, device=dev).exponential_(1.0, generator=rng)
+                    ratio = si / self.num_stages_minus_1 if self.num_stages_minus_1 > 0 else 0.0
+                    idx, h_soft = pm.sample_smooth(logits, B, l, t, q, top_k, top_p, q2, max(0.27 * (1 - ratio * 0.95), 0.005),
+                                                   1 + ratio, quant.embedding.weight.detach().float().contiguous(), mixed)
+                    if trace is not None:
+                        trace.setdefault("h", []).append(h_soft)
+                else:
+                    idx = pm.sample(logits, B, l, t, q, top_k, top_p, mixed)
                 if keep_mask is not None:
                     idx = torch.where(keep_mask[:, cur:cur + l], gt_tokens[:, cur:cur + l], idx).contiguous()
             if forced_idx is not None:
@@ -408,7 +419,11 @@ class VAR(nn.Module):
             if trace is not None:
                 trace["idx"].append(idx)
                 trace["logits"].append(mixed)
-            _, nxt = quant.get_next_autoregressive_input(si, S, f_hat, idx_Bl=idx, token_major=True)
+            if more_smooth:
+                _, nxt = quant.get_next_autoregressive_input(si, S, f_hat, h_soft.transpose(1, 2).reshape(B, self.Cvae, pn, pn),
+                                                             token_major=True)
+            else:
+                _, nxt = quant.get_next_autoregressive_input(si, S, f_hat, idx_Bl=idx, token_major=True)
             cur += l
         return f_hat
 
@@ -581,3 +596,13 @@ class PackedModel:
                                                   int(top_k), float(top_p), idx.data_ptr(), L.ptr(mixed),
                                                   L.current_stream()), "cfg_topk_sample")
         return idx
+
+    def sample_smooth(self, logits, B, l, t, q, top_k, top_p, q_gumbel, tau, logit_mul, codebook, mixed=None):
+        """Sampler + more_smooth soft embedding (var.py:178-180): returns (idx [B,l], h [B,l,Cvae])."""
+        idx = torch.empty((B, l), dtype=torch.int64, device=self.dev)
+        h = torch.empty((B, l, codebook.shape[1]), dtype=torch.float32, device=self.dev)
+        L.check(self.lib.var_b200_cfg_topk_sample_smooth(
+            logits.data_ptr(), B, l, self.V, 1, float(t), q.data_ptr(), int(top_k), float(top_p), idx.data_ptr(), L.ptr(mixed),
+            q_gumbel.data_ptr(), float(tau), float(logit_mul), codebook.data_ptr(), int(codebook.shape[1]), h.data_ptr(),
+            L.current_stream()), "cfg_topk_sample_smooth")
+        return idx, h
