@@ -253,6 +253,16 @@ VAR_B200_API int var_b200_scale_sums(const float* tok_logp, int n_seq, int L, in
                                      int first_pos, float* per_scale, float* total, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * 3x3 / stride 1 / zero-pad 1 convolution of the VQVAE CNN (models/basic_vae.py:45-46,52-59,130,159,195,225) as an
+ * implicit GEMM on the tcgen05 GEMM kernels: the nine taps are nine shifted TMA boxes of the NHWC bf16 activations
+ * (out-of-image rows/columns are zero-filled by TMA). x: bf16 [B,H,W,Cin]; w_packed: bf16 [Cout, 9, kpt*64] with
+ * kpt = ceil(Cin/64), w_packed[co, ky*3+kx, ci] = weight[co, ci, ky, kx], channels >= Cin zero; bias: fp32 [Cout] or
+ * NULL; resid: NULL or bf16 [B,H,W,Cout] added to the bf16-rounded result (ResnetBlock shortcut, basic_vae.py:60);
+ * out: bf16 [B,H,W,Cout]. Requires Cout % 32 == 0, Cin % 8 == 0, W | 128 or 128 | W, (H*W) % 128 == 0. */
+VAR_B200_API int var_b200_conv3x3_nhwc(const void* x, const void* w_packed, const float* bias, const void* resid,
+                                       void* out, int B, int H, int W, int Cin, int Cout, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * GroupNorm (+SiLU) on NHWC bf16 tensors: glue of the VQVAE CNN decoder/encoder around the cuDNN convolutions
  * (models/basic_vae.py:18-19,57-58,159,225). x, y: bf16 [B, HW, C]; gamma, beta: fp32 [C]. Deterministic. */
 VAR_B200_API size_t var_b200_gn_workspace(int B, int HW, int C, int groups);

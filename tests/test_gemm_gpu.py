@@ -135,3 +135,35 @@ def test_gemm_score_partials():
     ref_gl = logits.gather(1, gt.long()[:, None])[:, 0]
     assert (lse - ref_lse).abs().max().item() < 2e-3
     assert (gl - ref_gl).abs().max().item() < 2e-3
+
+
+def pack_conv3x3(w: torch.Tensor) -> torch.Tensor:
+    """[Cout, Cin, 3, 3] -> bf16 [Cout, 9 * kpt * 64], tap-major, channels zero-padded (include/var_b200.h)."""
+    Cout, Cin = w.shape[:2]
+    kp = (Cin + 63) // 64 * 64
+    out = torch.zeros(Cout, 9, kp, device=w.device, dtype=torch.bfloat16)
+    out[:, :, :Cin] = w.permute(0, 2, 3, 1).reshape(Cout, 9, Cin).to(torch.bfloat16)
+    return out.reshape(Cout, 9 * kp).contiguous()
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,resid", [
+    (2, 16, 16, 32, 640, False), (2, 16, 16, 640, 640, True), (3, 32, 32, 320, 320, True), (1, 64, 64, 320, 160, False),
+    (2, 128, 128, 160, 160, True), (1, 256, 256, 160, 192, False), (1, 8, 16, 64, 64, True), (5, 16, 16, 160, 128, False),
+])
+def test_conv3x3_nhwc_vs_torch(B, H, W, Cin, Cout, resid):
+    """Implicit-GEMM 3x3 convolution (nine shifted TMA boxes, zero-filled borders) vs torch conv2d on the same bf16 data."""
+    torch.manual_seed(B * 1000 + H + Cin)
+    x = torch.randn(B, H, W, Cin, device="cuda").bfloat16()
+    w = (torch.randn(Cout, Cin, 3, 3, device="cuda") / math.sqrt(9 * Cin)).bfloat16()
+    bias = torch.randn(Cout, device="cuda")
+    r = torch.randn(B, H, W, Cout, device="cuda").bfloat16() if resid else None
+    out = torch.full((B, H, W, Cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    L.check(L.load().var_b200_conv3x3_nhwc(x.data_ptr(), pack_conv3x3(w).data_ptr(), bias.data_ptr(),
+                                           r.data_ptr() if resid else None, out.data_ptr(), B, H, W, Cin, Cout,
+                                           L.current_stream()), "conv3x3")
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1).permute(0, 2, 3, 1)
+    if resid:
+        ref = ref.bfloat16().float() + r.float()
+    err = (out.float() - ref).abs().max().item()
+    assert torch.isfinite(out.float()).all() and err <= 2 ** -7 * ref.abs().max().item() + 1e-2, f"max err {err}"  # bf16 ulp

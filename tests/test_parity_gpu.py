@@ -328,15 +328,19 @@ def test_nhwc_decoder_matches_pytorch_decoder():
     ref = vae.decoder(vae.post_quant_conv(f_hat)).clamp(-1, 1)
     vae.decoder_dtype, vae.decoder_nhwc = torch.bfloat16, True
     try:
-        got = vae.fhat_to_img(f_hat)
+        got = vae.fhat_to_img(f_hat)                 # own implicit-GEMM convolutions (default)
+        vae.decoder_own_conv = False
+        got_cudnn = vae.fhat_to_img(f_hat)           # same plan, cuDNN convolutions
         vae.decoder_nhwc = False
         plain16 = vae.fhat_to_img(f_hat)
     finally:
-        vae.decoder_dtype, vae.decoder_nhwc = None, True
+        vae.decoder_dtype, vae.decoder_nhwc, vae.decoder_own_conv = None, True, True
     assert got.shape == ref.shape == (3, 3, 256, 256) and got.dtype == torch.float32
-    e_plan, e_plain = (got - ref).abs(), (plain16 - ref).abs()
-    print(f"nhwc plan: max {e_plan.max():.4f} mean {e_plan.mean():.5f}; plain bf16: max {e_plain.max():.4f} mean {e_plain.mean():.5f}")
+    e_plan, e_plain, e_cudnn = (got - ref).abs(), (plain16 - ref).abs(), (got_cudnn - ref).abs()
+    print(f"nhwc plan: max {e_plan.max():.4f} mean {e_plan.mean():.5f}; cudnn convs: max {e_cudnn.max():.4f} mean "
+          f"{e_cudnn.mean():.5f}; plain bf16: max {e_plain.max():.4f} mean {e_plain.mean():.5f}")
     assert e_plan.mean().item() < 2.0 * e_plain.mean().item() + 1e-3 and e_plan.max().item() < 0.25
+    assert e_cudnn.mean().item() < 2.0 * e_plain.mean().item() + 1e-3 and e_cudnn.max().item() < 0.25
     # deterministic (no atomics): two runs are bit-identical
     vae.decoder_dtype = torch.bfloat16
     try:

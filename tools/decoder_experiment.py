@@ -28,9 +28,9 @@ def timeit(fn, n=3):
 
 
 vae.decoder_dtype = torch.bfloat16
-for nhwc in (False, True):
-    vae.decoder_nhwc = nhwc
-    print(f"bf16 decoder nhwc_plan={nhwc}: {1e3 * timeit(lambda: vae.fhat_to_img(f)) / B:.3f} ms/img")
+for nhwc, own in ((False, False), (True, False), (True, True)):
+    vae.decoder_nhwc, vae.decoder_own_conv = nhwc, own
+    print(f"bf16 decoder nhwc_plan={nhwc} own_conv={own}: {1e3 * timeit(lambda: vae.fhat_to_img(f)) / B:.3f} ms/img")
 from torch.profiler import ProfilerActivity, profile  # noqa: E402
 
 with profile(activities=[ProfilerActivity.CUDA]) as prof:

@@ -7,6 +7,8 @@ loads with strict=True.
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -142,10 +144,12 @@ class Decoder(nn.Module):
 
 
 class NHWCDecoder:
-    """16-bit channels-last execution plan of a `Decoder` (+ post_quant_conv). The convolutions run bias-free on
-    cuDNN's NHWC tensor-core kernels (no layout conversions); everything between them is var_b200's NHWC glue
-    (csrc/groupnorm.cu): GroupNorm+SiLU in two passes with the producing convolution's bias folded in, the residual add
-    with both convolution biases folded in, nearest-2x up-sampling. Same function as
+    """16-bit channels-last execution plan of a `Decoder` (+ post_quant_conv). The 3x3 convolutions run on var_b200's own
+    implicit-GEMM tcgen05 kernel (`var_b200_conv3x3_nhwc`: nine shifted TMA boxes per K sweep, bias and the ResnetBlock
+    shortcut fused into the epilogue) and the 1x1 shortcuts on the plain GEMM; shapes the kernel cannot tile
+    (`own_conv=False`, odd widths, 3 output channels) fall back to bias-free cuDNN NHWC convolutions. Everything between
+    the convolutions is var_b200's NHWC glue (csrc/groupnorm.cu): GroupNorm+SiLU in two passes, residual adds with the
+    convolution biases folded in, nearest-2x up-sampling. Same function as
     Decoder.forward(post_quant_conv(f_hat)) up to 16-bit rounding
     (tests/test_parity_gpu.py::test_nhwc_decoder_matches_pytorch_decoder)."""
 
@@ -156,6 +160,7 @@ class NHWCDecoder:
         self.dec = decoder
         self.post = post_quant_conv
         self._w = {}
+        self.own_conv = True   # False: every convolution through cuDNN (A/B measurements)
         from . import lib as L
         self.L, self.lib = L, L.load()
 
@@ -174,6 +179,47 @@ class NHWCDecoder:
 
     def _bias(self, m):
         return self._cw(m)[1]
+
+    # ---- own tcgen05 convolutions
+    def _own_ok(self, x, m: nn.Conv2d) -> bool:
+        B, Cin, H, W = x.shape if isinstance(x, torch.Tensor) else x
+        if not self.own_conv or m.stride != (1, 1) or m.out_channels % 32 or Cin % 8:
+            return False
+        if m.kernel_size == (1, 1):
+            return m.padding == (0, 0) and Cin % 64 == 0
+        return (m.kernel_size == (3, 3) and m.padding == (1, 1) and (H * W) % 128 == 0
+                and (128 % W == 0 if W <= 128 else W % 128 == 0))
+
+    def _packed(self, m: nn.Conv2d):
+        key = ("own", id(m))
+        w = self._w.get(key)
+        if w is None or w[2] != (m.weight._version, m.bias._version):
+            Cout, Cin, kh, kw = m.weight.shape
+            kp = (Cin + 63) // 64 * 64
+            wp = torch.zeros((Cout, kh * kw, kp), dtype=torch.bfloat16, device=m.weight.device)
+            wp[:, :, :Cin] = m.weight.detach().permute(0, 2, 3, 1).reshape(Cout, kh * kw, Cin).to(torch.bfloat16)
+            w = (wp.reshape(Cout, kh * kw * kp).contiguous(), m.bias.detach().float().contiguous(),
+                 (m.weight._version, m.bias._version))
+            self._w[key] = w
+        return w
+
+    def _own_conv(self, x, m: nn.Conv2d, resid=None):
+        """conv + bias (+ resid) on the tcgen05 kernels; x / resid / result: bf16 channels_last"""
+        B, Cin, H, W = x.shape
+        Cout = m.out_channels
+        assert x.is_contiguous(memory_format=torch.channels_last) and x.dtype == torch.bfloat16
+        wp, bias, _ = self._packed(m)
+        y = torch.empty((B, Cout, H, W), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+        if m.kernel_size == (3, 3):
+            self.L.check(self.lib.var_b200_conv3x3_nhwc(x.data_ptr(), wp.data_ptr(), bias.data_ptr(), self.L.ptr(resid),
+                                                        y.data_ptr(), B, H, W, Cin, Cout, self.L.current_stream()), "conv3x3_nhwc")
+        else:  # 1x1: a plain GEMM over the pixels
+            assert resid is None
+            a = self.L.GemmArgs()
+            a.A, a.W, a.M, a.N, a.K, a.epilogue = x.data_ptr(), wp.data_ptr(), B * H * W, Cout, Cin, self.L.EPI_BIAS_BF16
+            a.bias, a.out = bias.data_ptr(), y.data_ptr()
+            self.L.check(self.lib.var_b200_gemm_bf16(C.byref(a), self.L.current_stream()), "gemm_bf16 (1x1 conv)")
+        return y
 
     def _gn(self, x, m: nn.GroupNorm, silu: bool, pre_bias=None):
         B, Cc, H, W = x.shape
@@ -198,7 +244,20 @@ class NHWCDecoder:
         return out
 
     def _res(self, x, blk: ResnetBlock):
-        h = self._conv(self._gn(x, blk.norm1, True), blk.conv1)
+        g1 = self._gn(x, blk.norm1, True)
+        B_, _, H_, W_ = g1.shape
+        if self._own_ok(g1, blk.conv1) and self._own_ok((B_, blk.conv1.out_channels, H_, W_), blk.conv2):
+            h = self._own_conv(g1, blk.conv1)
+            g2 = self._gn(h, blk.norm2, True)
+            if isinstance(blk.nin_shortcut, nn.Identity):
+                sc = x
+            elif self._own_ok(x, blk.nin_shortcut):
+                sc = self._own_conv(x, blk.nin_shortcut)
+            else:
+                sc = self._conv(x, blk.nin_shortcut)
+                sc = self._add(sc, self._bias(blk.nin_shortcut), None, None, out=sc)
+            return self._own_conv(g2, blk.conv2, resid=sc)
+        h = self._conv(g1, blk.conv1)
         h = self._conv(self._gn(h, blk.norm2, True, pre_bias=self._bias(blk.conv1)), blk.conv2)
         if isinstance(blk.nin_shortcut, nn.Identity):
             return self._add(h, self._bias(blk.conv2), x, None, out=h)
@@ -227,6 +286,8 @@ class NHWCDecoder:
         up = torch.empty((B, Cc, 2 * H, 2 * W), dtype=h.dtype, device=h.device, memory_format=torch.channels_last)
         self.L.check(self.lib.var_b200_upsample2x_nhwc(h.data_ptr(), None, up.data_ptr(), B, H, W, Cc,
                                                        self.L.current_stream()), "upsample2x_nhwc")
+        if self._own_ok(up, conv):
+            return self._own_conv(up, conv)
         y = self._conv(up, conv)
         return self._add(y, self._bias(conv), None, None, out=y)
 
@@ -235,8 +296,12 @@ class NHWCDecoder:
         d = self.dec
         x = f_hat.to(self.dtype).contiguous(memory_format=torch.channels_last)
         h = self._conv(x, self.post)
-        h = self._conv(self._add(h, self._bias(self.post), None, None, out=h), d.conv_in)
-        h = self._add(h, self._bias(d.conv_in), None, None, out=h)
+        h = self._add(h, self._bias(self.post), None, None, out=h)
+        if self._own_ok(h, d.conv_in):
+            h = self._own_conv(h, d.conv_in)
+        else:
+            h = self._conv(h, d.conv_in)
+            h = self._add(h, self._bias(d.conv_in), None, None, out=h)
         h = self._res(h, d.mid.block_1)
         h = self._attn(h, d.mid.attn_1)
         h = self._res(h, d.mid.block_2)

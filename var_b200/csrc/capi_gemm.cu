@@ -28,3 +28,8 @@ extern "C" int var_b200_gemm_bf16(const var_b200_gemm_args_t* a, void* stream) {
 }
 
 extern "C" int var_b200_gemm_tile_n(int N) { return vb::gemm_pick_bn(N); }
+
+extern "C" int var_b200_conv3x3_nhwc(const void* x, const void* w_packed, const float* bias, const void* resid, void* out,
+                                     int B, int H, int W, int Cin, int Cout, void* stream) {
+  return vb::conv3x3_launch(x, w_packed, bias, resid, out, B, H, W, Cin, Cout, (cudaStream_t)stream);
+}

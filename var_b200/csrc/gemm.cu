@@ -6,11 +6,22 @@
 
 namespace vb {
 
+static thread_local int g_conv_cin = 0;  // true channel count of the activation tensor of a conv3x3_launch call
+
 template <int BN, int EPI, int CTAS>
 static int launch_one(const void* A, const void* W, const GemmParams& p, cudaStream_t st) {
   using Cfg = GemmCfg<BN, CTAS>;
   CUtensorMap tmA, tmB;
-  {
+  if (p.conv_kpt > 0) {
+    // activations [B, H, W, Cin] as a 4-D map (C, W, H, B); a box = bw x bh pixels x 64 channels = one 128-row A tile
+    const int Cin = g_conv_cin, nB = p.M / (p.conv_H * p.conv_W);
+    const uint32_t bw = p.conv_W < GEMM_BM ? p.conv_W : GEMM_BM, bh = GEMM_BM / bw;
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)p.conv_W, (uint64_t)p.conv_H, (uint64_t)nB};
+    uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)p.conv_W * Cin * 2, (uint64_t)p.conv_H * p.conv_W * Cin * 2};
+    uint32_t box[4] = {GEMM_BK, bw, bh, 1};
+    int r = make_tmap_bf16_sw128(&tmA, A, 4, dims, str, box);
+    if (r) return r;
+  } else {
     uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.M};
     uint64_t str[1] = {(uint64_t)p.K * 2};
     uint32_t box[2] = {GEMM_BK, GEMM_BM};
@@ -83,7 +94,7 @@ int gemm_launch(const void* A, const void* W, const GemmParams& p, int epi, cuda
   VB_REQUIRE(A && W, "gemm: null operand");
   VB_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
   VB_REQUIRE(p.K % GEMM_BK == 0, "gemm: K=%d must be a multiple of %d", p.K, GEMM_BK);
-  VB_REQUIRE(p.N % 64 == 0, "gemm: N=%d must be a multiple of 64", p.N);
+  VB_REQUIRE(p.N % (epi == EPI_QKV ? 64 : 32) == 0, "gemm: N=%d must be a multiple of %d", p.N, epi == EPI_QKV ? 64 : 32);
   VB_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0, "gemm: operands must be 16-byte aligned");
   if (epi == EPI_QKV) {
     VB_REQUIRE(p.N == 3 * p.C && p.C % 64 == 0 && p.H * 64 == p.C, "gemm/qkv: N=%d C=%d H=%d inconsistent", p.N, p.C, p.H);
@@ -102,6 +113,10 @@ int gemm_launch(const void* A, const void* W, const GemmParams& p, int epi, cuda
   const int bn = force_bn ? (force_bn & 0xffff) : gemm_pick_bn(p.N);
   // CTA-pair tiles (256 x BN) unless the problem is a single 128-row tile or the caller forces 1-CTA (bit 16)
   const bool pair = !(force_bn & 0x10000) && p.M > GEMM_BM;
+  if (bn == 160) {  // 160-wide tiles exist for the convolution epilogue only (channel counts 160 / 320 / 640 of the VQVAE)
+    VB_REQUIRE(epi == EPI_BIAS_BF16, "gemm: tile width 160 is only built for EPI_BIAS_BF16");
+    return pair ? launch_one<160, EPI_BIAS_BF16, 2>(A, W, p, st) : launch_one<160, EPI_BIAS_BF16, 1>(A, W, p, st);
+  }
   if (pair) {
     switch (bn) {
       case 256: return launch_bn<256, 2>(A, W, p, epi, st);
@@ -117,6 +132,29 @@ int gemm_launch(const void* A, const void* W, const GemmParams& p, int epi, cuda
   }
   set_error("gemm: unsupported tile width %d", bn);
   return VB_ERR_ARG;
+}
+
+int conv3x3_launch(const void* x, const void* w_packed, const float* bias, const void* resid, void* out, int B, int H,
+                   int W, int Cin, int Cout, cudaStream_t st) {
+  VB_REQUIRE(x && w_packed && out && B > 0 && H > 0 && W > 0, "conv3x3: bad arguments");
+  VB_REQUIRE(Cin > 0 && Cin % 8 == 0 && Cout % 32 == 0, "conv3x3: Cin=%d must be a multiple of 8, Cout=%d of 32", Cin, Cout);
+  VB_REQUIRE((W <= GEMM_BM ? GEMM_BM % W == 0 : W % GEMM_BM == 0) && (H * W) % GEMM_BM == 0,
+             "conv3x3: H=%d W=%d not tileable into 128-pixel row patches", H, W);
+  VB_REQUIRE((long long)B * H * W < (1ll << 31), "conv3x3: too many pixels");
+  GemmParams p{};
+  p.M = B * H * W;
+  p.N = Cout;
+  p.conv_kpt = (Cin + GEMM_BK - 1) / GEMM_BK;
+  p.K = 9 * p.conv_kpt * GEMM_BK;
+  p.conv_H = H;
+  p.conv_W = W;
+  p.bias = bias;
+  p.out = out;
+  p.resid_bf16 = reinterpret_cast<const __nv_bfloat16*>(resid);
+  g_conv_cin = Cin;
+  const int r = gemm_launch(x, w_packed, p, EPI_BIAS_BF16, st, Cout % 160 == 0 ? 160 : 0);
+  g_conv_cin = 0;
+  return r;
 }
 
 }  // namespace vb

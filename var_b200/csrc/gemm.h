@@ -34,6 +34,12 @@ struct GemmParams {
   int gt_mod;
   float2* part;     // [M, 2*n_tiles] (max, sum exp(x - max)) per row, tile and epilogue half
   float* gt_logit;  // [M]
+  // EPI_BIAS_BF16: optional bf16 [M,N] added to the rounded result (ResnetBlock shortcut, models/basic_vae.py:60)
+  const __nv_bfloat16* resid_bf16;
+  // Implicit-GEMM 3x3 convolution, stride 1, zero padding 1 (models/basic_vae.py:45-46,52-59): A is the NHWC bf16
+  // activation tensor [B, conv_H, conv_W, Cin] seen through a 4-D tensor map, row m = pixel ((b*H + y)*W + x);
+  // K = 9 taps x conv_kpt 64-channel blocks (weights packed [N, 9, conv_kpt*64], zero padded). 0 = plain GEMM.
+  int conv_kpt, conv_H, conv_W;
 };
 
 // Tile width the launcher will use for a given N (needed to size EPI_SCORE partials: n_tiles = ceil(N / bn)).
@@ -41,5 +47,10 @@ int gemm_pick_bn(int N);
 // A: [M,K] bf16 row-major, W: [N,K] bf16 row-major (nn.Linear layout). force_bn: 0 = auto, else 128/192/256,
 // optionally | 0x10000 to force the 1-CTA kernel (the default is the CTA-pair kernel whenever M > 128).
 int gemm_launch(const void* A, const void* W, const GemmParams& p, int epi, cudaStream_t st, int force_bn = 0);
+// 3x3 / stride 1 / pad 1 convolution on NHWC bf16 through the same kernels: x [B,H,W,Cin], w_packed [Cout, 9*kpt*64]
+// (tap-major, channels zero-padded to kpt*64), out [B,H,W,Cout] bf16 = conv + bias (+ resid). Requires Cout % 32 == 0,
+// Cin % 8 == 0, W | 128 or 128 | W, (H*W) % 128 == 0.
+int conv3x3_launch(const void* x, const void* w_packed, const float* bias, const void* resid, void* out, int B, int H,
+                   int W, int Cin, int Cout, cudaStream_t st);
 
 }  // namespace vb

@@ -86,6 +86,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       for (int tile = cid; tile < total_tiles; tile += ncl) {
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        const int m0 = m_blk * TILE_M + rank * GEMM_BM;  // first accumulator row (pixel) of this CTA
+        // conv mode: the 128 rows are a bw x bh patch of one image; tap (dy,dx) reads the patch shifted by (dy-1,dx-1),
+        // rows/columns outside the image come back as zeros from TMA (= the convolution's zero padding)
+        int cx0 = 0, cy0 = 0, cb = 0;
+        if (p.conv_kpt > 0) {
+          const int hw = p.conv_H * p.conv_W;
+          cb = m0 / hw;
+          const int rem = m0 - cb * hw;
+          cy0 = rem / p.conv_W;
+          cx0 = rem - cy0 * p.conv_W;
+        }
+        int tap = 0, kc = 0;  // conv mode: filter tap and channel block of k-block kb
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
@@ -93,13 +105,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             // completion bytes of BOTH CTAs are credited to the leader's full barrier (it gates the pair's MMAs)
             const uint32_t fb = mapa_shared(full_bar(stage), 0);
             if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
-            tma_load_2d_cg2(&tmA, fb, sa, kb * GEMM_BK, m_blk * TILE_M + rank * GEMM_BM);
+            if (p.conv_kpt > 0)
+              tma_load_4d_cg2(&tmA, fb, sa, kc * GEMM_BK, cx0 + tap % 3 - 1, cy0 + tap / 3 - 1, cb);
+            else
+              tma_load_2d_cg2(&tmA, fb, sa, kb * GEMM_BK, m0);
             tma_load_2d_cg2(&tmB, fb, sa + Cfg::A_BYTES, kb * GEMM_BK, n_blk * BN + rank * (BN / 2));
           } else {
             mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
-            tma_load_2d(&tmA, full_bar(stage), sa, kb * GEMM_BK, m_blk * GEMM_BM);
+            if (p.conv_kpt > 0)
+              tma_load_4d(&tmA, full_bar(stage), sa, kc * GEMM_BK, cx0 + tap % 3 - 1, cy0 + tap / 3 - 1, cb);
+            else
+              tma_load_2d(&tmA, full_bar(stage), sa, kb * GEMM_BK, m0);
             tma_load_2d(&tmB, full_bar(stage), sa + Cfg::A_BYTES, kb * GEMM_BK, n_blk * BN);
           }
+          if (++kc == p.conv_kpt) { kc = 0; ++tap; }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -369,9 +388,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int i = 0; i < 4; ++i) {
               const int r = rsub + 8 * i;
               const int rg = row_w0 + r;
-              if (rg < p.M)
-                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)rg * p.N + n0 + cg * 8) =
-                    *reinterpret_cast<const uint4*>(stg + r * EPI_STG_LD + cg * 4);
+              if (rg < p.M) {
+                uint4 w = *reinterpret_cast<const uint4*>(stg + r * EPI_STG_LD + cg * 4);
+                const size_t off = (size_t)rg * p.N + n0 + cg * 8;
+                if constexpr (EPI == EPI_BIAS_BF16) {
+                  if (p.resid_bf16 != nullptr) {  // bf16 + bf16 like the eager `x + h` of the reference's ResnetBlock
+                    const uint4 rr = *reinterpret_cast<const uint4*>(p.resid_bf16 + off);
+                    __nv_bfloat162* a2 = reinterpret_cast<__nv_bfloat162*>(&w);
+                    const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&rr);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) a2[e] = __hadd2(a2[e], b2[e]);
+                  }
+                }
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off) = w;
+              }
             }
             __syncwarp();
           }

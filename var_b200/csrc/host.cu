@@ -45,7 +45,7 @@ static EncodeTiledFn get_encode() {
 // Descriptor cache: the block driver re-encodes the same (pointer, shape, box) maps on every call (weights and
 // workspace buffers keep their addresses), and cuTensorMapEncodeTiled costs microseconds of host time each.
 struct TmapKey {
-  uint64_t w[12];
+  uint64_t w[16];  // ptr | rank | dims[5] | box[5] | strides[4]
 };
 static std::unordered_map<std::string, CUtensorMap> g_tmaps;
 static std::mutex g_tmaps_mu;
@@ -57,8 +57,8 @@ int make_tmap_bf16_sw128(CUtensorMap* out, const void* gptr, int rank, const uin
   key.w[1] = (uint64_t)rank;
   for (int i = 0; i < rank; ++i) {
     key.w[2 + i] = dims[i];
-    key.w[6 + i] = box[i];
-    if (i + 1 < rank) key.w[9 + i] = strides_bytes[i];
+    key.w[7 + i] = box[i];
+    if (i + 1 < rank) key.w[12 + i] = strides_bytes[i];
   }
   const std::string ks(reinterpret_cast<const char*>(&key), sizeof(key));
   {

@@ -125,6 +125,7 @@ def _EXTRA_SIGS(vp, i32, i64, f32):
         "var_b200_quant_decode": [C.POINTER(QuantDesc), vp, i32, vp, vp, vp, vp],
         "var_b200_quant_next_input": [C.POINTER(QuantDesc), i32, vp, vp, i32, vp, vp, vp],
         "var_b200_cfg_topk_sample": [vp, i32, i32, i32, i32, dbl, vp, i32, f32, vp, vp, vp],
+        "var_b200_conv3x3_nhwc": [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
         "var_b200_cfg_topk_sample_smooth": [vp, i32, i32, i32, i32, dbl, vp, i32, f32, vp, vp, vp, f32, f32, vp, i32, vp, vp],
         "var_b200_cfg_token_logprob": [vp, vp, vp, vp, i32, i32, i32, vp, vp],
         "var_b200_neighbor_select": [vp, i32, i32, i32, dbl, vp, vp, vp, i32, i32, i32, f32, f32, vp, vp, vp, vp],

@@ -19,6 +19,7 @@ class VQVAE(nn.Module):
         self.test_mode = test_mode
         self.decoder_dtype = None  # set to torch.bfloat16 / float16 to run fhat_to_img through a 16-bit decoder copy
         self.decoder_nhwc = True   # with decoder_dtype=bfloat16: channels-last plan with the fused GroupNorm+SiLU kernel
+        self.decoder_own_conv = True  # ... and the 3x3 convolutions on var_b200's implicit-GEMM tcgen05 kernel (else cuDNN)
         self.encoder_dtype = None  # torch.bfloat16: channels-last 16-bit encoder plan (token indices then depend on bf16
         #                            rounding of the features; the default fp32 encoder keeps them reference-exact)
         self.V, self.Cvae = vocab_size, z_channels
@@ -46,6 +47,7 @@ class VQVAE(nn.Module):
             if getattr(self, "_nhwc_dec", None) is None:
                 from .basic_vae import NHWCDecoder
                 self._nhwc_dec = NHWCDecoder(self.decoder, self.post_quant_conv)
+            self._nhwc_dec.own_conv = bool(getattr(self, "decoder_own_conv", True))
             return self._nhwc_dec(f_hat).clamp_(-1, 1)
         if self.decoder_dtype is not None and f_hat.is_cuda:
             post, dec = self._low_precision_decoder()
@@ -77,6 +79,7 @@ class VQVAE(nn.Module):
             if getattr(self, "_nhwc_enc", None) is None:
                 from .basic_vae import NHWCEncoder
                 self._nhwc_enc = NHWCEncoder(self.encoder, self.quant_conv)
+            self._nhwc_enc.own_conv = bool(getattr(self, "decoder_own_conv", True))
             return self._nhwc_enc(inp_img_no_grad)
         return self.quant_conv(self.encoder(inp_img_no_grad))
 
