@@ -92,6 +92,7 @@ __device__ float block_kth_largest(const float* xs, int V, int k, int* hist, uin
   return key2f(*sel_prefix);
 }
 
+template <bool SMOOTH>  // SMOOTH: also emit the more_smooth soft embedding (separate instantiation: 32 extra registers)
 __global__ void __launch_bounds__(ST)
 sample_kernel(const float* __restrict__ logits, int B, int l, int V, int use_cfg, float one_plus_t, float t,
               const float* __restrict__ q, int top_k, float top_p, float p_lim, long long* __restrict__ idx_out,
@@ -178,7 +179,7 @@ sample_kernel(const float* __restrict__ logits, int B, int l, int V, int use_cfg
       if (bval[w] > best || (bval[w] == best && bidx[w] < bi)) { best = bval[w]; bi = bidx[w]; }
     idx_out[r] = bi == 0x7fffffff ? 0 : bi;
   }
-  if (q_gumbel == nullptr) return;
+  if constexpr (!SMOOTH) return;
   // ---- more_smooth (models/var.py:178-180, helpers.py:22-36): soft embedding of the filtered row,
   //      h = softmax((x * (1 + ratio) - log(q_gumbel)) / tau) @ codebook, q_gumbel ~ Exp(1) drawn after the sampler noise
   __syncthreads();
@@ -231,14 +232,16 @@ int sample_launch(const SampleArgs& a, cudaStream_t st) {
   }
   static size_t attr = 0;
   if (smem > attr && smem > 40 * 1024) {  // static smem (~1.2 KB) counts against the 48 KB default limit
-    VB_CUDA_CHECK(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VB_CUDA_CHECK(cudaFuncSetAttribute(sample_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VB_CUDA_CHECK(cudaFuncSetAttribute(sample_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
   const float opt = (float)(1.0 + a.t), tf = (float)a.t;
   vb::ProfScope prof_scope(vb::PK_SAMPLE, st);
-  sample_kernel<<<a.B * a.l, ST, smem, st>>>(a.logits, a.B, a.l, a.V, a.use_cfg, opt, tf, a.q, a.top_k, a.top_p, (float)(1.0 - (double)a.top_p),
-                                             reinterpret_cast<long long*>(a.idx_out), a.mixed_out, use_p ? vp2 : 0, a.q_gumbel, a.tau, a.logit_mul,
-                                             a.codebook, a.Cvae, a.h_out);
+  auto kern = a.q_gumbel != nullptr ? sample_kernel<true> : sample_kernel<false>;
+  kern<<<a.B * a.l, ST, smem, st>>>(a.logits, a.B, a.l, a.V, a.use_cfg, opt, tf, a.q, a.top_k, a.top_p, (float)(1.0 - (double)a.top_p),
+                                    reinterpret_cast<long long*>(a.idx_out), a.mixed_out, use_p ? vp2 : 0, a.q_gumbel, a.tau, a.logit_mul,
+                                    a.codebook, a.Cvae, a.h_out);
   VB_CUDA_CHECK(cudaGetLastError());
   vb::count_launch();
   return VB_OK;
