@@ -12,6 +12,7 @@ sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from var_b200 import lib as L  # noqa: E402
 
 depth, n_seq, l = (int(a) for a in sys.argv[1:4]) if len(sys.argv) > 3 else (30, 512, 256)
+FORCE_BN = int(sys.argv[4]) if len(sys.argv) > 4 else 0  # 0 = the launcher's choice
 Cd, H, Lmax = 64 * depth, depth, 680
 M = n_seq * l
 lib = L.load()
@@ -38,6 +39,7 @@ def base(N, K, epi):
     a = L.GemmArgs()
     a.A, a.W, a.M, a.N, a.K, a.epilogue = A.data_ptr(), W.data_ptr(), M, N, K, epi
     a.bias = bias.data_ptr()
+    a.force_bn = FORCE_BN
     return a, (A, W, bias)
 
 
