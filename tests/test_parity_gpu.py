@@ -77,6 +77,51 @@ def test_quant_decode_and_step_bit_exact():
     assert np.array_equal(f_hat.cpu().numpy(), f_ref)
 
 
+def test_embed_to_fhat_arbitrary_maps_bit_exact():
+    """embed_to_fhat (quant.py:107-121): on codebook rows it must equal idxBl_to_fhat bit for bit; on arbitrary maps it
+    must equal the oracle's accumulation of Phi(bicubic(h)) (same fp32 op order)."""
+    g = golden("quant_forward_d2.npz")
+    vae, _ = seeded_models(device=DEV)
+    q = vae.quantize
+    idx = [_t(i) for i in split_scales(g["idx"])]
+    hs = [q.embedding(i).transpose(1, 2).reshape(3, 32, p, p) for i, p in zip(idx, PATCH_NUMS)]
+    fl = q.embed_to_fhat(hs, all_to_max_scale=True, last_one=False)
+    ref = q.idxBl_to_fhat(idx, last_one=False)
+    assert len(fl) == 10 and all(torch.equal(a, b) for a, b in zip(fl, ref))
+    assert torch.equal(q.embed_to_fhat(hs, last_one=True), ref[-1])
+    # arbitrary (non-codebook) maps: the single-scale step kernel is the independent restatement
+    gen = torch.Generator().manual_seed(5)
+    hs = [torch.randn(2, 32, p, p, generator=gen).to(DEV) for p in PATCH_NUMS]
+    last = q.embed_to_fhat(hs, last_one=True)
+    f_hat = torch.zeros(2, 32, 16, 16, device=DEV)
+    for si in range(10):
+        q.get_next_autoregressive_input(si, 10, f_hat, hs[si])
+    assert torch.equal(last, f_hat)
+    with pytest.raises(NotImplementedError):
+        q.embed_to_fhat(hs, all_to_max_scale=False)
+    imgs = vae.embed_to_img(hs, all_to_max_scale=True, last_one=True)
+    assert imgs.shape == (2, 3, 256, 256) and float(imgs.abs().max()) <= 1.0
+
+
+def test_get_logits_matches_forward_head():
+    """VAR.get_logits(h, cond_BD) (var.py:118-124) == the head of VAR.forward on the same final activations."""
+    _, var = seeded_models(device=DEV)
+    gen = torch.Generator().manual_seed(3)
+    labels = torch.tensor([5, 999], device=DEV)
+    vin = torch.randn(2, 679, 32, generator=gen).to(DEV)
+    logits, blocks = var(labels, vin, return_blocks=True)
+    got = var.get_logits(blocks[-1], var.class_emb(labels))
+    assert got.shape == (2, 680, 4096) and got.dtype == torch.float32
+    # SiLU(cond) is rounded to bf16 by two different producers (torch here, cond_silu_kernel in forward): 1-ulp
+    # differences of the GEMM operand allowed, nothing more
+    assert (got - logits).abs().max().item() < 5e-3
+    assert torch.equal(var.get_logits(blocks[-1], labels=labels), logits)
+    part = var.get_logits(blocks[-1][:, 5:14], var.class_emb(labels))  # any l, as the AR loop calls it (var.py:168)
+    assert torch.equal(part, got[:, 5:14])
+    pair = var.get_logits((blocks[-1] * 0.25, blocks[-1] * 0.75), labels=labels)  # (h, residual) form
+    assert (pair - logits).abs().max().item() < 5e-3
+
+
 def test_vqvae_boundary_functions():
     """img_to_idxBl / idxBl_to_img keep the reference signatures (vqvae.py:65,77); encoder/decoder are PyTorch."""
     g = golden("quant_forward_d2.npz")

@@ -175,9 +175,28 @@ class VectorQuantizer2(nn.Module):
         return last if last_one else [fl[i] for i in range(fl.shape[0])]
 
     def embed_to_fhat(self, ms_h_BChw: List[torch.Tensor], all_to_max_scale=True, last_one=False):
-        raise NotImplementedError(
-            "embed_to_fhat on arbitrary embeddings is not on the hot path; use idxBl_to_fhat (token indices), which is "
-            "what VQVAE.idxBl_to_img feeds it (vqvae.py:77-84)")
+        """quant.py:107-133 on arbitrary per-scale maps h_si [B, Cvae, ph, pw]. The decode kernel reads them through a
+        "virtual codebook" (row = one (scale, image, position) vector, identity indices), so the arithmetic is the
+        one `idxBl_to_fhat` runs on codebook lookups."""
+        if not all_to_max_scale:
+            raise NotImplementedError("all_to_max_scale=False is the reference's experimental path (quant.py:122-131)")
+        hws = [_hw(pn) for pn in self.v_patch_nums]
+        assert len(ms_h_BChw) == len(hws)
+        B, dev = ms_h_BChw[0].shape[0], ms_h_BChw[0].device
+        for h, (ph, pw) in zip(ms_h_BChw, hws):
+            assert tuple(h.shape) == (B, self.Cvae, ph, pw), f"{tuple(h.shape)=} != {(B, self.Cvae, ph, pw)}"
+        rows = torch.cat([h.detach().float().reshape(B, self.Cvae, -1).transpose(1, 2).reshape(-1, self.Cvae)
+                          for h in ms_h_BChw]).contiguous()
+        d = self._desc(hws)
+        d.codebook, d.V = rows.data_ptr(), rows.shape[0]
+        d._keep = d._keep + (rows,)
+        idx = torch.arange(rows.shape[0], device=dev, dtype=torch.int64)
+        H, W = hws[-1]
+        fl = None if last_one else torch.empty((len(hws), B, self.Cvae, H, W), dtype=torch.float32, device=dev)
+        last = torch.empty((B, self.Cvae, H, W), dtype=torch.float32, device=dev)
+        L.check(L.load().var_b200_quant_decode(C.byref(d), idx.data_ptr(), B, None, L.ptr(fl), last.data_ptr(),
+                                               L.current_stream()), "quant_decode")
+        return last if last_one else [fl[i] for i in range(fl.shape[0])]
 
     def get_next_autoregressive_input(self, si: int, SN: int, f_hat: torch.Tensor, h_BChw: torch.Tensor = None, *,
                                       idx_Bl: torch.Tensor = None, token_major: bool = False):

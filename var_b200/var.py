@@ -189,8 +189,24 @@ class VAR(nn.Module):
 
     @torch.no_grad()
     def get_logits(self, h_or_h_and_residual, cond_BD=None, *, labels: Optional[torch.Tensor] = None):
-        """models/var.py:118-124. The kernel path is driven by labels (cond_BD = class_emb(label))."""
-        raise NotImplementedError("get_logits is fused into forward/autoregressive_infer_cfg (var_b200_head_logits)")
+        """models/var.py:118-124: head(head_nm(h.float(), cond_BD)) -> fp32 logits [B, l, V]. The head's (scale, shift)
+        come from `cond_BD` (SiLU -> Linear on the tcgen05 GEMM) or, keyword-only, from `labels`
+        (cond_BD = class_emb(labels), the table `forward` uses)."""
+        if not isinstance(h_or_h_and_residual, torch.Tensor):  # (h, residual) pair of the fused add-norm path
+            h, resi = h_or_h_and_residual
+            h = resi + h  # drop_path is the identity at inference
+        else:
+            h = h_or_h_and_residual
+        pm = self._model()
+        B, l, _ = h.shape
+        x = h.detach().to(self.lvl_1L.device).float().contiguous()
+        if labels is not None:
+            ada = pm.ada_params(self._labels_i32(labels, B))
+        elif cond_BD is not None:
+            ada = pm.head_ada_from_cond(cond_BD.reshape(B, self.D))
+        else:
+            raise ValueError("get_logits needs cond_BD or labels")
+        return pm.head_logits(x, ada, B, l)
 
     @torch.no_grad()
     def forward(self, label_B: torch.LongTensor, x_BLCv_wo_first_l: torch.Tensor, *, return_blocks: bool = False):
@@ -519,6 +535,7 @@ class PackedModel:
         if gss is not None:
             keep.append(gss)
         self.m, self._keep = m, keep
+        self.w_ada, self.b_ada = t["w_ada"], t["b_ada"]
         self.depth, self.C, self.H, self.V, self.Cvae, self.L, self.first_l = self.var_cfg
         self.ada_ld = self.lib.var_b200_ada_ld(C.byref(m))
         self._ws = {}
@@ -539,6 +556,21 @@ class PackedModel:
         L.check(self.lib.var_b200_ada_params(C.byref(self.m), labels_i32.data_ptr(), n, out.data_ptr(), ws.data_ptr(),
                                              ws.numel(), L.current_stream()), "ada_params")
         return out
+
+    def head_ada_from_cond(self, cond: torch.Tensor) -> torch.Tensor:
+        """adaLN table with only the head_nm columns filled: Linear(SiLU(cond)) (basic_var.py:173) on the GEMM kernel."""
+        n = cond.shape[0]
+        a_in = torch.nn.functional.silu(cond.detach().to(self.dev).float()).to(torch.bfloat16).contiguous()
+        rows = 2 * self.C
+        w, b = self.w_ada[-rows:], self.b_ada[-rows:]  # head_nm.ada_lin is the last 2C rows of the packed adaLN weights
+        out = torch.empty((n, rows), dtype=torch.float32, device=self.dev)
+        g = L.GemmArgs()
+        g.A, g.W, g.M, g.N, g.K, g.epilogue = a_in.data_ptr(), w.data_ptr(), n, rows, a_in.shape[1], L.EPI_BIAS_F32
+        g.bias, g.out = b.data_ptr(), out.data_ptr()
+        L.check(self.lib.var_b200_gemm_bf16(C.byref(g), L.current_stream()), "gemm(head ada)")
+        ada = torch.zeros((n, self.ada_ld), dtype=torch.float32, device=self.dev)
+        ada[:, self.ada_ld - rows:] = out
+        return ada
 
     def embed(self, x_in, n_x, labels_i32, n_seq, l, first_rows, pos0) -> torch.Tensor:
         out = torch.empty((n_seq, l, self.C), dtype=torch.float32, device=self.dev)

@@ -73,6 +73,11 @@ class VQVAE(nn.Module):
             return self.fhat_to_img(self.quantize.idxBl_to_fhat(ms_idx_Bl, last_one=True))
         return [self.fhat_to_img(f) for f in self.quantize.idxBl_to_fhat(ms_idx_Bl, last_one=False)]
 
+    def embed_to_img(self, ms_h_BChw: List[torch.Tensor], all_to_max_scale: bool, last_one=False):
+        """vqvae.py:86-90 on arbitrary per-scale embedding maps."""
+        fs = self.quantize.embed_to_fhat(ms_h_BChw, all_to_max_scale=all_to_max_scale, last_one=last_one)
+        return self.fhat_to_img(fs) if last_one else [self.fhat_to_img(f) for f in fs]
+
     # ---- encode side (vqvae.py:65-75, 92-98)
     def img_to_post(self, inp_img_no_grad: torch.Tensor, v_patch_nums=None):
         if self.encoder_dtype is torch.bfloat16 and inp_img_no_grad.is_cuda:
