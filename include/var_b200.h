@@ -99,10 +99,15 @@ VAR_B200_API int var_b200_umma_probe(const void* A, const void* B, float* D, int
  * Block-causal attention (models/basic_var.py:98-117, mask of models/var.py:107-112), tcgen05/TMEM.
  * q: bf16 [n_seq,H,Lq,64], k/v: bf16 [n_seq,H,Lmax,64] (the preallocated KV cache), out: bf16 [n_seq,Lq,H*64].
  * A query at absolute position q_pos0 + i of pyramid level s attends keys [0, level_end[s]).
+ * max_score: an upper bound on |q.k| if the caller knows one (for VAR the largest per-head scale
+ * exp(min(scale_mul, ln 100)), basic_var.py:101, a model constant), else 0. With 0 < max_score <= 43 the softmax runs
+ * against that fixed reference (no row maximum, eight softmax warps per CTA); otherwise the general kernel tracks a
+ * per-row reference maximum and rebases on overflow. Both give softmax(q k^T + mask) v.
  * ---------------------------------------------------------------------------------------------- */
 #define VAR_B200_MAX_SCALES 16
 VAR_B200_API int var_b200_attention(const void* q, const void* k, const void* v, void* out, int n_seq, int H, int Lq,
-                                    int Lmax, int q_pos0, int n_scales, const int* level_end /* host */, void* stream);
+                                    int Lmax, int q_pos0, int n_scales, const int* level_end /* host */,
+                                    float max_score, void* stream);
 
 /* LN(x)*(1+scale[seq])+shift[seq] -> bf16 (models/basic_var.py:157-158,174). scale/shift: row stride ada_ld. */
 VAR_B200_API int var_b200_ln_modulate(const float* x, const float* scale, const float* shift, int ada_ld,
@@ -186,6 +191,7 @@ typedef struct var_b200_model {
   const float* class_emb; /* [num_classes+1, C] */
   const float* pos_start; /* [first_l, C] */
   const float* lvl_pos;   /* [L, C] = lvl_embed[lvl_1L] + pos_1LC   (var.py:153,207) */
+  float attn_max_score;   /* max over blocks and heads of q_scale (bound on |q.k|, see var_b200_attention); 0 = unknown */
 } var_b200_model_t;
 
 /* Row stride (floats) of the per-sequence adaLN parameter table: (6*depth + 2) * C.

@@ -15,6 +15,7 @@ struct AttnArgs {
   int q_pos0;                    // absolute sequence position of query row 0
   int n_scales;                  // pyramid levels
   int level_end[VB_MAX_SCALES];  // cumulative token count after each level
+  float max_score;               // upper bound on |q.k| if the caller knows one (the per-head scale), else 0
 };
 
 int attn_launch(const AttnArgs& a, cudaStream_t st);

@@ -153,6 +153,7 @@ extern "C" int var_b200_blocks(const var_b200_model_t* m, float* x, const float*
   const size_t cache_elems = (size_t)n_seq * m->H * Lmax * 64;
   AttnArgs at{};
   at.n_seq = n_seq; at.H = m->H; at.Lq = l; at.Lmax = Lmax; at.q_pos0 = pos0; at.n_scales = m->n_scales;
+  at.max_score = m->attn_max_score;
   level_ends(m, at.level_end);
   VB_REQUIRE(pos0 + l <= at.level_end[m->n_scales - 1], "blocks: positions beyond the pyramid");
   for (int i = 0; i < m->depth; ++i) {
@@ -239,11 +240,12 @@ extern "C" int var_b200_head_score(const var_b200_model_t* m, const float* x, co
 }
 
 extern "C" int var_b200_attention(const void* q, const void* k, const void* v, void* out, int n_seq, int H, int Lq, int Lmax,
-                                  int q_pos0, int n_scales, const int* level_end, void* stream) {
+                                  int q_pos0, int n_scales, const int* level_end, float max_score, void* stream) {
   VB_REQUIRE(level_end && n_scales > 0 && n_scales <= VAR_B200_MAX_SCALES, "attention: bad level table");
   AttnArgs a{};
   a.q = q; a.k = k; a.v = v; a.out = out; a.n_seq = n_seq; a.H = H; a.Lq = Lq; a.Lmax = Lmax; a.q_pos0 = q_pos0;
   a.n_scales = n_scales;
+  a.max_score = max_score;
   for (int i = 0; i < n_scales; ++i) a.level_end[i] = level_end[i];
   return attn_launch(a, (cudaStream_t)stream);
 }

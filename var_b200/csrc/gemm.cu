@@ -92,6 +92,18 @@ int gemm_pick_bn(int N) {
   return best;
 }
 
+// M-aware refinement: with at least two full waves of 256 x 256 tiles the wider tile still wins at up to 7 % padding
+// (d30 proj / fc2, N = 1920: 1200 / 1449 vs 1160 / 1418 TFLOP/s at M = 131072); below that the narrower tile keeps
+// more CTA pairs busy. The SCORE epilogue sizes its partials with gemm_pick_bn(N) and keeps that choice.
+static int gemm_pick_bn_mn(int M, int N, int epi) {
+  const int bn = gemm_pick_bn(N);
+  if (bn == 256 || epi == EPI_SCORE) return bn;
+  const long long pad256 = ((N + 255) / 256) * 256LL;
+  const long long tiles256 = ((M + 255) / 256) * (pad256 / 256);
+  if (pad256 * 100 <= (long long)N * 107 && tiles256 >= 2LL * (vb::sm_count() / 2)) return 256;
+  return bn;
+}
+
 int gemm_launch(const void* A, const void* W, const GemmParams& p, int epi, cudaStream_t st, int force_bn) {
   VB_REQUIRE(A && W, "gemm: null operand");
   VB_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
@@ -112,7 +124,7 @@ int gemm_launch(const void* A, const void* W, const GemmParams& p, int epi, cuda
     if (epi == EPI_GATE_RESID)
       VB_REQUIRE(p.resid && p.gate && p.rows_per_seq > 0, "gemm/gate: null pointer or rows_per_seq=%d", p.rows_per_seq);
   }
-  const int bn = force_bn ? (force_bn & 0xffff) : gemm_pick_bn(p.N);
+  const int bn = force_bn ? (force_bn & 0xffff) : gemm_pick_bn_mn(p.M, p.N, epi);
   // CTA-pair tiles (256 x BN) unless the problem is a single 128-row tile or the caller forces 1-CTA (bit 16)
   const bool pair = !(force_bn & 0x10000) && p.M > GEMM_BM;
   if (bn == 160) {  // 160-wide tiles exist for the convolution epilogue only (channel counts 160 / 320 / 640 of the VQVAE)

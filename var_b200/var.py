@@ -531,6 +531,9 @@ class PackedModel:
             setattr(m, k, v.data_ptr())
             keep.append(v)
         m.ada_rows = w_ada.shape[0]
+        # |q.k| <= per-head scale (basic_var.py:101-105): lets the attention kernel use a fixed softmax reference
+        m.attn_max_score = float(torch.stack([b.attn.scale_mul_1H11.detach().clamp_max(b.attn.max_scale_mul).exp().max()
+                                              for b in var.blocks]).max().item())  # one host read at pack time
         m.ada_gss = gss.data_ptr() if gss is not None else None
         if gss is not None:
             keep.append(gss)
