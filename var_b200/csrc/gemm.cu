@@ -1,3 +1,4 @@
+#include <stdlib.h>
 // Host launcher for the tcgen05 GEMM family + the raw C-ABI entry used by tests and by the block driver.
 #include "gemm.h"
 
@@ -98,6 +99,8 @@ int gemm_pick_bn(int N) {
 static int gemm_pick_bn_mn(int M, int N, int epi) {
   const int bn = gemm_pick_bn(N);
   if (bn == 256 || epi == EPI_SCORE) return bn;
+  static const int wide = [] { const char* e = getenv("VAR_B200_GEMM_WIDE"); return e ? atoi(e) : 1; }();  // A/B switch
+  if (!wide) return bn;
   const long long pad256 = ((N + 255) / 256) * 256LL;
   const long long tiles256 = ((M + 255) / 256) * (pad256 / 256);
   if (pad256 * 100 <= (long long)N * 107 && tiles256 >= 2LL * (vb::sm_count() / 2)) return 256;
