@@ -103,11 +103,14 @@ VAR_B200_API int var_b200_umma_probe(const void* A, const void* B, float* D, int
  * exp(min(scale_mul, ln 100)), basic_var.py:101, a model constant), else 0. With 0 < max_score <= 43 the softmax runs
  * against that fixed reference (no row maximum, eight softmax warps per CTA); otherwise the general kernel tracks a
  * per-row reference maximum and rebases on overflow. Both give softmax(q k^T + mask) v.
+ * q_log2 != 0: q is already multiplied by log2(e) (var_b200_model_t folds it into q_scale), i.e. the scores are base-2
+ * exponents and the bounded-score kernel feeds them to exp2 unchanged; requires 0 < max_score <= 43 (max_score stays in
+ * natural units), else VB_ERR_ARG.
  * ---------------------------------------------------------------------------------------------- */
 #define VAR_B200_MAX_SCALES 16
 VAR_B200_API int var_b200_attention(const void* q, const void* k, const void* v, void* out, int n_seq, int H, int Lq,
                                     int Lmax, int q_pos0, int n_scales, const int* level_end /* host */,
-                                    float max_score, void* stream);
+                                    float max_score, int q_log2, void* stream);
 
 /* LN(x)*(1+scale[seq])+shift[seq] -> bf16 (models/basic_var.py:157-158,174). scale/shift: row stride ada_ld. */
 VAR_B200_API int var_b200_ln_modulate(const float* x, const float* scale, const float* shift, int ada_ld,
@@ -191,7 +194,9 @@ typedef struct var_b200_model {
   const float* class_emb; /* [num_classes+1, C] */
   const float* pos_start; /* [first_l, C] */
   const float* lvl_pos;   /* [L, C] = lvl_embed[lvl_1L] + pos_1LC   (var.py:153,207) */
-  float attn_max_score;   /* max over blocks and heads of q_scale (bound on |q.k|, see var_b200_attention); 0 = unknown */
+  float attn_max_score;   /* max over blocks and heads of exp(min(scale_mul, ln 100)) (bound on |q.k|, natural units,
+                             see var_b200_attention); 0 = unknown */
+  int attn_q_log2;        /* blocks[].q_scale already carries a factor log2(e) (only with 0 < attn_max_score <= 43) */
 } var_b200_model_t;
 
 /* Row stride (floats) of the per-sequence adaLN parameter table: (6*depth + 2) * C.

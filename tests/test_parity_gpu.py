@@ -2,6 +2,7 @@
 Bit-exact: VQ indices, f_hat / var_input (same fp32 op order as the C oracle), sampled tokens given logits + noise.
 Tolerance (bf16 tensor-core GEMMs vs the fp32 oracle): stated per test."""
 import ctypes as C
+import math
 
 import numpy as np
 import pytest
@@ -153,10 +154,10 @@ def _attn_ref(q, k, v, q_pos0, ends):
     return (s.softmax(-1) @ v.float()).transpose(1, 2).reshape(q.shape[0], Lq, -1)
 
 
-@pytest.mark.parametrize("scale,bound", [(6.0, 0.0), (6.0, 6.0), (6.0, 43.0), (40.0, 40.0)],
-                         ids=["general", "bounded", "bounded_loose", "bounded_scale40"])
+@pytest.mark.parametrize("scale,bound,q_log2", [(6.0, 0.0, 0), (6.0, 6.0, 0), (6.0, 6.0, 1), (6.0, 43.0, 1), (40.0, 40.0, 1)],
+                         ids=["general", "bounded", "bounded_log2", "bounded_loose_log2", "bounded_scale40_log2"])
 @pytest.mark.parametrize("n_seq,H,si", [(2, 2, None), (3, 16, None), (2, 4, 0), (4, 2, 3), (2, 30, 9), (1, 2, 8), (5, 3, 7)])
-def test_attention_block_causal(n_seq, H, si, scale, bound):
+def test_attention_block_causal(n_seq, H, si, scale, bound, q_log2):
     """General kernel (per-row reference maximum, 4 softmax warps) and the bounded-score kernel (fixed reference =
     the caller's bound on |q.k|, 8 softmax warps) against fp32 softmax attention with the block-causal mask."""
     torch.manual_seed(7)
@@ -166,13 +167,16 @@ def test_attention_block_causal(n_seq, H, si, scale, bound):
     q = torch.nn.functional.normalize(torch.randn(n_seq, H, Lq, 64, device=DEV), dim=-1) * scale
     k = torch.nn.functional.normalize(torch.randn(n_seq, H, Lmax, 64, device=DEV), dim=-1)
     v = torch.randn(n_seq, H, Lmax, 64, device=DEV)
-    qb, kb, vb = q.bfloat16(), k.bfloat16(), v.bfloat16()
+    # q_log2: the caller hands over q * log2(e) (what the packed model's QKV epilogue produces); the reference then uses
+    # the bf16 values the kernel saw, divided by log2(e)
+    qb = (q * math.log2(math.e)).bfloat16() if q_log2 else q.bfloat16()
+    kb, vb = k.bfloat16(), v.bfloat16()
     out = torch.full((n_seq, Lq, H * 64), float("nan"), device=DEV, dtype=torch.bfloat16)
     arr = (C.c_int * 10)(*[int(e) for e in ends])
     L.check(L.load().var_b200_attention(qb.data_ptr(), kb.data_ptr(), vb.data_ptr(), out.data_ptr(), n_seq, H, Lq, Lmax,
-                                        pos0, 10, arr, bound, L.current_stream()), "attention")
+                                        pos0, 10, arr, bound, q_log2, L.current_stream()), "attention")
     torch.cuda.synchronize()
-    ref = _attn_ref(qb, kb, vb, pos0, ends)
+    ref = _attn_ref(qb.float() / math.log2(math.e) if q_log2 else qb, kb, vb, pos0, ends)
     err = (out.float() - ref).abs().max().item()
     assert torch.isfinite(out.float()).all() and err < 3e-2, f"max err {err}"
 
@@ -192,7 +196,7 @@ def test_attention_reference_rebase_path():
     out = torch.full((n_seq, Lq, H * 64), float("nan"), device=DEV, dtype=torch.bfloat16)
     arr = (C.c_int * 10)(*[int(e) for e in ends])
     L.check(L.load().var_b200_attention(qb.data_ptr(), kb.data_ptr(), vb.data_ptr(), out.data_ptr(), n_seq, H, Lq, Lmax,
-                                        0, 10, arr, 90.0, L.current_stream()), "attention")  # bound > 43: general kernel
+                                        0, 10, arr, 90.0, 0, L.current_stream()), "attention")  # bound > 43: general kernel
     torch.cuda.synchronize()
     ref = _attn_ref(qb, kb, vb, 0, ends)
     assert torch.isfinite(out.float()).all()

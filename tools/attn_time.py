@@ -21,13 +21,16 @@ k = torch.nn.functional.normalize(torch.randn(n_seq, H, Lq, 64, device="cuda"), 
 v = torch.randn(n_seq, H, Lq, 64, device="cuda").bfloat16()
 out = torch.empty(n_seq, Lq, H * 64, device="cuda", dtype=torch.bfloat16)
 BOUND = float(os.environ.get("ATTN_BOUND", "6"))  # 0 = general kernel
+QLOG2 = int(os.environ.get("ATTN_QLOG2", "1" if BOUND > 0 else "0"))  # q pre-multiplied by log2(e)
+if QLOG2:
+    q = (q.float() * 1.4426950408889634).bfloat16()
 arr = (C.c_int * 10)(*[int(e) for e in ends])
 lib = L.load()
 
 
 def run():
     L.check(lib.var_b200_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), n_seq, H, Lq, Lq, 0, 10, arr,
-                                   BOUND, L.current_stream()))
+                                   BOUND, QLOG2, L.current_stream()))
 
 
 for _ in range(5):
@@ -39,4 +42,4 @@ for _ in range(20):
     run()
 e1.record()
 torch.cuda.synchronize()
-print(os.environ.get("VAR_B200_LIB", "default"), f"bound={BOUND} attention {e0.elapsed_time(e1) / 20 * 1e3:.1f} us per call")
+print(os.environ.get("VAR_B200_LIB", "default"), f"bound={BOUND} q_log2={QLOG2} attention {e0.elapsed_time(e1) / 20 * 1e3:.1f} us per call")

@@ -16,6 +16,7 @@ struct AttnArgs {
   int n_scales;                  // pyramid levels
   int level_end[VB_MAX_SCALES];  // cumulative token count after each level
   float max_score;               // upper bound on |q.k| if the caller knows one (the per-head scale), else 0
+  int q_log2;                    // q is pre-multiplied by log2(e) (needs 0 < max_score <= 43; bound in natural units)
 };
 
 int attn_launch(const AttnArgs& a, cudaStream_t st);

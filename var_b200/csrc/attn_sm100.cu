@@ -169,7 +169,9 @@ struct AttnItem {
 // doubles the warps per scheduler that hide the dependent-issue latency of the exp2 chain (ncu: the 4-warp kernel
 // issues one instruction per 5.7 cycles per warp, XU 44 % busy). The halves only meet at the end of an item, where
 // they exchange their partial row sums through shared memory (named barrier per row quarter).
-template <bool FAST>
+// QLOG2 (FAST only): q arrives pre-multiplied by log2(e) (the QKV epilogue folds it into the per-head scale), so the
+// scores are already base-2 exponents with |s| <= 62: P = exp2(s) straight from TMEM, no scaling FMA and no offset.
+template <bool FAST, bool QLOG2>
 __global__ void __launch_bounds__(FAST ? ATT_THREADS_FAST : ATT_THREADS, 2)
 attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
             const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, int Lq, int H, int q_pos0,
@@ -507,8 +509,11 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         // levels) lies in [-B, B], so the argument is in [-126, 0] and no clamp / maximum is needed
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
-          float2 a = __ffma2_rn(make_float2(s[i], s[i + 1]), l2e, nm);
-          float2 c2 = __ffma2_rn(make_float2(s[i + 2], s[i + 3]), l2e, nm);
+          float2 a = make_float2(s[i], s[i + 1]), c2 = make_float2(s[i + 2], s[i + 3]);
+          if constexpr (!QLOG2) {
+            a = __ffma2_rn(a, l2e, nm);
+            c2 = __ffma2_rn(c2, l2e, nm);
+          }
           a.x = ATT_EXP2(a.x); a.y = ATT_EXP2(a.y);
           if (ATT_POLY_EXP && ((i >> 2) % ATT_POLY_EXP) == 0) {
             c2 = exp2_poly2_noclamp(c2);
@@ -736,14 +741,16 @@ int attn_launch(const AttnArgs& a, cudaStream_t st) {
   }
   static bool attr_set = false;
   if (!attr_set) {
-    VB_CUDA_CHECK(cudaFuncSetAttribute(attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    VB_CUDA_CHECK(cudaFuncSetAttribute(attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    VB_CUDA_CHECK(cudaFuncSetAttribute(attn_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    VB_CUDA_CHECK(cudaFuncSetAttribute(attn_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    VB_CUDA_CHECK(cudaFuncSetAttribute(attn_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     attr_set = true;
   }
   // Bounded-score variant: needs |q.k| <= max_score with 2*max_score*log2(e) <= 126 (exp2 arguments stay normal).
   // VAR_B200_ATTN_FAST=0 forces the general kernel (measurements).
   bool fast = a.max_score > 0.f && a.max_score <= ATT_FAST_MAX_SCORE;
-  if (const char* e = getenv("VAR_B200_ATTN_FAST")) fast = fast && atoi(e) != 0;
+  VB_REQUIRE(!a.q_log2 || fast, "attn: q_log2 needs a score bound 0 < max_score <= %g (got %g)", ATT_FAST_MAX_SCORE, a.max_score);
+  if (const char* e = getenv("VAR_B200_ATTN_FAST")) fast = (fast && atoi(e) != 0) || a.q_log2;
   const int n_qt = (a.Lq + ATT_BM - 1) / ATT_BM;
   const long long total = (long long)n_qt * a.H * a.n_seq;
   VB_REQUIRE(total < (1ll << 31), "attn: too many work items");
@@ -762,13 +769,14 @@ int attn_launch(const AttnArgs& a, cudaStream_t st) {
     while (grid > 1 && grid % n_qt != 1 % n_qt) --grid;
   }
   vb::ProfScope prof_scope(vb::PK_ATTN, st);
-  if (fast)
-    attn_kernel<true><<<grid, ATT_THREADS_FAST, ATT_SMEM, st>>>(tmQ, tmK, tmV, reinterpret_cast<__nv_bfloat16*>(a.out),
-                                                                a.Lq, a.H, a.q_pos0, lv, n_qt, (int)total,
-                                                                a.max_score * 1.4426950408889634f);
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out);
+  const float mb2 = a.max_score * 1.4426950408889634f;
+  if (fast && a.q_log2)
+    attn_kernel<true, true><<<grid, ATT_THREADS_FAST, ATT_SMEM, st>>>(tmQ, tmK, tmV, o, a.Lq, a.H, a.q_pos0, lv, n_qt, (int)total, mb2);
+  else if (fast)
+    attn_kernel<true, false><<<grid, ATT_THREADS_FAST, ATT_SMEM, st>>>(tmQ, tmK, tmV, o, a.Lq, a.H, a.q_pos0, lv, n_qt, (int)total, mb2);
   else
-    attn_kernel<false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, reinterpret_cast<__nv_bfloat16*>(a.out), a.Lq,
-                                                            a.H, a.q_pos0, lv, n_qt, (int)total, 0.f);
+    attn_kernel<false, false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, o, a.Lq, a.H, a.q_pos0, lv, n_qt, (int)total, 0.f);
   VB_CUDA_CHECK(cudaGetLastError());
   vb::count_launch();
   return VB_OK;

@@ -154,6 +154,7 @@ extern "C" int var_b200_blocks(const var_b200_model_t* m, float* x, const float*
   AttnArgs at{};
   at.n_seq = n_seq; at.H = m->H; at.Lq = l; at.Lmax = Lmax; at.q_pos0 = pos0; at.n_scales = m->n_scales;
   at.max_score = m->attn_max_score;
+  at.q_log2 = m->attn_q_log2;
   level_ends(m, at.level_end);
   VB_REQUIRE(pos0 + l <= at.level_end[m->n_scales - 1], "blocks: positions beyond the pyramid");
   for (int i = 0; i < m->depth; ++i) {
@@ -240,12 +241,14 @@ extern "C" int var_b200_head_score(const var_b200_model_t* m, const float* x, co
 }
 
 extern "C" int var_b200_attention(const void* q, const void* k, const void* v, void* out, int n_seq, int H, int Lq, int Lmax,
-                                  int q_pos0, int n_scales, const int* level_end, float max_score, void* stream) {
+                                  int q_pos0, int n_scales, const int* level_end, float max_score, int q_log2,
+                                  void* stream) {
   VB_REQUIRE(level_end && n_scales > 0 && n_scales <= VAR_B200_MAX_SCALES, "attention: bad level table");
   AttnArgs a{};
   a.q = q; a.k = k; a.v = v; a.out = out; a.n_seq = n_seq; a.H = H; a.Lq = Lq; a.Lmax = Lmax; a.q_pos0 = q_pos0;
   a.n_scales = n_scales;
   a.max_score = max_score;
+  a.q_log2 = q_log2;
   for (int i = 0; i < n_scales; ++i) a.level_end[i] = level_end[i];
   return attn_launch(a, (cudaStream_t)stream);
 }

@@ -57,7 +57,7 @@ class ModelDesc(C.Structure):
         ("w_ada", C.c_void_p), ("b_ada", C.c_void_p), ("ada_rows", C.c_int), ("ada_gss", C.c_void_p),
         ("w_head", C.c_void_p), ("b_head", C.c_void_p), ("w_word", C.c_void_p), ("b_word", C.c_void_p),
         ("class_emb", C.c_void_p), ("pos_start", C.c_void_p), ("lvl_pos", C.c_void_p),
-        ("attn_max_score", C.c_float),
+        ("attn_max_score", C.c_float), ("attn_q_log2", C.c_int),
     ]
 
 
@@ -120,7 +120,7 @@ def exported_symbols():
 def _EXTRA_SIGS(vp, i32, i64, f32):
     sz, dbl = C.c_size_t, C.c_double
     return {
-        "var_b200_attention": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, C.POINTER(C.c_int), f32, vp],
+        "var_b200_attention": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, C.POINTER(C.c_int), f32, i32, vp],
         "var_b200_ln_modulate": [vp, vp, vp, i32, i32, vp, i32, i32, f32, vp],
         "var_b200_quant_encode": [C.POINTER(QuantDesc), vp, i32, vp, vp, vp, sz, i32, vp],
         "var_b200_quant_decode": [C.POINTER(QuantDesc), vp, i32, vp, vp, vp, vp],

@@ -497,12 +497,19 @@ class PackedModel:
         f32 = lambda t: t.detach().float().contiguous()
         keep: List[torch.Tensor] = []
         self.blocks_arr = (L.BlockWeights * depth)()
+        # |q.k| <= per-head scale exp(min(scale_mul, ln 100)) (basic_var.py:101-105), a model constant: with the largest
+        # one <= 43 the attention kernel runs its bounded-score variant, and log2(e) is folded into q_scale so that the
+        # scores leave the tensor core as base-2 exponents (one host read at pack time)
+        max_score = float(torch.stack([b.attn.scale_mul_1H11.detach().clamp_max(b.attn.max_scale_mul).exp().max()
+                                       for b in var.blocks]).max().item())
+        q_log2 = 0.0 < max_score <= 43.0
+        q_mul = math.log2(math.e) if q_log2 else 1.0
         for i, b in enumerate(var.blocks):
             a = b.attn
             ts = dict(
                 w_qkv=bf(a.mat_qkv.weight),
                 b_qkv=f32(torch.cat((a.q_bias, torch.zeros_like(a.q_bias), a.v_bias))),
-                q_scale=f32(a.scale_mul_1H11.clamp_max(a.max_scale_mul).exp().reshape(-1)),
+                q_scale=f32(a.scale_mul_1H11.clamp_max(a.max_scale_mul).exp().reshape(-1) * q_mul),
                 w_proj=bf(a.proj.weight), b_proj=f32(a.proj.bias),
                 w_fc1=bf(b.ffn.fc1.weight), b_fc1=f32(b.ffn.fc1.bias),
                 w_fc2=bf(b.ffn.fc2.weight), b_fc2=f32(b.ffn.fc2.bias))
@@ -531,9 +538,7 @@ class PackedModel:
             setattr(m, k, v.data_ptr())
             keep.append(v)
         m.ada_rows = w_ada.shape[0]
-        # |q.k| <= per-head scale (basic_var.py:101-105): lets the attention kernel use a fixed softmax reference
-        m.attn_max_score = float(torch.stack([b.attn.scale_mul_1H11.detach().clamp_max(b.attn.max_scale_mul).exp().max()
-                                              for b in var.blocks]).max().item())  # one host read at pack time
+        m.attn_max_score, m.attn_q_log2 = max_score, int(q_log2)
         m.ada_gss = gss.data_ptr() if gss is not None else None
         if gss is not None:
             keep.append(gss)
