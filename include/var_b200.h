@@ -60,6 +60,7 @@ enum {
   VAR_B200_EPI_SCORE = 5       /* per-row partial log-sum-exp and ground-truth logit eval_prob.py:446-452 */
 };
 
+#define VAR_B200_GEMM_EPI_PARTS 2
 typedef struct var_b200_gemm_args {
   const void* A; /* [M,K] bf16 row-major */
   const void* W; /* [N,K] bf16 row-major (nn.Linear weight) */
@@ -82,7 +83,8 @@ typedef struct var_b200_gemm_args {
   /* SCORE */
   const int32_t* gt; /* row m uses gt[m % gt_mod] */
   int gt_mod;        /* 0 = M */
-  float* part;       /* [M, 2*ceil(N / var_b200_gemm_tile_n(N)), 2]: (max, sumexp) per row, tile and epilogue half */
+  float* part;       /* [M, VAR_B200_GEMM_EPI_PARTS*ceil(N / var_b200_gemm_tile_n(N)), 2]: (max, sumexp) per row, tile and
+                        epilogue warp of the row's lane quarter */
   float* gt_logit;   /* [M] */
 } var_b200_gemm_args_t;
 

@@ -125,7 +125,7 @@ def test_gemm_score_partials():
     gt = torch.randint(0, N, (M,), device="cuda", dtype=torch.int32)
     bn = L.load().var_b200_gemm_tile_n(N)
     nt = (N + bn - 1) // bn
-    part = torch.zeros(M, 2 * nt, 2, device="cuda")
+    part = torch.zeros(M, L.GEMM_EPI_PARTS * nt, 2, device="cuda")
     gl = torch.zeros(M, device="cuda")
     _gemm(A, W, L.EPI_SCORE, bias=bias, gt=gt, part=part, gt_logit=gl)
     logits = _ref(A, W) + bias

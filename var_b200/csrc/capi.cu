@@ -72,7 +72,7 @@ BlockWs carve_blocks(const var_b200_model_t* m, int n_seq, int l, void* work, si
   w.h = cv.take(M * 4 * C * 2);    // FFN hidden (bf16)
   if (score) {
     const int nt = (m->V + gemm_pick_bn(m->V) - 1) / gemm_pick_bn(m->V);
-    w.part = cv.take(M * nt * 2 * 8);  // one (max, sumexp) per row, tile and epilogue half
+    w.part = cv.take(M * nt * GEMM_EPI_SUB * 8);  // one (max, sumexp) per row, tile and epilogue sub-warp
     w.gtl = cv.take(M * 4);
   }
   w.bytes = cv.off;
@@ -236,7 +236,7 @@ extern "C" int var_b200_head_score(const var_b200_model_t* m, const float* x, co
   int ends[VAR_B200_MAX_SCALES];
   level_ends(m, ends);
   const int bn = gemm_pick_bn(m->V);
-  return score_finalize(w.part, 2 * ((m->V + bn - 1) / bn), reinterpret_cast<float*>(w.gtl), n_seq, l, m->n_scales, ends,
+  return score_finalize(w.part, GEMM_EPI_SUB * ((m->V + bn - 1) / bn), reinterpret_cast<float*>(w.gtl), n_seq, l, m->n_scales, ends,
                         tok_logp, per_scale, scores, first_pos, st);
 }
 

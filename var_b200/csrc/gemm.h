@@ -5,6 +5,12 @@
 
 namespace vb {
 
+// Epilogue warps per TMEM lane quarter: the 32-column chunks of a tile are dealt round-robin to them (EPI_SCORE also
+// writes one partial per row, tile and such warp). 2 -> eight epilogue warps, 320 threads. Three (twelve warps) was
+// measured in a same-box A/B inside both bench steps: d30 sampling 274.5 vs 276.6 img/s, d16 scoring 3.03 vs 3.06 (the
+// 64-column QKV chunks deal unevenly over three warps), although the GELU epilogue alone gains 2-3 %.
+constexpr int GEMM_EPI_SUB = 2;
+
 enum EpiMode : int {
   EPI_BIAS_F32 = 0,    // out fp32 = acc + bias                                  (head: models/var.py:124)
   EPI_BIAS_BF16 = 1,   // out bf16 = acc + bias
@@ -32,7 +38,7 @@ struct GemmParams {
   // EPI_SCORE
   const int* gt;    // ground-truth token of row m = gt[m % gt_mod]
   int gt_mod;
-  float2* part;     // [M, 2*n_tiles] (max, sum exp(x - max)) per row, tile and epilogue half
+  float2* part;     // [M, GEMM_EPI_SUB*n_tiles] (max, sum exp(x - max)) per row, tile and epilogue sub-warp
   float* gt_logit;  // [M]
   // EPI_BIAS_BF16: optional bf16 [M,N] added to the rounded result (ResnetBlock shortcut, models/basic_vae.py:60)
   const __nv_bfloat16* resid_bf16;

@@ -7,7 +7,7 @@
 //     kernel is capped near 60 % tensor-active by that ingress, profiles/r01_gemm_1cta_ncu.txt)
 //   * accumulators are double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps
 //     the main loop of tile i+1
-//   * eight epilogue warps read TMEM with tcgen05.ld (one accumulator row per thread) and apply the
+//   * eight epilogue warps (4 * GEMM_EPI_SUB) read TMEM with tcgen05.ld (one accumulator row per thread) and apply the
 //     fused epilogue of the VAR block (reference semantics cited per mode in gemm.h)
 #pragma once
 #include "common.cuh"
@@ -17,7 +17,8 @@ namespace vb {
 
 constexpr int GEMM_BM = 128;        // accumulator rows per CTA (TMEM lanes)
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 320;   // warp0: TMA, warp1: MMA + TMEM owner, warps 2-9: epilogue
+constexpr int GEMM_EPI_WARPS = 4 * GEMM_EPI_SUB;
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;   // warp0: TMA, warp1: MMA + TMEM owner, then the epilogue warps
 constexpr int EPI_STG_LD = 20;      // floats per staging row (16 + 4 pad: 16-byte aligned)
 
 template <int BN, int CTAS>
@@ -25,7 +26,7 @@ struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = (BN / CTAS) * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STG_BYTES = 8 * 32 * EPI_STG_LD * 4;  // epilogue staging, one 32x20 fp32 tile per warp
+  static constexpr int STG_BYTES = GEMM_EPI_WARPS * 32 * EPI_STG_LD * 4;  // epilogue staging, one 32x20 fp32 tile per warp
   static constexpr int BUDGET = 232448 - 2048 - STG_BYTES;  // 227 KB per CTA minus alignment slack / static smem
   static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024;  // +1024: manual alignment slack
@@ -66,7 +67,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 8 * CTAS);  // one arrive per epilogue warp of every CTA of the pair
+      mbar_init(tempty_bar(s), GEMM_EPI_WARPS * CTAS);  // one arrive per epilogue warp of every CTA of the pair
     }
     mbar_fence_init();
   }
@@ -158,11 +159,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // ------------------------------ epilogue warps ------------------------------
-    // Eight warps: two per TMEM lane quarter, interleaving the column chunks of the tile between them, so that the
-    // epilogue (which is ALU/latency bound: one accumulator row per thread) keeps up with the 8192-cycle main loop
-    // of a K=1024 tile.
+    // GEMM_EPI_SUB warps per TMEM lane quarter, dealing the column chunks of the tile round-robin between them. The
+    // epilogue is latency bound (one accumulator row per thread): the GELU epilogue costs a K=1024 tile 14 % (d16 fc1:
+    // 1206 TFLOP/s against 1408 with the plain bias epilogue, tools/gemm_k_sweep.py); a third warp per quarter wins
+    // back only 2-3 % of that and loses it again in the QKV epilogue (see gemm.h).
     const int quarter = warp & 3;          // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;      // which interleaved half of the column chunks
+    const int half = (warp - 2) >> 2;      // which of the GEMM_EPI_SUB warps of that quarter (chunk c = half, half+SUB, ..)
     int it = 0;
     for (int tile = cid; tile < total_tiles; tile += ncl, ++it) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
@@ -191,7 +193,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           kv_off[i] = ((size_t)sq * p.H * p.Lmax + p.pos0 + tt) * 64;
         }
 #pragma unroll 1
-        for (int c = half; c < BN / 64; c += 2) {
+        for (int c = half; c < BN / 64; c += GEMM_EPI_SUB) {
           const int n0 = n_base + c * 64;
           if (n0 >= p.N) break;
           float v[64];
@@ -250,7 +252,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         float run_max = -INFINITY, run_sum = 0.f;
         const int gt = row_ok ? __ldg(p.gt + (row % p.gt_mod)) : -1;
 #pragma unroll 1
-        for (int c = half; c < BN / 32; c += 2) {
+        for (int c = half; c < BN / 32; c += GEMM_EPI_SUB) {
           const int n0 = n_base + c * 32;
           if (n0 >= p.N) break;
           float v[32];
@@ -276,8 +278,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           run_sum = run_sum * __expf(run_max - new_max) + sacc;
           run_max = new_max;
         }
-        // one partial per (row, tile, half); an empty half contributes (-inf, 0)
-        if (row_ok) p.part[((size_t)row * n_tiles + n_blk) * 2 + half] = make_float2(run_max, run_sum);
+        // one partial per (row, tile, sub-warp); an empty share contributes (-inf, 0)
+        if (row_ok) p.part[((size_t)row * n_tiles + n_blk) * GEMM_EPI_SUB + half] = make_float2(run_max, run_sum);
       } else if constexpr (EPI == EPI_GATE_RESID) {
         // Residual update needs coalesced reads of resid/gate: transpose 32x16 accumulator pieces through a private
         // smem tile so that each warp instruction touches 8 rows x 64 contiguous bytes. (Issuing the residual reads a
@@ -287,7 +289,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < 4; ++i) seqs[i] = (row_w0 + rsub + 8 * i) / p.rows_per_seq;
 #pragma unroll 1
-        for (int c = half; c < BN / 32; c += 2) {
+        for (int c = half; c < BN / 32; c += GEMM_EPI_SUB) {
           const int n0 = n_base + c * 32;
           if (n0 >= p.N) break;
           float v[32];
@@ -329,12 +331,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       } else {
         // software-pipelined: the TMEM load of chunk i+1 is in flight while chunk i is converted and stored
-        constexpr int NCH = (BN / 32 + 1) / 2;  // chunks per warp (interleaved with the sibling warp)
+        constexpr int NCH = (BN / 32 + GEMM_EPI_SUB - 1) / GEMM_EPI_SUB;  // chunks per warp (dealt round-robin)
         float vbuf[2][32];
         int n_valid = 0;
 #pragma unroll
         for (int i = 0; i < NCH; ++i)
-          if ((half + 2 * i) * 32 < BN && n_base + (half + 2 * i) * 32 < p.N) n_valid = i + 1;
+          if ((half + GEMM_EPI_SUB * i) * 32 < BN && n_base + (half + GEMM_EPI_SUB * i) * 32 < p.N) n_valid = i + 1;
         if (n_valid > 0) {
           __syncwarp();
           tmem_ld_32x32(taddr + half * 32, vbuf[0]);
@@ -343,11 +345,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int i = 0; i < NCH; ++i) {
           if (i >= n_valid) break;
           float* v = vbuf[i & 1];
-          const int n0 = n_base + (half + 2 * i) * 32;
+          const int n0 = n_base + (half + GEMM_EPI_SUB * i) * 32;
           tmem_ld_wait_dep(v);
           if (i + 1 < n_valid) {
             __syncwarp();
-            tmem_ld_32x32(taddr + (half + 2 * (i + 1)) * 32, vbuf[(i + 1) & 1]);
+            tmem_ld_32x32(taddr + (half + GEMM_EPI_SUB * (i + 1)) * 32, vbuf[(i + 1) & 1]);
           }
           if (p.bias != nullptr) {
 #pragma unroll

@@ -8,10 +8,15 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-_LIB_PATH = Path(__file__).resolve().parent / "libvar_b200.so"
+import os
+
+# VAR_B200_LIB: a variant build of the same library (developer A/B measurements); default = the in-tree build
+_LIB_PATH = Path(os.environ["VAR_B200_LIB"]).resolve() if os.environ.get("VAR_B200_LIB") else \
+    Path(__file__).resolve().parent / "libvar_b200.so"
 _lib = None
 
 EPI_BIAS_F32, EPI_BIAS_BF16, EPI_GELU_BF16, EPI_GATE_RESID, EPI_QKV, EPI_SCORE = range(6)
+GEMM_EPI_PARTS = 2  # VAR_B200_GEMM_EPI_PARTS: EPI_SCORE partials per row and tile
 
 
 class VarB200Error(RuntimeError):
