@@ -207,6 +207,16 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Arrive without release semantics: for hand-offs whose payload is not generic-proxy memory (a TMEM accumulator stage
+// whose tcgen05.ld results are already in registers, ordered by tcgen05.fence::before_thread_sync). A releasing arrive
+// makes the warp sit out all of its outstanding global stores first (MEMBAR + ERRBAR: 18 % of all warp samples of the
+// GEMM epilogue warps, profiles/r01_ncu_gemm_d16_fc1_epilogue.txt).
+__device__ __forceinline__ void mbar_arrive_relaxed_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_relaxed(uint32_t bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 // TMA load into this CTA's smem whose completion bytes are credited to an mbarrier that may live in the peer CTA
 __device__ __forceinline__ void tma_load_4d(const CUtensorMap* tm, uint32_t bar, uint32_t dst, int c0, int c1, int c2,
                                             int c3) {

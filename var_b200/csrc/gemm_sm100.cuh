@@ -203,12 +203,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int which = n0 / p.C;  // 0 q, 1 k, 2 v
           const int head = (n0 - which * p.C) >> 6;
           const float qs = which == 0 ? __ldg(p.q_scale + head) : 1.f;
+          float4 bq[16];  // the chunk's bias, requested while the accumulator is still on its way from TMEM
+#pragma unroll
+          for (int j = 0; j < 16; ++j) bq[j] = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j);
           tmem_ld_wait_dep(v);
           tmem_ld_wait_dep(v + 32);
           float2 ss2 = make_float2(0.f, 0.f);
 #pragma unroll
           for (int j = 0; j < 64; j += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+            const float4 b = bq[j >> 2];
             const float2 a0 = __fadd2_rn(make_float2(v[j], v[j + 1]), make_float2(b.x, b.y));
             const float2 a1 = __fadd2_rn(make_float2(v[j + 2], v[j + 3]), make_float2(b.z, b.w));
             ss2 = __ffma2_rn(a0, a0, ss2);
@@ -333,13 +336,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // software-pipelined: the TMEM load of chunk i+1 is in flight while chunk i is converted and stored
         constexpr int NCH = (BN / 32 + GEMM_EPI_SUB - 1) / GEMM_EPI_SUB;  // chunks per warp (dealt round-robin)
         float vbuf[2][32];
+        float4 bbuf[2][8];  // bias of the chunk, fetched one chunk ahead like the accumulator (its latency was the
+                            // largest long-scoreboard stall of the epilogue warps)
         int n_valid = 0;
 #pragma unroll
         for (int i = 0; i < NCH; ++i)
           if ((half + GEMM_EPI_SUB * i) * 32 < BN && n_base + (half + GEMM_EPI_SUB * i) * 32 < p.N) n_valid = i + 1;
+        const bool has_bias = p.bias != nullptr;
         if (n_valid > 0) {
           __syncwarp();
           tmem_ld_32x32(taddr + half * 32, vbuf[0]);
+          if (has_bias) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bbuf[0][j] = __ldg(reinterpret_cast<const float4*>(p.bias + n_base + half * 32) + j);
+          }
         }
 #pragma unroll
         for (int i = 0; i < NCH; ++i) {
@@ -350,12 +360,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (i + 1 < n_valid) {
             __syncwarp();
             tmem_ld_32x32(taddr + (half + GEMM_EPI_SUB * (i + 1)) * 32, vbuf[(i + 1) & 1]);
-          }
-          if (p.bias != nullptr) {
+            if (has_bias) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+              for (int j = 0; j < 8; ++j)
+                bbuf[(i + 1) & 1][j] = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + GEMM_EPI_SUB * 32) + j);
+            }
+          }
+          if (has_bias) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = bbuf[i & 1][j];
+              v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
             }
           }
           if (!row_ok) {
@@ -413,8 +428,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if constexpr (CTAS == 2) mbar_arrive_cluster(mapa_shared(tempty_bar(as), 0));  // the leader CTA's MMA thread waits
-        else mbar_arrive(tempty_bar(as));
+        // relaxed: the accumulator values are in registers already; do not wait for this tile's global stores
+        if constexpr (CTAS == 2) mbar_arrive_relaxed_cluster(mapa_shared(tempty_bar(as), 0));  // the leader CTA's MMA thread waits
+        else mbar_arrive_relaxed(tempty_bar(as));
       }
     }
   }
