@@ -46,6 +46,7 @@ def test_umma_probe(N, b_mn):
     (128, 256, 64, 0), (128, 256, 256, 0), (300, 1024, 1024, 0), (5440, 3072, 1024, 0),
     (680, 1920, 1920, 0), (680, 1920, 1920, 128), (1000, 4096, 1024, 256), (257, 5760, 1920, 0),
     (4096, 7680, 1920, 0), (128, 1024, 4096, 128),
+    (700, 1920, 1920, 256), (300, 2080, 512, 256), (300, 352, 256, 0), (129, 160, 128, 128),  # narrow last N tiles: 128 / 32 / 160 / 32 wide
     # the same shapes through the 1-CTA kernel (bit 16 of force_bn)
     (300, 1024, 1024, 0x10000 | 256), (680, 1920, 1920, 0x10000 | 192), (1000, 4096, 1024, 0x10000 | 128),
     (129, 256, 64, 0), (257, 256, 128, 0), (7000, 3072, 1024, 0),
