@@ -7,17 +7,19 @@
 // largest level end among its 128 query rows and masks per row inside the last tiles. The KV-cached decode step
 // (attn_bias=None, keys = all cached + current scale) is the same kernel with every query on the newest level.
 //
-// One CTA = 128 query rows of one (sequence, head). Warps 0-3: softmax (one row per thread == one TMEM lane),
-// warp 4: TMA producer + UMMA issuer (one elected thread). (An 8-warp variant that split the keys of a tile between
-// warp pairs measured no faster: the kernel is bound by the per-tile issue/commit/mbarrier round trips.)
-//   S_j = Q K_j^T : UMMA 128x64x16 x4, Q and K tiles K-major SW128 in smem, S double-buffered in TMEM [0,64),[64,128)
-//   P_j = exp2(..): registers -> bf16 -> TMEM, overwriting the first 32 columns of S_j (tcgen05.st); the second MMA
-//                   takes its A operand straight from tensor memory (no smem round trip, no proxy fence)
+// Persistent CTAs (2 per SM); work item = 128 query rows of one (sequence, head). Warp roles: softmax warps (thread
+// = query row = TMEM lane), one TMA producer warp, and the UMMA issuer(s) (warp-uniform loops, one elected lane issues).
+//   S_j = Q K_j^T : UMMA 128x64x16 x4, Q and K tiles K-major SW128 in smem, S triple-buffered in TMEM [0,192)
+//   P_j = exp2(..): registers -> bf16 -> TMEM, overwriting columns of S_j (tcgen05.st); the second MMA takes its A
+//                   operand straight from tensor memory (no smem round trip, no proxy fence)
 //   O  += P_j V_j : UMMA(TS) 128x64x16 x4, V tile in its natural [key, d] layout = MN-major B operand, TMEM [192,256)
-// The output accumulates in TMEM across key tiles against a per-row reference maximum fixed at the first tile
-// (q_hat.k_hat is bounded by the per-head scale <= 100, basic_var.py:101): softmax warps never wait for P V and the
-// tensor pipe runs QK_{j+1} under softmax_j. If a later tile exceeds the reference by more than 2^80 (only possible
-// for scales > 27) the accumulator is rescaled in TMEM (tcgen05.ld / st), which is exact like the usual recurrence.
+// Two variants of the softmax (template parameter FAST, see attn_kernel):
+//   general  - 4 softmax warps; the output accumulates against a per-row reference maximum fixed at the first key tile
+//              (q_hat.k_hat is bounded by the per-head scale <= 100, basic_var.py:101). If a later tile exceeds the
+//              reference by more than 2^80 (only possible for scales > 27) the accumulator is rescaled in TMEM
+//              (tcgen05.ld / st), which is exact like the usual online-softmax recurrence.
+//   bounded  - the caller passes the bound B <= 43 on |q.k|: fixed reference, no maximum, no rescale; 8 softmax warps
+//              split every key tile, separate QK and P V issuer warps; optionally q pre-multiplied by log2(e).
 #include <stdlib.h>
 
 #include "attn.h"
