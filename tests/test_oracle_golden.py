@@ -32,6 +32,39 @@ def test_capi_exports_every_declared_symbol():
     assert lib.var_b200_gemm_tile_n(1920) == 192 and lib.var_b200_gemm_tile_n(4096) == 256
 
 
+def test_header_constants_and_struct_layouts_match_the_binding():
+    """The ctypes mirror must agree with include/var_b200.h and the kernels: constants, field order of the structs."""
+    import ctypes as C
+    import re
+    from pathlib import Path
+    from var_b200 import lib as L
+    root = Path(__file__).resolve().parent.parent
+    hdr = (root / "include" / "var_b200.h").read_text()
+    gemm_h = (root / "var_b200" / "csrc" / "gemm.h").read_text()
+    assert int(re.search(r"#define VAR_B200_GEMM_EPI_PARTS (\d+)", hdr).group(1)) == L.GEMM_EPI_PARTS
+    assert int(re.search(r"constexpr int GEMM_EPI_SUB = (\d+);", gemm_h).group(1)) == L.GEMM_EPI_PARTS
+    assert int(re.search(r"#define VAR_B200_MAX_SCALES (\d+)", hdr).group(1)) == L.MAX_SCALES
+
+    def fields_of(struct_name):
+        body = re.search(r"typedef struct " + struct_name + r" \{(.*?)\} ", hdr, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            for part in decl.split(","):
+                names.append(re.search(r"(\w+)\s*(\[[^\]]*\])?\s*$", part.strip()).group(1))
+        return names
+
+    assert fields_of("var_b200_gemm_args") == [f[0] for f in L.GemmArgs._fields_]
+    assert fields_of("var_b200_model") == [f[0] for f in L.ModelDesc._fields_]
+    assert fields_of("var_b200_quant") == [f[0] for f in L.QuantDesc._fields_]
+    assert fields_of("var_b200_block_weights") == [f[0] for f in L.BlockWeights._fields_]
+    # the attention entry point takes (.., level_end, max_score, q_log2, stream)
+    assert L.load().var_b200_attention.argtypes[-3:] == [C.c_float, C.c_int, C.c_void_p]
+
+
 def test_quant_oracle_indices_match_reference_golden():
     g = golden("quant_forward_d2.npz")
     vae, _ = seeded_models()

@@ -10,9 +10,6 @@ import torch
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from var_b200 import lib as L  # noqa: E402
 
-if os.environ.get("VAR_B200_LIB"):  # a variant build of the library (measurement experiments)
-    L._LIB_PATH = Path(os.environ["VAR_B200_LIB"]).resolve()
-
 PN = (1, 2, 3, 4, 5, 6, 8, 10, 13, 16)
 ends = list(np.cumsum([p * p for p in PN]))
 n_seq, H, Lq = 125, 16, 680

@@ -6,9 +6,8 @@ shared object is missing, `load()` raises with the build command.
 from __future__ import annotations
 
 import ctypes as C
-from pathlib import Path
-
 import os
+from pathlib import Path
 
 # VAR_B200_LIB: a variant build of the same library (developer A/B measurements); default = the in-tree build
 _LIB_PATH = Path(os.environ["VAR_B200_LIB"]).resolve() if os.environ.get("VAR_B200_LIB") else \
