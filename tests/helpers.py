@@ -79,3 +79,15 @@ def replay_noise(seed: int, B: int, V: int = 4096, patch_nums=PATCH_NUMS, device
     g = torch.Generator(device=device).manual_seed(seed)
     return [None if si in skip_scales else torch.empty(B * pn * pn, V, device=device).exponential_(1, generator=g)
             for si, pn in enumerate(patch_nums)]
+
+
+def embed_inputs(B: int = 2, seed: int = 5, patch_nums=PATCH_NUMS):
+    """Arbitrary per-scale maps for embed_to_fhat (shared by oracle/gen_golden_embed.py and the tests)."""
+    g = torch.Generator().manual_seed(seed)
+    return [torch.randn(B, 32, p, p, generator=g) for p in patch_nums]
+
+
+def logits_inputs(C: int, B: int = 2, l: int = 9, seed: int = 6):
+    """(h [B,l,C], labels) for get_logits (shared by oracle/gen_golden_embed.py and the tests)."""
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(B, l, C, generator=g), torch.tensor([7, 1000])

@@ -220,3 +220,25 @@ def test_more_smooth_oracle_matches_reference_golden():
                       g_noise=gs, codebook=vae.quantize.embedding.weight.detach())
     err = (out["f_hat"] - torch.from_numpy(g["f_hat"])).abs().max().item()
     assert err < 2e-3 * float(np.abs(g["f_hat"]).max()), err
+
+
+def test_embed_to_fhat_and_get_logits_oracle_match_reference_golden():
+    """quant.py:107-121 on arbitrary per-scale maps and var.py:118-124, against outputs of the imported reference
+    (oracle/gen_golden_embed.py; same seeded inputs from helpers.py)."""
+    from helpers import embed_inputs, logits_inputs
+    g = golden("embed_get_logits_d2.npz")
+    vae, var = seeded_models(depth=2)
+    qo = quant_oracle_of(vae)
+    hs = [h.numpy() for h in embed_inputs()]
+    f_hat = np.zeros((2, 32, 16, 16), np.float32)
+    for si in range(10):
+        qo.get_next_autoregressive_input(si, f_hat, None, h=hs[si])
+        if si == 3:
+            assert np.abs(f_hat - g["fhat_s3"]).max() < 2e-5
+        if si == 8:
+            assert np.abs(f_hat[:, ::4] - g["fhat_s8_sub"]).max() < 2e-5
+    assert np.abs(f_hat - g["fhat_last"]).max() < 2e-5
+    h, labels = logits_inputs(var.C)
+    sd = sd_cpu(var)
+    logits = VO.get_logits(sd, var_cfg_of(var), h, sd["class_emb.weight"][labels])
+    assert (logits[:, :, ::8] - torch.from_numpy(g["logits_sub"])).abs().max().item() < 5e-4

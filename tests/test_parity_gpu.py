@@ -104,6 +104,28 @@ def test_embed_to_fhat_arbitrary_maps_bit_exact():
     assert imgs.shape == (2, 3, 256, 256) and float(imgs.abs().max()) <= 1.0
 
 
+def test_embed_to_fhat_and_get_logits_match_reference_golden():
+    """The kernels against outputs of the imported reference (oracle/gen_golden_embed.py): embed_to_fhat on arbitrary maps
+    within fp32 rounding of the reference (2e-5) and bit-identical to the C oracle; get_logits within the logit tolerance."""
+    from helpers import embed_inputs, logits_inputs
+    g = golden("embed_get_logits_d2.npz")
+    vae, var = seeded_models(device=DEV)
+    hs = embed_inputs()
+    fl = vae.quantize.embed_to_fhat([h.to(DEV) for h in hs], all_to_max_scale=True, last_one=False)
+    assert (fl[-1].cpu() - torch.from_numpy(g["fhat_last"])).abs().max().item() < 2e-5
+    assert (fl[3].cpu() - torch.from_numpy(g["fhat_s3"])).abs().max().item() < 2e-5
+    assert (fl[8][:, ::4].cpu() - torch.from_numpy(g["fhat_s8_sub"])).abs().max().item() < 2e-5
+    qo = quant_oracle_of(vae)
+    f_ref = np.zeros((2, 32, 16, 16), np.float32)
+    for si in range(10):
+        qo.get_next_autoregressive_input(si, f_ref, None, h=hs[si].numpy())
+    assert np.array_equal(fl[-1].cpu().numpy(), f_ref)
+    h, labels = logits_inputs(var.C)
+    got = var.get_logits(h.to(DEV), var.class_emb(labels.to(DEV)))
+    err = (got[:, :, ::8].cpu() - torch.from_numpy(g["logits_sub"])).abs().max().item()
+    assert err < 6e-2, f"get_logits max-abs err {err} vs the reference"  # LOGIT_TOL: bf16 GEMM operands vs fp32 reference
+
+
 def test_get_logits_matches_forward_head():
     """VAR.get_logits(h, cond_BD) (var.py:118-124) == the head of VAR.forward on the same final activations."""
     _, var = seeded_models(device=DEV)
