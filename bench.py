@@ -279,7 +279,7 @@ def main():
 
         img_host = torch.empty((B, 3, 256, 256), dtype=torch.float32).pin_memory()
 
-        vae.decoder_dtype = torch.bfloat16  # CNN decoder (cuDNN boundary helper) in bf16, as the reference's autocast runs it
+        vae.decoder_dtype = torch.bfloat16  # CNN decoder as the 16-bit NHWC plan (own tcgen05 convolutions + GroupNorm glue)
 
         def step_e2e():  # public API: host labels in, images out
             lab = labels_host.to(dev, non_blocking=True)
@@ -383,7 +383,7 @@ def main():
                 vs_baseline=None, dtype="bf16", data="synthetic (random labels/images, seeded dense random-init weights)",
                 config=wl["config"], clocks=clk,
                 e2e=dict(value=value_e2e, unit="images/sec", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                         note="public API call incl. CNN decoder (cuDNN, bf16 autocast) and host copies"),
+                         note="public API call with host buffers: pinned H2D of the inputs, the whole call (sampling: incl. the bf16 NHWC CNN decoder on the tcgen05 implicit-GEMM convolutions), D2H of the result"),
                 gpu_launches=int(launches), roofline=roofline)
 
     if rank == 0 and world == 1 and not args.no_secondary and args.workload == "sample_d30":
