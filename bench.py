@@ -9,6 +9,7 @@ One "step" = one pass of the hot path over one batch of synthetic input:
   score_d16  (configs[3]): VAR-d16 1000-class likelihood scoring of one image per step per GPU... (classes sharded
               over the ranks with one all-gather when N > 1). Metric: images/sec.
   sample_d16 (configs[2]): VAR-d16 sampling, B=64.
+  sample_d36_512: the 512 px variant (2240-token pyramid, d36 with shared adaLN), B=32; GPU arm only.
 The JSON line carries `value` (device-timed, inputs resident, to f_hat), `e2e` (public API with host labels in, images
 out, CNN decoder under bf16 autocast), `roofline` (dominant kernel = the tcgen05 GEMM, timed live at the step's
 largest shape), `cpu_baseline` (the oracle port on this box's host cores, bounded sample) and `secondary` (the other
@@ -32,19 +33,21 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 PATCH_NUMS = (1, 2, 3, 4, 5, 6, 8, 10, 13, 16)
+PATCH_NUMS_512 = (1, 2, 3, 4, 6, 9, 13, 18, 24, 32)  # utils/arg_util.py:246-247
 L_SEQ = sum(p * p for p in PATCH_NUMS)
 V, CVAE = 4096, 32
 
 
-def flops_per_seq(depth: int) -> float:
-    """Algorithmic FLOPs of one 680-token sequence; attention counted on visible pairs only."""
+def flops_per_seq(depth: int, patch_nums=PATCH_NUMS) -> float:
+    """Algorithmic FLOPs of one token-pyramid sequence; attention counted on visible pairs only."""
     C = 64 * depth
     vis, cum = 0, 0
-    for p in PATCH_NUMS:
+    for p in patch_nums:
         cum += p * p
         vis += p * p * cum
-    return (24 * C * C * depth * L_SEQ + 4 * C * depth * vis + 2 * C * V * L_SEQ + (12 * C * C * depth + 4 * C * C)
-            + 2 * CVAE * C * (L_SEQ - 1))
+    L = cum
+    return (24 * C * C * depth * L + 4 * C * depth * vis + 2 * C * V * L + (12 * C * C * depth + 4 * C * C)
+            + 2 * CVAE * C * (L - 1))
 
 
 def peaks():
@@ -208,7 +211,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="var_b200")
-    ap.add_argument("--workload", default="sample_d30", choices=["sample_d30", "sample_d16", "score_d16"])
+    ap.add_argument("--workload", default="sample_d30", choices=["sample_d30", "sample_d16", "score_d16", "sample_d36_512"])
     ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (sampling) / classes (scoring)")
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -221,18 +224,27 @@ def main():
                         metric="images/sec: VAR-d16 256px CFG sampling (autoregressive_infer_cfg, cfg=1.5, top_k=900)"),
         score_d16=dict(kind="score", depth=16, batch=1000,
                        metric="images/sec: VAR-d16 1000-class likelihood scoring (eval_prob bayesian)"),
+        # the 512 px variant: 2240-token pyramid, d36 with shared adaLN (GPU arm only)
+        sample_d36_512=dict(kind="sample", depth=36, batch=32, px=512, patch_nums=PATCH_NUMS_512, shared_aln=True,
+                            metric="images/sec: VAR-d36 512px CFG sampling (autoregressive_infer_cfg, cfg=1.5, top_k=900)"),
     )[args.workload]
+    pns = wl.get("patch_nums", PATCH_NUMS)
+    px = wl.get("px", 256)
+    L_wl = sum(p * p for p in pns)
     if args.batch:
         wl["batch"] = args.batch
     # sampling: per-GPU batch fixed (weak); scoring: the 1000 classes of one image are split over the ranks (strong)
     wl["scaling"] = "weak" if wl["kind"] == "sample" else "strong"
-    wl["config"] = dict(workload=args.workload, depth=wl["depth"], px=256, tokens=L_SEQ,
+    wl["config"] = dict(workload=args.workload, depth=wl["depth"], px=px, tokens=L_wl,
                         per_gpu_batch=wl["batch"] if wl["kind"] == "sample" else 1,
                         classes=1000 if wl["kind"] == "score" else None,
                         sampler="cfg=1.5,top_k=900,top_p=0" if wl["kind"] == "sample" else None,
                         l2="activations per step >> 126 MB L2 (inputs larger than L2)", parallelism=f"dp{args.gpus}")
 
     if args.impl == "reference":
+        if px != 256:
+            print(json.dumps(dict(impl="reference", unavailable="the CPU arm is built for the 256 px headline workloads")))
+            return
         run_reference_arm(args, wl)
         return
 
@@ -262,8 +274,8 @@ def main():
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         return float(t.item())
 
-    def build(depth):
-        vae, var = build_vae_var(dev, depth=depth)
+    def build(depth, **kw):
+        vae, var = build_vae_var(dev, depth=depth, **kw)
         dense_init_(var, seed=2)
         dense_init_(vae, seed=1)
         var.eval(); vae.eval(); var.cond_drop_rate = 0
@@ -277,7 +289,7 @@ def main():
         def step_hot():  # inputs resident, hot path to f_hat
             var.autoregressive_infer_cfg(B, labels_dev, g_seed=0, cfg=1.5, top_k=900, top_p=0.0, decode=False)
 
-        img_host = torch.empty((B, 3, 256, 256), dtype=torch.float32).pin_memory()
+        img_host = torch.empty((B, 3, px, px), dtype=torch.float32).pin_memory()
 
         vae.decoder_dtype = torch.bfloat16  # CNN decoder as the 16-bit NHWC plan (own tcgen05 convolutions + GroupNorm glue)
 
@@ -287,7 +299,7 @@ def main():
             img_host.copy_(img, non_blocking=True)
             torch.cuda.current_stream().synchronize()
             return img_host
-        return step_hot, step_e2e, B, labels_host.numel() * 8, B * 3 * 256 * 256 * 4
+        return step_hot, step_e2e, B, labels_host.numel() * 8, B * 3 * px * px * 4
 
     def scoring_runner(vae, var, K):
         from var_b200.scoring import class_log_likelihoods, gather_class_scores, shard_range
@@ -324,7 +336,7 @@ def main():
         return max_over_ranks(e0.elapsed_time(e1) * 1e-3), launches
 
     shard_lo, shard_hi = 0, 0
-    vae, var = build(wl["depth"])
+    vae, var = build(wl["depth"], **({"patch_nums": pns, "shared_aln": True} if wl.get("shared_aln") else {}))
     if wl["kind"] == "sample":
         hot, e2e, units, h2d, d2h = sampling_runner(vae, var, wl["batch"])
     else:
@@ -351,17 +363,17 @@ def main():
     ncu_path = ROOT / "profiles" / "r01_ncu_gemm_d30_fc1.json"
     ncu_traffic = json.loads(ncu_path.read_text()) if ncu_path.exists() else {}
     n_seq_step = (2 * wl["batch"]) if wl["kind"] == "sample" else (shard_hi - shard_lo)
-    gemm_flops = n_seq_step * (24.0 * C_ * C_ * depth * L_SEQ + 2.0 * C_ * V * L_SEQ + 12.0 * C_ * C_ * depth + 4.0 * C_ * C_)
+    gemm_flops = n_seq_step * (24.0 * C_ * C_ * depth * L_wl + 2.0 * C_ * V * L_wl + 12.0 * C_ * C_ * depth + 4.0 * C_ * C_)
     barrier()
     with L.kernel_profile() as kp:
         hot()
     gemm_ms = sum(v for k, v in kp.ms.items() if k.startswith("gemm"))
     all_ms = sum(kp.ms.values())
     gemm_tf_step = gemm_flops / (gemm_ms * 1e-3) / 1e12
-    M_big = (2 * wl["batch"] * 256) if wl["kind"] == "sample" else min(125, shard_hi - shard_lo) * L_SEQ
+    M_big = (2 * wl["batch"] * pns[-1] ** 2) if wl["kind"] == "sample" else min(125, shard_hi - shard_lo) * L_SEQ
     t_g = time_gemm(M_big, 4 * C_, C_, L.EPI_GELU_BF16)
     gemm_tf = 2.0 * M_big * 4 * C_ * C_ / t_g / 1e12
-    fl_img = (2 if wl["kind"] == "sample" else 1000) * flops_per_seq(depth)
+    fl_img = (2 if wl["kind"] == "sample" else 1000) * flops_per_seq(depth, pns)
     step_tf = value / world * fl_img / 1e12
     roofline = dict(bound="tensor", kernel="gemm_bf16_kernel<BN,EPI,2> (all fused epilogues of the step)",
                     achieved=gemm_tf_step, peak=pk["sustained"], unit="TFLOP/s", frac=gemm_tf_step / pk["sustained"],
@@ -398,7 +410,7 @@ def main():
         line["secondary"] = dict(metric="images/sec: VAR-d16 1000-class likelihood scoring", value=v2, unit="images/sec",
                                  e2e=units2 * 2 / t2e, pairs_per_sec=v2 * 1000,
                                  step_frac=v2 * 1000 * flops_per_seq(16) / 1e12 / pk["sustained"])
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu and px == 256:
         threads = host_threads()
         if wl["kind"] == "sample":
             t_cpu = cpu_sampling_step(wl["depth"], 1, threads)
