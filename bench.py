@@ -148,23 +148,88 @@ def host_threads() -> int:
         return os.cpu_count() or 1
 
 
+REF_IMAGES = 4    # images per step of the reference arm's sampling sample (CFG batch 8)
+REF_CLASSES = 8   # classes per step of the reference arm's scoring sample
+
+
+_REF_STATE = {}
+
+
+def _reference_models(depth: int):
+    """The UNMODIFIED reference (oracle/_ref = byte copies of /root/reference/models + dist.py, oracle/ref_loader.py)
+    on CPU with the same seeded dense init as the GPU arm."""
+    if depth not in _REF_STATE:
+        from oracle import ref_loader
+        from var_b200.init_utils import dense_init_
+        build, _, _ = ref_loader.load()
+        vae, var = build(depth=depth)
+        dense_init_(vae, seed=1)
+        dense_init_(var, seed=2)
+        _REF_STATE.clear()  # one model at a time (d30 is 8 GB in fp32)
+        _REF_STATE[depth] = (vae, var)
+    return _REF_STATE[depth]
+
+
+def ref_sampling_step(depth: int, n_img: int, threads: int):
+    """models/var.py:126-190 as shipped: labels -> images [n_img,3,256,256] (CNN decoder included), fp32, CPU."""
+    torch.set_num_threads(threads)
+    vae, var = _reference_models(depth)
+    g = torch.Generator().manual_seed(0)
+    labels = torch.randint(0, 1000, (n_img,), generator=g)
+    t0 = time.perf_counter()
+    with torch.inference_mode():
+        img = var.autoregressive_infer_cfg(B=n_img, label_B=labels, g_seed=0, cfg=1.5, top_k=900, top_p=0.0)
+    assert img.shape == (n_img, 3, 256, 256)
+    return time.perf_counter() - t0
+
+
+def ref_scoring_step(depth: int, n_cls: int, threads: int):
+    """The class loop of eval_prob.py:423-465 around the reference's own modules (eval_prob.py itself needs clip /
+    matplotlib, absent here): one class per forward, idxBl_to_var_input recomputed per class as the script does."""
+    torch.set_num_threads(threads)
+    vae, var = _reference_models(depth)
+    g = torch.Generator().manual_seed(0)
+    gt_idx = [torch.randint(0, V, (1, p * p), generator=g) for p in PATCH_NUMS]
+    gt = torch.cat(gt_idx, dim=1)
+    t0 = time.perf_counter()
+    scores = []
+    with torch.inference_mode():
+        for c in range(n_cls):
+            x_in = vae.quantize.idxBl_to_var_input(gt_idx)                     # eval_prob.py:436
+            logits = var(torch.tensor([c]), x_in)                                # eval_prob.py:441
+            lp = torch.log_softmax(logits, dim=-1).gather(-1, gt.unsqueeze(-1))  # eval_prob.py:446-463
+            scores.append(lp.sum())
+    return time.perf_counter() - t0
+
+
+def cpu_arm(workload):
+    """(step function, units per step, kind, sample description) of the CPU arm for this workload."""
+    from oracle import ref_loader
+    threads = host_threads()
+    depth = workload["depth"]
+    if ref_loader.available():
+        if workload["kind"] == "sample":
+            return (lambda: ref_sampling_step(depth, REF_IMAGES, threads), float(REF_IMAGES), "reference",
+                    f"{REF_IMAGES} images per step (CFG batch {2 * REF_IMAGES}), all 10 scales, cfg=1.5, top_k=900, fp32: the "
+                    "unmodified reference VAR.autoregressive_infer_cfg incl. the CNN decoder, labels -> images")
+        return (lambda: ref_scoring_step(depth, REF_CLASSES, threads), REF_CLASSES / 1000.0, "reference",
+                f"{REF_CLASSES} of the 1000 classes of one image per step, fp32: the unmodified reference VAR.forward in the "
+                "class loop of eval_prob.py:423-465 (one class per forward)")
+    if workload["kind"] == "sample":
+        return (lambda: cpu_sampling_step(depth, 1, threads), 1.0, "port",
+                "1 image per step, all 10 scales, fp32 oracle port of autoregressive_infer_cfg to f_hat (oracle/_ref absent)")
+    return (lambda: cpu_scoring_step(depth, 4, threads), 4 / 1000.0, "port",
+            "4 of 1000 classes of one image per step, fp32 oracle port of VAR.forward + score (oracle/_ref absent)")
+
+
 def run_reference_arm(args, workload):
-    """--impl reference: the reference's CPU implementation of the path (oracle port; the Python reference itself
-    cannot travel to the GPU box) on a bounded sample, all host threads."""
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores (the unmodified
+    reference from oracle/_ref; the oracle port only if that copy is absent), each step a bounded sample."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = host_threads()
-    depth = workload["depth"]
-    if workload["kind"] == "sample":
-        n_img, unit_per_step = 1, 1.0
-        fn = lambda: cpu_sampling_step(depth, n_img, threads)
-        sample = f"{n_img} image(s), all 10 scales, cfg=1.5, top_k=900, fp32, oracle port of autoregressive_infer_cfg to f_hat"
-    else:
-        n_cls = 4
-        unit_per_step = n_cls / 1000.0
-        fn = lambda: cpu_scoring_step(depth, n_cls, threads)
-        sample = f"{n_cls} of 1000 classes of one image, fp32 oracle port of VAR.forward + log-softmax/gather/sum"
+    fn, unit_per_step, kind, sample = cpu_arm(workload)
     for _ in range(args.warmup):
         fn()
     ts = [fn() for _ in range(args.steps)]
@@ -173,7 +238,9 @@ def run_reference_arm(args, workload):
     line = dict(impl="reference", metric=workload["metric"], value=value, unit="images/sec", n_gpus=args.gpus,
                 steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * total / args.steps, higher_is_better=True,
                 scaling=workload["scaling"], vs_baseline=None, dtype="f32", data="synthetic", config=workload["config"],
-                cpu_baseline=dict(value=value, unit="images/sec", cores=threads, kind="port", sample=sample),
+                sample=dict(what=sample, units_per_step=unit_per_step, note="config is the GPU arm's (the driver pairs the "
+                            "two lines on it); THIS arm runs the bounded sample stated here, not the full batch"),
+                cpu_baseline=dict(value=value, unit="images/sec", cores=threads, kind=kind, sample=sample),
                 e2e=dict(value=value, unit="images/sec", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line), flush=True)
 
@@ -242,6 +309,7 @@ def main():
                         l2="activations per step >> 126 MB L2 (inputs larger than L2)", parallelism=f"dp{args.gpus}")
 
     if args.impl == "reference":
+        os.environ["CUDA_VISIBLE_DEVICES"] = ""  # CPU arm: the reference picks its device from torch.cuda.is_available()
         if px != 256:
             print(json.dumps(dict(impl="reference", unavailable="the CPU arm is built for the 256 px headline workloads")))
             return
@@ -274,6 +342,14 @@ def main():
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         return float(t.item())
 
+    def all_ranks(obj):
+        """obj of every rank, in rank order (diagnostics only, outside every timed region)."""
+        if world == 1:
+            return [obj]
+        out = [None] * world
+        torch.distributed.all_gather_object(out, obj)
+        return out
+
     def build(depth, **kw):
         vae, var = build_vae_var(dev, depth=depth, **kw)
         dense_init_(var, seed=2)
@@ -281,13 +357,14 @@ def main():
         var.eval(); vae.eval(); var.cond_drop_rate = 0
         return vae, var
 
-    def sampling_runner(vae, var, B):
+    def sampling_runner(vae, var, B, cuda_graph=False):
         g = torch.Generator(device="cpu").manual_seed(rank)
         labels_host = torch.randint(0, 1000, (B,), generator=g).pin_memory()
         labels_dev = labels_host.to(dev)
 
         def step_hot():  # inputs resident, hot path to f_hat
-            var.autoregressive_infer_cfg(B, labels_dev, g_seed=0, cfg=1.5, top_k=900, top_p=0.0, decode=False)
+            var.autoregressive_infer_cfg(B, labels_dev, g_seed=0, cfg=1.5, top_k=900, top_p=0.0, decode=False,
+                                         cuda_graph=cuda_graph)
 
         img_host = torch.empty((B, 3, px, px), dtype=torch.float32).pin_memory()
 
@@ -295,7 +372,7 @@ def main():
 
         def step_e2e():  # public API: host labels in, images out
             lab = labels_host.to(dev, non_blocking=True)
-            img = var.autoregressive_infer_cfg(B, lab, g_seed=0, cfg=1.5, top_k=900, top_p=0.0)
+            img = var.autoregressive_infer_cfg(B, lab, g_seed=0, cfg=1.5, top_k=900, top_p=0.0, cuda_graph=cuda_graph)
             img_host.copy_(img, non_blocking=True)
             torch.cuda.current_stream().synchronize()
             return img_host
@@ -321,6 +398,7 @@ def main():
         return step_hot, step_e2e, 1.0 / world, img_host.numel() * 4, 8
 
     def measure(step, steps, warmup):
+        """-> (max over ranks of the device time of `steps` steps [s], launches of this rank, this rank's own time)."""
         for _ in range(warmup):
             step()
         barrier()
@@ -333,7 +411,21 @@ def main():
         e1.record(st)
         barrier()
         launches = lib.var_b200_launch_count() - n0
-        return max_over_ranks(e0.elapsed_time(e1) * 1e-3), launches
+        own = e0.elapsed_time(e1) * 1e-3
+        return max_over_ranks(own), launches, own
+
+    def kernel_split(step):
+        """One extra step with the library's per-kernel CUDA events (recorded on the launching stream around every launch)."""
+        barrier()
+        with L.kernel_profile() as kp:
+            step()
+        return kp
+
+    def family_ms(kp):
+        fam = dict(gemm=sum(v for k, v in kp.ms.items() if k.startswith("gemm")), attn=kp.ms.get("attn", 0.0),
+                   ln_modulate=kp.ms.get("ln_modulate", 0.0))
+        fam["other"] = sum(kp.ms.values()) - sum(fam.values())
+        return {k: round(v, 2) for k, v in fam.items()}
 
     shard_lo, shard_hi = 0, 0
     vae, var = build(wl["depth"], **({"patch_nums": pns, "shared_aln": True} if wl.get("shared_aln") else {}))
@@ -345,11 +437,10 @@ def main():
         hot, e2e, units, h2d, d2h = scoring_runner(vae, var, wl["batch"])
 
     clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
-    t_hot, launches = measure(hot, args.steps, max(args.warmup, 3))
-    clk = clocks.stop() if rank == 0 else None
-    t_e2e, _ = measure(e2e, args.steps, 1)
+    clocks.start()
+    t_hot, launches, own_hot = measure(hot, args.steps, max(args.warmup, 3))
+    clk = clocks.stop()
+    t_e2e, _, _ = measure(e2e, args.steps, 1)
     value = units * world * args.steps / t_hot
     value_e2e = units * world * args.steps / t_e2e
 
@@ -364,9 +455,7 @@ def main():
     ncu_traffic = json.loads(ncu_path.read_text()) if ncu_path.exists() else {}
     n_seq_step = (2 * wl["batch"]) if wl["kind"] == "sample" else (shard_hi - shard_lo)
     gemm_flops = n_seq_step * (24.0 * C_ * C_ * depth * L_wl + 2.0 * C_ * V * L_wl + 12.0 * C_ * C_ * depth + 4.0 * C_ * C_)
-    barrier()
-    with L.kernel_profile() as kp:
-        hot()
+    kp = kernel_split(hot)
     gemm_ms = sum(v for k, v in kp.ms.items() if k.startswith("gemm"))
     all_ms = sum(kp.ms.values())
     gemm_tf_step = gemm_flops / (gemm_ms * 1e-3) / 1e12
@@ -389,6 +478,10 @@ def main():
                                   peak=pk["burst"], frac=gemm_tf / pk["burst"]),
                     step_achieved=step_tf, step_peak=pk["sustained"], step_frac=step_tf / pk["sustained"],
                     step_note="whole-step algorithmic FLOPs (SURVEY 8d; attention on visible pairs only) / step time")
+    # every rank's own step time, kernel-family split and clocks: attributes a scaling loss to a GPU or to the host
+    per_rank = all_ranks(dict(rank=rank, ms_per_step=round(1e3 * own_hot / args.steps, 2), kernel_ms=family_ms(kp),
+                              host_gap_ms=round(1e3 * own_hot / args.steps - all_ms, 2), sm_mhz=clk["sm_mhz"],
+                              reasons=clk["reasons"]))
 
     line = dict(metric=wl["metric"], value=value, unit="images/sec", n_gpus=world, steps=args.steps,
                 warmup=max(args.warmup, 3), ms_per_step=1e3 * t_hot / args.steps, higher_is_better=True, scaling=wl["scaling"],
@@ -396,34 +489,68 @@ def main():
                 config=wl["config"], clocks=clk,
                 e2e=dict(value=value_e2e, unit="images/sec", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                          note="public API call with host buffers: pinned H2D of the inputs, the whole call (sampling: incl. the bf16 NHWC CNN decoder on the tcgen05 implicit-GEMM convolutions), D2H of the result"),
-                gpu_launches=int(launches), roofline=roofline)
+                gpu_launches=int(launches), roofline=roofline, per_rank=per_rank)
 
-    if rank == 0 and world == 1 and not args.no_secondary and args.workload == "sample_d30":
-        # the other headline metric, measured in the same run (d16 1000-class scoring, one image per step)
+    sec_steps = max(10, args.steps)
+    if not args.no_secondary and args.workload == "sample_d30":
+        # (1) BASELINE configs[4] as written: 256 images TOTAL, 256/N per GPU ("strong"), the whole 10-scale loop replayed
+        #     as one CUDA graph (at 32 images per GPU the small scales are launch-bound in eager mode)
+        B_total = wl["batch"]
+        if B_total % world == 0:
+            Bs = B_total // world
+            hot_s, e2e_s, _, _, _ = sampling_runner(vae, var, Bs, cuda_graph=True)
+            ts, _, own_s = measure(hot_s, args.steps, 2)
+            tse, _, _ = measure(e2e_s, args.steps, 1)
+            kps = kernel_split(lambda: var.autoregressive_infer_cfg(Bs, torch.zeros(Bs, dtype=torch.long, device=dev), g_seed=0,
+                                                                    cfg=1.5, top_k=900, decode=False))
+            fams = all_ranks(dict(rank=rank, ms_per_step=round(1e3 * own_s / args.steps, 2), eager_kernel_ms=family_ms(kps)))
+            v_s = B_total * args.steps / ts
+            line["strong_config5"] = dict(
+                metric="images/sec: VAR-d30 256px CFG sampling, 256 images total batch-sharded over the GPUs (BASELINE configs[4])",
+                scaling="strong", total_batch=B_total, per_gpu_batch=Bs, cuda_graph=True, value=v_s, unit="images/sec",
+                ms_per_step=1e3 * ts / args.steps, e2e=B_total * args.steps / tse,
+                step_frac=v_s / world * fl_img / 1e12 / pk["sustained"], per_rank=fams,
+                limiting_kernel=max(fams[0]["eager_kernel_ms"].items(), key=lambda kv: kv[1])[0])
+        # (2) the other headline metric in the same run: d16 1000-class scoring of one image per step, the classes
+        #     sharded over the ranks, one all-gather of the per-class scores inside the timed region
         del var, vae, hot, e2e
+        if B_total % world == 0:
+            del hot_s, e2e_s
         torch.cuda.empty_cache()
         vae2, var2 = build(16)
         hot2, e2e2, units2, _, _ = scoring_runner(vae2, var2, 1000)
-        t2, _ = measure(hot2, 2, 1)
-        t2e, _ = measure(e2e2, 2, 1)
-        v2 = units2 * 2 / t2
-        line["secondary"] = dict(metric="images/sec: VAR-d16 1000-class likelihood scoring", value=v2, unit="images/sec",
-                                 e2e=units2 * 2 / t2e, pairs_per_sec=v2 * 1000,
-                                 step_frac=v2 * 1000 * flops_per_seq(16) / 1e12 / pk["sustained"])
+        t2, _, own2 = measure(hot2, sec_steps, 2)
+        t2e, _, _ = measure(e2e2, sec_steps, 1)
+        kp2 = kernel_split(hot2)
+        v2 = units2 * world * sec_steps / t2
+        line["secondary"] = dict(metric="images/sec: VAR-d16 1000-class likelihood scoring (classes sharded over the GPUs, "
+                                        "one all-gather of the scores)", value=v2, unit="images/sec", steps=sec_steps,
+                                 scaling="strong", e2e=units2 * world * sec_steps / t2e, pairs_per_sec=v2 * 1000,
+                                 ms_per_step=1e3 * t2 / sec_steps,
+                                 step_frac=v2 / world * 1000 * flops_per_seq(16) / 1e12 / pk["sustained"],
+                                 per_rank=all_ranks(dict(rank=rank, ms_per_step=round(1e3 * own2 / sec_steps, 2),
+                                                         kernel_ms=family_ms(kp2))))
     if rank == 0 and world == 1 and not args.no_cpu and px == 256:
-        threads = host_threads()
-        if wl["kind"] == "sample":
-            t_cpu = cpu_sampling_step(wl["depth"], 1, threads)
-            line["cpu_baseline"] = dict(value=1.0 / t_cpu, unit="images/sec", cores=threads, kind="port",
-                                        sample="1 image, all 10 scales, fp32 oracle port of autoregressive_infer_cfg to f_hat")
-        else:
-            t_cpu = cpu_scoring_step(wl["depth"], 4, threads)
-            line["cpu_baseline"] = dict(value=4 / 1000.0 / t_cpu, unit="images/sec", cores=threads, kind="port",
-                                        sample="4 of 1000 classes of one image, fp32 oracle port of VAR.forward + score")
+        line["cpu_baseline"] = cpu_baseline_subprocess(args.workload)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+def cpu_baseline_subprocess(workload: str):
+    """The CPU arm (`--impl reference`, one step, no warm-up) in a child process without CUDA: the reference chooses its
+    device from torch.cuda.is_available() at import time, and its fp32 d30 copy (8 GB) is gone when the child exits."""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        env.pop(k, None)
+    try:
+        r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--workload", workload, "--steps", "1",
+                            "--warmup", "0"], env=env, capture_output=True, text=True, timeout=900)
+        ref = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+        return ref["cpu_baseline"]
+    except Exception as e:  # noqa: BLE001 - a failed baseline must not lose the GPU measurement
+        return dict(value=None, unit="images/sec", cores=host_threads(), kind="unavailable", sample=f"CPU arm failed: {e!r}"[:300])
 
 
 if __name__ == "__main__":

@@ -281,7 +281,7 @@ def test_class_scores_vs_oracle():
     got, ps = class_log_likelihoods(var, [_t(i) for i in idx_np], labels, class_batch=4, per_scale=True)
     err = (got.cpu() - ref).abs().max().item()
     print(f"score abs err {err:.3f} on |score| ~ {ref.abs().mean():.1f}")
-    assert err < 1.5 and torch.argmax(got).item() == torch.argmax(ref).item()
+    assert err < 0.5 and torch.argmax(got).item() == torch.argmax(ref).item()  # measured 0.19
     assert (ps.sum(1) - got).abs().max().item() < 1e-2
     tail = class_log_likelihoods(var, [_t(i) for i in idx_np], labels, first_pos=424)
     assert (tail.cpu() - VO.class_scores(ref_logits, gt, first_pos=424)).abs().max().item() < 1.0
@@ -414,8 +414,8 @@ def test_nhwc_decoder_matches_pytorch_decoder():
     e_plan, e_plain, e_cudnn = (got - ref).abs(), (plain16 - ref).abs(), (got_cudnn - ref).abs()
     print(f"nhwc plan: max {e_plan.max():.4f} mean {e_plan.mean():.5f}; cudnn convs: max {e_cudnn.max():.4f} mean "
           f"{e_cudnn.mean():.5f}; plain bf16: max {e_plain.max():.4f} mean {e_plain.mean():.5f}")
-    assert e_plan.mean().item() < 2.0 * e_plain.mean().item() + 1e-3 and e_plan.max().item() < 0.25
-    assert e_cudnn.mean().item() < 2.0 * e_plain.mean().item() + 1e-3 and e_cudnn.max().item() < 0.25
+    assert e_plan.mean().item() < 2.0 * e_plain.mean().item() + 1e-3 and e_plan.max().item() < 0.12  # measured 0.055
+    assert e_cudnn.mean().item() < 2.0 * e_plain.mean().item() + 1e-3 and e_cudnn.max().item() < 0.12
     # deterministic (no atomics): two runs are bit-identical
     vae.decoder_dtype = torch.bfloat16
     try:
@@ -558,11 +558,13 @@ def test_smooth_sampling_vs_oracle_and_reference_golden(tag, kw):
         same = tr["sel"][si].cpu() == ref["sel"][si]   # near-tied decisions may flip under the bf16 logit error
         n_diff += int((~same).sum())
         assert ((tr["dlogp"][si].cpu() - ref["dlogp"][si]).abs() * same).max().item() < 1e-2  # cdist: GPU matmul path vs CPU
+    print(f"smooth_sampling[{tag}] forced: {n_diff} of {gt.numel()} selections differ from the oracle")
     assert n_diff <= 0.02 * gt.numel(), f"{n_diff} selections differ from the oracle"
     # unforced: our own selections vs the reference's tokens (decisions with sub-tolerance margins may flip)
     img, sll2, sdll2, tr2 = var.smooth_sampling(gt.to(DEV), 8, label=labels.to(DEV), g_seed=1, cfg=1.5, return_trace=True, **kw)
     tok = torch.cat(tr2["idx"], dim=1).cpu().numpy()
     n_diff = int((tok != g[f"tok_{tag}"].astype(np.int64)).sum())
+    print(f"smooth_sampling[{tag}] free: {n_diff} of {tok.size} selections differ from the reference")
     assert n_diff <= 0.02 * tok.size, f"{n_diff} of {tok.size} selections differ from the reference"
     assert img.shape == (2, 3, 256, 256) and sll2.dtype == torch.int64
     assert torch.equal(tr2["idx"][0].cpu(), gt[:, :1])  # candidate_count = 1 at scale 0: the gt token itself (d = 0)
