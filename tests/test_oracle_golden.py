@@ -32,6 +32,18 @@ def test_capi_exports_every_declared_symbol():
     assert lib.var_b200_gemm_tile_n(1920) == 192 and lib.var_b200_gemm_tile_n(4096) == 256
 
 
+def test_custom_op_layer_registers_cuda_only_ops():
+    """var_b200/ops.py: every C entry point of the path is a `var_b200::` torch.library op with a CUDA kernel only;
+    CPU tensors are refused by the dispatcher (no fallback)."""
+    import var_b200  # noqa: F401
+    from var_b200 import ops
+    for name in ops.OPS:
+        assert hasattr(torch.ops.var_b200, name), name
+    x = torch.randn(4, 64)
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        torch.ops.var_b200.ln_modulate(x, torch.zeros(1, 64), torch.zeros(1, 64), 64, 4, 1e-6)
+
+
 def test_header_constants_and_struct_layouts_match_the_binding():
     """The ctypes mirror must agree with include/var_b200.h and the kernels: constants, field order of the structs."""
     import ctypes as C

@@ -392,6 +392,71 @@ def test_ar_cuda_graph_matches_eager():
     assert torch.equal(eager2, graph2) and not torch.equal(graph, graph2)
 
 
+def test_cuda_graph_survives_workspace_reallocation():
+    """A captured AR loop holds raw pointers into the packed model's shared KV cache / scratch. An eager call with a
+    larger batch reallocates them; replaying the old graph afterwards must not touch the freed storage: the graphs are
+    dropped and re-captured (PackedModel.ws_gen)."""
+    vae, var = seeded_models(device=DEV)
+    labels = torch.tensor([1, 2, 3], device=DEV)
+    eager3 = var.autoregressive_infer_cfg(3, labels, g_seed=5, cfg=1.5, top_k=900, decode=False)
+    graph3 = var.autoregressive_infer_cfg(3, labels, g_seed=5, cfg=1.5, top_k=900, decode=False, cuda_graph=True)
+    assert torch.equal(eager3, graph3)
+    pm = var._model()
+    gen = pm.ws_gen
+    big = torch.arange(8, device=DEV)
+    eager8 = var.autoregressive_infer_cfg(8, big, g_seed=6, cfg=1.5, top_k=900, decode=False)   # reallocates KV + scratch
+    assert pm.ws_gen > gen
+    junk = [torch.full((1 << 20,), float("nan"), device=DEV) for _ in range(8)]                  # recycle freed blocks
+    again3 = var.autoregressive_infer_cfg(3, labels, g_seed=5, cfg=1.5, top_k=900, decode=False, cuda_graph=True)
+    assert torch.equal(again3, eager3)
+    assert torch.equal(var.autoregressive_infer_cfg(8, big, g_seed=6, cfg=1.5, top_k=900, decode=False), eager8)
+    del junk
+
+
+def test_out_of_range_labels_and_tokens_raise():
+    """The reference's embedding lookups raise / device-assert on a bad index; here the host checks before any launch."""
+    from var_b200.scoring import class_log_likelihoods
+    vae, var = seeded_models(device=DEV)
+    g = golden("quant_forward_d2.npz")
+    vin = torch.from_numpy(g["var_input"][:2]).to(DEV)
+    with pytest.raises(IndexError):
+        var(torch.tensor([1, 1001], device=DEV), vin)
+    with pytest.raises(IndexError):
+        var.autoregressive_infer_cfg(2, torch.tensor([-1, 3], device=DEV), g_seed=0, decode=False)
+    with pytest.raises(RuntimeError):
+        var(torch.tensor([1, 2], device=DEV), vin[:, :100])
+    idx = [_t(i) for i in split_scales(g["idx"][:1])]
+    bad = [t.clone() for t in idx]
+    bad[4][0, 3] = 4096
+    with pytest.raises(IndexError):
+        vae.quantize.idxBl_to_var_input(bad)
+    with pytest.raises(IndexError):
+        class_log_likelihoods(var, bad, torch.tensor([1, 2]))
+    with pytest.raises(IndexError):
+        class_log_likelihoods(var, idx, torch.tensor([1, 2000]))
+
+
+def test_custom_ops_are_the_call_path():
+    """The host mirrors reach the C-ABI through the `var_b200::` torch.library ops (var_b200/ops.py), CUDA key only."""
+    from var_b200 import ops
+    vae, var = seeded_models(device=DEV)
+    for name in ops.OPS:
+        assert hasattr(torch.ops.var_b200, name), name
+    g = golden("quant_forward_d2.npz")
+    f = _t(g["f"])
+    cb, w, b, ph, pw, phi_of, resi = vae.quantize._qargs([(p, p) for p in PATCH_NUMS])
+    idx, _ = torch.ops.var_b200.quant_encode(f, cb, w, b, ph, pw, phi_of, resi, False, 0)
+    got = torch.cat([t.reshape(3, -1) for t in torch.split(idx, [3 * p * p for p in PATCH_NUMS])], dim=1).cpu().numpy()
+    assert np.array_equal(got, g["idx"].astype(np.int64))
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        torch.ops.var_b200.quant_encode(f.cpu(), cb.cpu(), w.cpu(), b.cpu(), ph, pw, phi_of, resi, False, 0)
+    x = torch.randn(64, 128, device=DEV)
+    sc, sh = torch.randn(2, 128, device=DEV) * 0.1, torch.randn(2, 128, device=DEV) * 0.1
+    out = torch.ops.var_b200.ln_modulate(x, sc, sh, 128, 32, 1e-6)
+    ref = torch.nn.functional.layer_norm(x, (128,), eps=1e-6).view(2, 32, 128) * (1 + sc[:, None]) + sh[:, None]
+    assert (out.float().view(2, 32, 128) - ref).abs().max().item() < 3e-2
+
+
 def test_nhwc_decoder_matches_pytorch_decoder():
     """The channels-last bf16 decoder plan (cuDNN NHWC convs + var_b200 GroupNorm/SiLU kernel) vs the fp32 PyTorch
     decoder (models/basic_vae.py:163-226) and vs a plain bf16 copy of it."""

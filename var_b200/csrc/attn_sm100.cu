@@ -741,13 +741,9 @@ int attn_launch(const AttnArgs& a, cudaStream_t st) {
     r = make_tmap_bf16_sw128(&tmV, a.v, 3, dims, str, box);
     if (r) return r;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    VB_CUDA_CHECK(cudaFuncSetAttribute(attn_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    VB_CUDA_CHECK(cudaFuncSetAttribute(attn_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    VB_CUDA_CHECK(cudaFuncSetAttribute(attn_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    attr_set = true;
-  }
+  static vb::SmemAttrCache attr_cache;
+  if (vb::ensure_dyn_smem(attr_cache, ATT_SMEM, attn_kernel<false, false>, attn_kernel<true, false>, attn_kernel<true, true>))
+    return vb::VB_ERR_CUDA;
   // Bounded-score variant: needs |q.k| <= max_score with 2*max_score*log2(e) <= 126 (exp2 arguments stay normal).
   // VAR_B200_ATTN_FAST=0 forces the general kernel (measurements).
   bool fast = a.max_score > 0.f && a.max_score <= ATT_FAST_MAX_SCORE;

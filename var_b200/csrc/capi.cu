@@ -228,6 +228,8 @@ extern "C" int var_b200_head_score(const var_b200_model_t* m, const float* x, co
   const float* ah = ada + (size_t)6 * m->depth * C;
   rc = ln_modulate(x, ah, ah + C, ld, l, w.a, M, C, m->norm_eps, st);
   if (rc) return rc;
+  // NaN-fill: a ground-truth token outside [0, V) leaves its row unwritten and the score becomes NaN, never stale data
+  VB_CUDA_CHECK(cudaMemsetAsync(w.gtl, 0xFF, (size_t)M * 4, st));
   GemmParams p{};
   p.M = M; p.N = m->V; p.K = C; p.bias = m->b_head;
   p.gt = gt; p.gt_mod = gt_rows; p.part = reinterpret_cast<float2*>(w.part); p.gt_logit = reinterpret_cast<float*>(w.gtl);

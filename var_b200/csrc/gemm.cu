@@ -7,15 +7,13 @@
 
 namespace vb {
 
-static thread_local int g_conv_cin = 0;  // true channel count of the activation tensor of a conv3x3_launch call
-
 template <int BN, int EPI, int CTAS>
 static int launch_one(const void* A, const void* W, const GemmParams& p, cudaStream_t st) {
   using Cfg = GemmCfg<BN, CTAS>;
   CUtensorMap tmA, tmB;
   if (p.conv_kpt > 0) {
     // activations [B, H, W, Cin] as a 4-D map (C, W, H, B); a box = bw x bh pixels x 64 channels = one 128-row A tile
-    const int Cin = g_conv_cin, nB = p.M / (p.conv_H * p.conv_W);
+    const int Cin = p.conv_cin, nB = p.M / (p.conv_H * p.conv_W);
     const uint32_t bw = p.conv_W < GEMM_BM ? p.conv_W : GEMM_BM, bh = GEMM_BM / bw;
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)p.conv_W, (uint64_t)p.conv_H, (uint64_t)nB};
     uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)p.conv_W * Cin * 2, (uint64_t)p.conv_H * p.conv_W * Cin * 2};
@@ -37,11 +35,8 @@ static int launch_one(const void* A, const void* W, const GemmParams& p, cudaStr
     if (r) return r;
   }
   auto kern = gemm_bf16_kernel<BN, EPI, CTAS>;
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
-    VB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
+  static SmemAttrCache attr_cache;  // per instantiation, per device
+  if (ensure_dyn_smem(attr_cache, Cfg::SMEM_BYTES, kern)) return VB_ERR_CUDA;
   const int m_tiles = (p.M + GEMM_BM * CTAS - 1) / (GEMM_BM * CTAS);
   const int n_tiles = (p.N + BN - 1) / BN;
   const int total = m_tiles * n_tiles;
@@ -168,10 +163,8 @@ int conv3x3_launch(const void* x, const void* w_packed, const float* bias, const
   p.bias = bias;
   p.out = out;
   p.resid_bf16 = reinterpret_cast<const __nv_bfloat16*>(resid);
-  g_conv_cin = Cin;
-  const int r = gemm_launch(x, w_packed, p, EPI_BIAS_BF16, st, Cout % 160 == 0 ? 160 : 0);
-  g_conv_cin = 0;
-  return r;
+  p.conv_cin = Cin;
+  return gemm_launch(x, w_packed, p, EPI_BIAS_BF16, st, Cout % 160 == 0 ? 160 : 0);
 }
 
 }  // namespace vb

@@ -46,6 +46,7 @@ struct GemmParams {
   // activation tensor [B, conv_H, conv_W, Cin] seen through a 4-D tensor map, row m = pixel ((b*H + y)*W + x);
   // K = 9 taps x conv_kpt 64-channel blocks (weights packed [N, 9, conv_kpt*64], zero padded). 0 = plain GEMM.
   int conv_kpt, conv_H, conv_W;
+  int conv_cin;  // true channel count of the activation tensor (the tensor map's innermost extent; tails read as zeros)
 };
 
 // Tile width the launcher will use for a given N (needed to size EPI_SCORE partials: n_tiles = ceil(N / bn)).

@@ -128,13 +128,22 @@ ProfScope::~ProfScope() {
   g_prof.push_back(r);
 }
 
+int current_device() {
+  int dev = 0;
+  return cudaGetDevice(&dev) == cudaSuccess ? dev : -1;
+}
+
 int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  static std::atomic<int> cache[VB_MAX_DEVICES];  // zero-initialised: 0 = not queried yet
+  const int dev = current_device();
+  if (dev < 0) return 148;
+  if (dev < VB_MAX_DEVICES) {
+    const int c = cache[dev].load(std::memory_order_relaxed);
+    if (c > 0) return c;
   }
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  if (dev < VB_MAX_DEVICES) cache[dev].store(n, std::memory_order_relaxed);
   return n;
 }
 

@@ -4,6 +4,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+#include <mutex>
+
 namespace vb {
 
 void set_error(const char* fmt, ...);
@@ -14,7 +17,10 @@ const char* get_error();
 int make_tmap_bf16_sw128(CUtensorMap* out, const void* gptr, int rank, const uint64_t* dims,
                          const uint64_t* strides_bytes, const uint32_t* box);
 
+// SM count of the CURRENT device (cached per device).
 int sm_count();
+// Current device ordinal (cudaGetDevice), -1 on error.
+int current_device();
 // number of kernels this library has launched in the process (bench.py's gpu_launches claim)
 void count_launch(int n = 1);
 
@@ -48,5 +54,31 @@ struct ProfScope {
       return vb::VB_ERR_ARG;         \
     }                                \
   } while (0)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute of a kernel: this cache remembers, per device,
+// the largest size already granted to the kernels of one launcher, and serialises the (rare) slow path, so the
+// launchers are safe with several GPUs in one process and with several host threads.
+constexpr int VB_MAX_DEVICES = 64;
+struct SmemAttrCache {
+  std::atomic<int> granted[VB_MAX_DEVICES];
+  std::mutex mu;
+  SmemAttrCache() { for (auto& g : granted) g.store(-1, std::memory_order_relaxed); }
+};
+template <class... Kerns>
+inline int ensure_dyn_smem(SmemAttrCache& cache, size_t bytes, Kerns... kerns) {
+  const int dev = current_device();
+  const bool cached = dev >= 0 && dev < VB_MAX_DEVICES;
+  if (cached && (int)bytes <= cache.granted[dev].load(std::memory_order_acquire)) return 0;
+  std::lock_guard<std::mutex> lk(cache.mu);
+  if (cached && (int)bytes <= cache.granted[dev].load(std::memory_order_acquire)) return 0;
+  const cudaError_t errs[] = {cudaFuncSetAttribute(kerns, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)...};
+  for (cudaError_t e : errs)
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(MaxDynamicSharedMemorySize=%zu) failed: %s", bytes, cudaGetErrorString(e));
+      return -2;  // VB_ERR_CUDA (common.cuh)
+    }
+  if (cached) cache.granted[dev].store((int)bytes, std::memory_order_release);
+  return 0;
+}
 
 }  // namespace vb

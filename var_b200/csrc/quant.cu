@@ -386,11 +386,8 @@ int quant_launch(const QuantArgs& a, cudaStream_t st) {
   VB_REQUIRE(a.split == 0 || (a.z_out && a.zb_out && a.zz_out && a.f_rest), "quant: split mode needs pooled-token buffers");
   const size_t smem = quant_smem_bytes(a.H, a.W, a.V, a.f != nullptr && a.split == 0);
   VB_REQUIRE(smem <= 227 * 1024, "quant: shared memory %zu exceeds 227 KB (V=%d too large?)", smem, a.V);
-  static size_t attr = 0;
-  if (smem > attr) {
-    VB_CUDA_CHECK(cudaFuncSetAttribute(quant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
+  static vb::SmemAttrCache attr_cache;
+  if (vb::ensure_dyn_smem(attr_cache, smem, quant_kernel)) return vb::VB_ERR_CUDA;
   vb::ProfScope prof_scope(vb::PK_QUANT, st);
   quant_kernel<<<a.B, QT, smem, st>>>(p);
   VB_CUDA_CHECK(cudaGetLastError());

@@ -243,11 +243,8 @@ int quant_search_launch(const QuantSearchArgs& a, cudaStream_t st) {
     int r = make_tmap_bf16_sw128(&tmB, a.cb_bf16, 2, dims, str, box);
     if (r) return r;
   }
-  static size_t attr = 0;
-  if (smem > attr) {
-    VB_CUDA_CHECK(cudaFuncSetAttribute(quant_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
+  static SmemAttrCache attr_cache;
+  if (ensure_dyn_smem(attr_cache, smem, quant_search_kernel)) return VB_ERR_CUDA;
   const int n_mt = (a.N + QS_BM - 1) / QS_BM;
   const int grid = n_mt < sm_count() ? n_mt : sm_count();
   vb::ProfScope prof_scope(vb::PK_QUANT, st);

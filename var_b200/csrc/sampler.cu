@@ -230,12 +230,8 @@ int sample_launch(const SampleArgs& a, cudaStream_t st) {
     VB_REQUIRE(a.codebook && a.h_out && a.Cvae > 0 && a.Cvae <= 32 && a.tau > 0.f && a.V >= 256,
                "sample: more_smooth needs codebook, h_out, 0 < Cvae <= 32, tau > 0 (Cvae=%d tau=%f)", a.Cvae, a.tau);
   }
-  static size_t attr = 0;
-  if (smem > attr && smem > 40 * 1024) {  // static smem (~1.2 KB) counts against the 48 KB default limit
-    VB_CUDA_CHECK(cudaFuncSetAttribute(sample_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VB_CUDA_CHECK(cudaFuncSetAttribute(sample_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
+  static vb::SmemAttrCache attr_cache;  // static smem (~1.2 KB) counts against the 48 KB default limit
+  if (smem > 40 * 1024 && vb::ensure_dyn_smem(attr_cache, smem, sample_kernel<false>, sample_kernel<true>)) return vb::VB_ERR_CUDA;
   const float opt = (float)(1.0 + a.t), tf = (float)a.t;
   vb::ProfScope prof_scope(vb::PK_SAMPLE, st);
   auto kern = a.q_gumbel != nullptr ? sample_kernel<true> : sample_kernel<false>;
@@ -297,8 +293,8 @@ int cfg_token_expected_dist(const float* lc, const float* lu, const int* gt, con
   VB_REQUIRE(lu == nullptr || t_row != nullptr, "cfg_token_expected_dist: t_row is required with uncond logits");
   VB_REQUIRE(n_seq <= 65535 && top_k >= 0 && (size_t)V * 4 <= 200 * 1024, "cfg_token_expected_dist: n_seq/top_k/V out of range");
   const size_t smem = (size_t)V * sizeof(float);
-  if (smem > 40 * 1024)
-    VB_CUDA_CHECK(cudaFuncSetAttribute(expected_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static vb::SmemAttrCache attr_cache;
+  if (smem > 40 * 1024 && vb::ensure_dyn_smem(attr_cache, smem, expected_dist_kernel)) return vb::VB_ERR_CUDA;
   vb::ProfScope prof_scope(vb::PK_SCORE_FIN, st);
   expected_dist_kernel<<<dim3(L, n_seq), ST, smem, st>>>(lc, lu, gt, t_row, dists, L, V, top_k, out);
   VB_CUDA_CHECK(cudaGetLastError());
@@ -387,8 +383,8 @@ int neighbor_select(const float* logits, int B, int l, int V, double t, const in
   VB_REQUIRE(B > 0 && l > 0 && V > 0 && n_nb > 0 && n_nb <= V && (size_t)V * 4 <= 200 * 1024, "neighbor_select: bad shape");
   VB_REQUIRE(thr_mode || (cand_count >= 1 && cand_count <= n_nb), "neighbor_select: cand_count=%d out of [1,%d]", cand_count, n_nb);
   const size_t smem = (size_t)V * sizeof(float);
-  if (smem > 40 * 1024)
-    VB_CUDA_CHECK(cudaFuncSetAttribute(neighbor_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static vb::SmemAttrCache attr_cache;
+  if (smem > 40 * 1024 && vb::ensure_dyn_smem(attr_cache, smem, neighbor_select_kernel)) return vb::VB_ERR_CUDA;
   vb::ProfScope prof_scope(vb::PK_SAMPLE, st);
   neighbor_select_kernel<<<B * l, ST, smem, st>>>(logits, B, l, V, (float)(1.0 + t), (float)t, gt, neighbors, dists, n_nb,
                                                  cand_count, thr_mode, thr, ratio, reinterpret_cast<long long*>(tok_out),

@@ -182,3 +182,20 @@ def ptr(t) -> int:
 def current_stream() -> int:
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+
+def device_guard(fn):
+    """Decorator for module methods: run with the device of the module's parameters current, so that the kernels are
+    launched on that device's current stream whichever device the caller had selected."""
+    import functools
+
+    import torch
+
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        dev = self._device()
+        if dev.type != "cuda":
+            return fn(self, *args, **kwargs)  # raises VarB200Error further down: there is no CPU path
+        with torch.cuda.device(dev):
+            return fn(self, *args, **kwargs)
+    return wrapper

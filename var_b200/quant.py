@@ -91,6 +91,27 @@ class VectorQuantizer2(nn.Module):
     def forward(self, *a, **k):
         raise NotImplementedError("VectorQuantizer2.forward is VAE training (out of scope, SURVEY.md §2 row 3)")
 
+    def _device(self) -> torch.device:
+        return self.embedding.weight.device
+
+    def codebook_distances(self):
+        """(dists [V,V] fp32, order [V,V] int32): pairwise L2 distances of the code vectors and, per code, all codes
+        by increasing distance (models/var.py:459-462, var_analysis.py:256). Cached per codebook version."""
+        w = self.embedding.weight
+        key = (w._version, w.data_ptr())
+        if getattr(self, "_dist_key", None) != key:
+            E = w.detach().float()
+            d = torch.cdist(E, E, p=2).contiguous()
+            self._dist = (d, torch.argsort(d, dim=1).to(torch.int32).contiguous())
+            self._dist_key = key
+        return self._dist
+
+    def _check_tokens(self, idx: torch.Tensor, V: int):
+        if idx.numel():  # the reference's embedding lookup raises / device-asserts on a bad token
+            lo, hi = (int(v) for v in torch.aminmax(idx))
+            if lo < 0 or hi >= V:
+                raise IndexError(f"token index out of range [0, {V}) (embedding lookup, models/quant.py:180)")
+
     # ------------------------------------------------------------------ packing
     def _weights(self):
         ps = self.quant_resi.phis()
@@ -103,24 +124,19 @@ class VectorQuantizer2(nn.Module):
             self._pack_key = key
         return self._packed
 
-    def _desc(self, patch_hws: Sequence[Tuple[int, int]]) -> L.QuantDesc:
+    def _qargs(self, patch_hws: Sequence[Tuple[int, int]]):
+        """(codebook, phi_w, phi_b, ph, pw, phi_of_scale, resi): the quantizer arguments of the var_b200:: custom ops."""
         cb, w, b = self._weights()
         if not cb.is_cuda:
             raise L.VarB200Error("var_b200 quantizer needs its parameters on a CUDA device (no CPU path)")
         S = len(patch_hws)
         if S > L.MAX_SCALES:
             raise ValueError(f"at most {L.MAX_SCALES} scales are supported, got {S}")
-        d = L.QuantDesc()
-        d.Cvae, d.V, d.n_scales = self.Cvae, self.vocab_size, S
-        for i, (h, wd) in enumerate(patch_hws):
-            d.ph[i], d.pw[i] = h, wd
-            d.phi_of_scale[i] = self.quant_resi.index(i / (S - 1) if S > 1 else 0.0)
-        d.n_phi, d.resi = w.shape[0], abs(self.quant_resi_ratio)
-        d.codebook, d.phi_w, d.phi_b = cb.data_ptr(), w.data_ptr(), b.data_ptr()
-        d._keep = (cb, w, b)
-        return d
+        phi_of = [self.quant_resi.index(i / (S - 1) if S > 1 else 0.0) for i in range(S)]
+        return cb, w, b, [h for h, _ in patch_hws], [wd for _, wd in patch_hws], phi_of, abs(self.quant_resi_ratio)
 
     # ------------------------------------------------------------------ reference API
+    @L.device_guard
     def f_to_idxBl_or_fhat(self, f_BChw: torch.Tensor, to_fhat: bool,
                            v_patch_nums: Optional[Sequence[Union[int, Tuple[int, int]]]] = None):
         """quant.py:135-166."""
@@ -128,14 +144,7 @@ class VectorQuantizer2(nn.Module):
         patch_hws = [_hw(pn) for pn in (v_patch_nums or self.v_patch_nums)]
         assert patch_hws[-1][0] == H and patch_hws[-1][1] == W, f'{patch_hws[-1]=} != ({H=}, {W=})'
         f = f_BChw.detach().float().contiguous()
-        d = self._desc(patch_hws)
-        Ltot = sum(h * w for h, w in patch_hws)
-        idx = torch.empty(B * Ltot, dtype=torch.int64, device=f.device)
-        fh = torch.empty((len(patch_hws), B, Cc, H, W), dtype=torch.float32, device=f.device) if to_fhat else None
-        lib = L.load()
-        work = torch.empty(lib.var_b200_quant_encode_workspace(C.byref(d), B), dtype=torch.uint8, device=f.device)
-        L.check(lib.var_b200_quant_encode(C.byref(d), f.data_ptr(), B, idx.data_ptr(), L.ptr(fh), work.data_ptr(),
-                                          work.numel(), int(self.search_mode), L.current_stream()), "quant_encode")
+        idx, fh = torch.ops.var_b200.quant_encode(f, *self._qargs(patch_hws), bool(to_fhat), int(self.search_mode))
         if to_fhat:
             return [fh[i] for i in range(len(patch_hws))]
         out, off = [], 0
@@ -147,21 +156,15 @@ class VectorQuantizer2(nn.Module):
     def _flat_idx(self, ms_idx_Bl: List[torch.Tensor]) -> torch.Tensor:
         return torch.cat([t.reshape(-1).to(torch.int64) for t in ms_idx_Bl]).contiguous()
 
+    @L.device_guard
     def _decode(self, ms_idx_Bl, want_input: bool, want_list: bool):
         B = ms_idx_Bl[0].shape[0]
         hws = [_hw(pn) for pn in self.v_patch_nums]
         assert len(ms_idx_Bl) == len(hws)
-        d = self._desc(hws)
-        dev = ms_idx_Bl[0].device
-        H, W = hws[-1]
-        Ltot, l0 = sum(h * w for h, w in hws), hws[0][0] * hws[0][1]
         idx = self._flat_idx(ms_idx_Bl)
-        vin = torch.empty((B, Ltot - l0, self.Cvae), dtype=torch.float32, device=dev) if want_input else None
-        fl = torch.empty((len(hws), B, self.Cvae, H, W), dtype=torch.float32, device=dev) if want_list else None
-        last = torch.empty((B, self.Cvae, H, W), dtype=torch.float32, device=dev)
-        L.check(L.load().var_b200_quant_decode(C.byref(d), idx.data_ptr(), B, L.ptr(vin), L.ptr(fl), last.data_ptr(),
-                                               L.current_stream()), "quant_decode")
-        return vin, fl, last
+        self._check_tokens(idx, self.vocab_size)
+        vin, fl, last = torch.ops.var_b200.quant_decode(idx, B, *self._qargs(hws), bool(want_input), bool(want_list))
+        return (vin if want_input else None), (fl if want_list else None), last
 
     def idxBl_to_var_input(self, gt_ms_idx_Bl: List[torch.Tensor]) -> torch.Tensor:
         """quant.py:169-184 -> [B, L - first_l, Cvae] fp32."""
@@ -174,6 +177,7 @@ class VectorQuantizer2(nn.Module):
         _, fl, last = self._decode(ms_idx_Bl, False, not last_one)
         return last if last_one else [fl[i] for i in range(fl.shape[0])]
 
+    @L.device_guard
     def embed_to_fhat(self, ms_h_BChw: List[torch.Tensor], all_to_max_scale=True, last_one=False):
         """quant.py:107-133 on arbitrary per-scale maps h_si [B, Cvae, ph, pw]. The decode kernel reads them through a
         "virtual codebook" (row = one (scale, image, position) vector, identity indices), so the arithmetic is the
@@ -187,17 +191,12 @@ class VectorQuantizer2(nn.Module):
             assert tuple(h.shape) == (B, self.Cvae, ph, pw), f"{tuple(h.shape)=} != {(B, self.Cvae, ph, pw)}"
         rows = torch.cat([h.detach().float().reshape(B, self.Cvae, -1).transpose(1, 2).reshape(-1, self.Cvae)
                           for h in ms_h_BChw]).contiguous()
-        d = self._desc(hws)
-        d.codebook, d.V = rows.data_ptr(), rows.shape[0]
-        d._keep = d._keep + (rows,)
+        _, w, b, ph, pw, phi_of, resi = self._qargs(hws)
         idx = torch.arange(rows.shape[0], device=dev, dtype=torch.int64)
-        H, W = hws[-1]
-        fl = None if last_one else torch.empty((len(hws), B, self.Cvae, H, W), dtype=torch.float32, device=dev)
-        last = torch.empty((B, self.Cvae, H, W), dtype=torch.float32, device=dev)
-        L.check(L.load().var_b200_quant_decode(C.byref(d), idx.data_ptr(), B, None, L.ptr(fl), last.data_ptr(),
-                                               L.current_stream()), "quant_decode")
+        _, fl, last = torch.ops.var_b200.quant_decode(idx, B, rows, w, b, ph, pw, phi_of, resi, False, not last_one)
         return last if last_one else [fl[i] for i in range(fl.shape[0])]
 
+    @L.device_guard
     def get_next_autoregressive_input(self, si: int, SN: int, f_hat: torch.Tensor, h_BChw: torch.Tensor = None, *,
                                       idx_Bl: torch.Tensor = None, token_major: bool = False):
         """quant.py:187-196. The kernel path takes the sampled indices (h = embedding[idx], models/var.py:177,182);
@@ -205,7 +204,7 @@ class VectorQuantizer2(nn.Module):
         [B, l_next, Cvae] when token_major."""
         hws = [_hw(pn) for pn in self.v_patch_nums]
         assert SN == len(hws)
-        d = self._desc(hws)
+        cb, w, b, ph, pw, phi_of, resi = self._qargs(hws)
         B = f_hat.shape[0]
         assert f_hat.dtype == torch.float32 and f_hat.is_contiguous()
         if idx_Bl is None:
@@ -213,19 +212,8 @@ class VectorQuantizer2(nn.Module):
             # "virtual codebook" whose row b*l + t is h[b, :, t] and an identity index
             if h_BChw is None:
                 raise ValueError("get_next_autoregressive_input needs h_BChw or idx_Bl")
-            ph, pw = hws[si]
-            h_tok = h_BChw.detach().float().reshape(B, self.Cvae, ph * pw).transpose(1, 2).contiguous()
-            d.codebook, d.V = h_tok.data_ptr(), B * ph * pw
-            d._keep = d._keep + (h_tok,)
-            idx_Bl = torch.arange(B * ph * pw, device=f_hat.device, dtype=torch.int64).view(B, ph * pw)
+            cb = h_BChw.detach().float().reshape(B, self.Cvae, ph[si] * pw[si]).transpose(1, 2).reshape(-1, self.Cvae).contiguous()
+            idx_Bl = torch.arange(B * ph[si] * pw[si], device=f_hat.device, dtype=torch.int64).view(B, ph[si] * pw[si])
         idx = idx_Bl.to(torch.int64).contiguous()
-        nxt = None
-        if si != SN - 1:
-            nh, nw = hws[si + 1]
-            shape = (B, nh * nw, self.Cvae) if token_major else (B, self.Cvae, nh, nw)
-            nxt = torch.empty(shape, dtype=torch.float32, device=f_hat.device)
-        L.check(L.load().var_b200_quant_next_input(C.byref(d), si, f_hat.data_ptr(), idx.data_ptr(), B,
-                                                   L.ptr(nxt) if token_major else None,
-                                                   None if token_major else L.ptr(nxt), L.current_stream()),
-                "quant_next_input")
+        nxt = torch.ops.var_b200.quant_next_input(si, f_hat, idx, cb, w, b, ph, pw, phi_of, resi, bool(token_major))
         return f_hat, (nxt if si != SN - 1 else f_hat)

@@ -16,6 +16,20 @@ from .var import VAR
 from .vqvae import VQVAE
 
 
+def _on_var_device(fn):
+    """Run with the model's device current (the kernels launch on that device's current stream)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(var, *args, **kwargs):
+        dev = var._device()
+        if dev.type != "cuda":
+            return fn(var, *args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(var, *args, **kwargs)
+    return wrapper
+
+
 def shard_range(n_items: int, rank: int, world: int):
     """Contiguous, balanced shard [lo, hi) of n_items for `rank` (first n_items % world ranks get one extra)."""
     base, extra = divmod(n_items, world)
@@ -24,6 +38,7 @@ def shard_range(n_items: int, rank: int, world: int):
 
 
 @torch.no_grad()
+@_on_var_device
 def class_log_likelihoods(var: VAR, gt_idx_list: Sequence[torch.Tensor], labels: torch.Tensor, *, class_batch: int = 125,
                           first_pos: int = 0, per_scale: bool = False):
     """sum_t log p(gt_t | class) for every label in `labels` (one image: gt_idx_list[si] is [1, pn^2]).
@@ -34,7 +49,7 @@ def class_log_likelihoods(var: VAR, gt_idx_list: Sequence[torch.Tensor], labels:
     quant = var.vae_quant_proxy[0]
     x_in = quant.idxBl_to_var_input(list(gt_idx_list))  # [1, L-first_l, Cvae], computed once per image
     gt = torch.cat([g.reshape(-1) for g in gt_idx_list]).to(device=dev, dtype=torch.int32).contiguous()
-    labels = labels.reshape(-1).to(device=dev, dtype=torch.int32).contiguous()
+    labels = var._labels_i32(labels.reshape(-1), labels.numel())  # range-checked like the reference's embedding lookup
     K = labels.numel()
     scores = torch.empty(K, dtype=torch.float32, device=dev)
     ps_all = torch.empty((K, len(var.patch_nums)), dtype=torch.float32, device=dev) if per_scale else None
@@ -52,6 +67,7 @@ def class_log_likelihoods(var: VAR, gt_idx_list: Sequence[torch.Tensor], labels:
 
 
 @torch.no_grad()
+@_on_var_device
 def class_log_likelihoods_cfg(var: VAR, gt_idx_list: Sequence[torch.Tensor], labels: torch.Tensor, cfg: float, *,
                               class_batch: int = 64, first_pos: int = 0):
     """CFG-mixed likelihood scores (var_analysis.py:320-346,437-466): the teacher-forced logits of every candidate class
@@ -79,7 +95,7 @@ def class_log_likelihoods_cfg(var: VAR, gt_idx_list: Sequence[torch.Tensor], lab
         return pm.head_logits(x, ada, n, var.L)
 
     lu = logits_of(torch.tensor([var.num_classes], device=dev, dtype=torch.int32))
-    labels = labels.reshape(-1).to(device=dev, dtype=torch.int32).contiguous()
+    labels = var._labels_i32(labels.reshape(-1), labels.numel())  # range-checked like the reference's embedding lookup
     K = labels.numel()
     tok = torch.empty((K, var.L), dtype=torch.float32, device=dev)
     for lo in range(0, K, class_batch):
@@ -95,6 +111,7 @@ def class_log_likelihoods_cfg(var: VAR, gt_idx_list: Sequence[torch.Tensor], lab
 
 
 @torch.no_grad()
+@_on_var_device
 def class_expected_distances(var: VAR, gt_idx_list: Sequence[torch.Tensor], labels: torch.Tensor, cfg: float = 0.0, *,
                              top_k: Optional[int] = None, class_batch: int = 64, first_pos: int = 0):
     """--mode l2_dist of var_analysis.py (:252-256,468-524): per candidate class the negated expected codebook distance
@@ -111,8 +128,7 @@ def class_expected_distances(var: VAR, gt_idx_list: Sequence[torch.Tensor], labe
     x_in = quant.idxBl_to_var_input(list(gt_idx_list))
     gt = torch.cat([g.reshape(-1) for g in gt_idx_list]).to(device=dev, dtype=torch.int32).contiguous()
     S = len(var.patch_nums)
-    E = quant.embedding.weight.detach().float()
-    dists = torch.cdist(E, E, p=2).contiguous()  # var_analysis.py:256, once per call (V x V fp32 = 64 MB, L2 resident)
+    dists, _ = quant.codebook_distances()  # var_analysis.py:256, cached per codebook (V x V fp32 = 64 MB, L2 resident)
     t_row = torch.cat([torch.full((pn * pn,), cfg * (si / (S - 1))) for si, pn in enumerate(var.patch_nums)]).to(dev).float()
     ends = (C.c_int * S)(*[e for _, e in var.begin_ends])
 
@@ -124,7 +140,7 @@ def class_expected_distances(var: VAR, gt_idx_list: Sequence[torch.Tensor], labe
         return pm.head_logits(x, ada, n, var.L)
 
     lu = logits_of(torch.tensor([var.num_classes], device=dev, dtype=torch.int32)) if cfg > 0 else None
-    labels = labels.reshape(-1).to(device=dev, dtype=torch.int32).contiguous()
+    labels = var._labels_i32(labels.reshape(-1), labels.numel())  # range-checked like the reference's embedding lookup
     K = labels.numel()
     tok = torch.empty((K, var.L), dtype=torch.float32, device=dev)
     for lo in range(0, K, class_batch):

@@ -176,10 +176,15 @@ class VAR(nn.Module):
             self._pack_key = key
         return self._packed
 
+    def _device(self) -> torch.device:
+        return self.lvl_1L.device
+
     # ------------------------------------------------------------------ forward passes
     def _labels_i32(self, label_B: torch.Tensor, n: int) -> torch.Tensor:
-        if not label_B.is_cuda and label_B.numel() and (int(label_B.min()) < 0 or int(label_B.max()) > self.num_classes):
-            raise IndexError(f"class label out of range [0, {self.num_classes}] (class_emb, models/var.py:61)")
+        if label_B.numel():  # the reference's embedding lookup raises (CPU) / device-asserts (CUDA) on a bad label
+            lo, hi = (int(v) for v in torch.aminmax(label_B.detach().reshape(-1)))
+            if lo < 0 or hi > self.num_classes:
+                raise IndexError(f"class label out of range [0, {self.num_classes}] (class_emb, models/var.py:61)")
         lab = label_B.reshape(-1).to(device=self.lvl_1L.device, dtype=torch.int32)
         if lab.numel() == 1 and n > 1:
             lab = lab.expand(n)
@@ -188,6 +193,7 @@ class VAR(nn.Module):
         return lab.contiguous()
 
     @torch.no_grad()
+    @L.device_guard
     def get_logits(self, h_or_h_and_residual, cond_BD=None, *, labels: Optional[torch.Tensor] = None):
         """models/var.py:118-124: head(head_nm(h.float(), cond_BD)) -> fp32 logits [B, l, V]. The head's (scale, shift)
         come from `cond_BD` (SiLU -> Linear on the tcgen05 GEMM) or, keyword-only, from `labels`
@@ -209,6 +215,7 @@ class VAR(nn.Module):
         return pm.head_logits(x, ada, B, l)
 
     @torch.no_grad()
+    @L.device_guard
     def forward(self, label_B: torch.LongTensor, x_BLCv_wo_first_l: torch.Tensor, *, return_blocks: bool = False):
         """models/var.py:192-234: teacher-forced logits [B, L, V] fp32."""
         if self.prog_si >= 0:
@@ -218,6 +225,9 @@ class VAR(nn.Module):
         pm = self._model()
         B = x_BLCv_wo_first_l.shape[0]
         dev = self.lvl_1L.device
+        if tuple(x_BLCv_wo_first_l.shape) != (B, self.L - self.first_l, self.Cvae):
+            raise RuntimeError(f"x_BLCv_wo_first_l must be [B, {self.L - self.first_l}, {self.Cvae}], got "
+                               f"{tuple(x_BLCv_wo_first_l.shape)} (models/var.py:204-207)")
         # same RNG side effect and label dropout as the reference (var.py:201)
         drop = torch.rand(B, device=dev) < self.cond_drop_rate
         labels = self._labels_i32(label_B, B)
@@ -233,6 +243,7 @@ class VAR(nn.Module):
         return logits
 
     @torch.no_grad()
+    @L.device_guard
     def autoregressive_infer_cfg(self, B: int, label_B: Optional[Union[int, torch.LongTensor]], g_seed: Optional[int] = None,
                                  cfg=1.5, top_k=0, top_p=0.0, more_smooth=False, *, forced_idx=None, return_trace=False,
                                  decode=True, cuda_graph=False):
@@ -270,6 +281,7 @@ class VAR(nn.Module):
         return (img, trace) if return_trace else img
 
     @torch.no_grad()
+    @L.device_guard
     def inpainting(self, gt_tokens: torch.Tensor, mask: torch.Tensor, label: Optional[Union[int, torch.LongTensor]] = None,
                    g_seed: Optional[int] = None, cfg: float = 1.5, top_k: int = 0, top_p: float = 0.0,
                    more_smooth: bool = False, *, forced_idx=None, return_trace=False, decode=True):
@@ -311,6 +323,7 @@ class VAR(nn.Module):
         return (img, trace) if return_trace else img
 
     @torch.no_grad()
+    @L.device_guard
     def smooth_sampling(self, gt_tokens: torch.Tensor, n: int, label: Optional[Union[int, torch.LongTensor]] = None,
                         g_seed: Optional[int] = None, cfg: float = 1.5, more_smooth: bool = False,
                         neighbor_threshold: Optional[float] = None, *, forced_idx=None, return_trace=False, decode=True):
@@ -343,9 +356,8 @@ class VAR(nn.Module):
         if int(gt.min()) < 0 or int(gt.max()) >= self.V:
             raise ValueError(f"gt_tokens out of range [0, {self.V})")
         quant = self.vae_quant_proxy[0]
-        E = quant.embedding.weight.detach().float()
-        dists = torch.cdist(E, E, p=2).contiguous()                                   # var.py:459-460
-        neighbors = torch.argsort(dists, dim=1)[:, :n].to(torch.int32).contiguous()   # var.py:461-462
+        dists, order = quant.codebook_distances()                                      # var.py:459-462 (cached per codebook)
+        neighbors = order[:, :n].contiguous()
         pm = self._model()
         S = len(self.patch_nums)
         ada = pm.ada_params(labels)
@@ -445,12 +457,16 @@ class VAR(nn.Module):
 
     def _ar_graph_replay(self, B, labels, rng, cfg, top_k, top_p, g_seed=None):
         """Capture-once / replay of _ar_loop. Static inputs: the label buffer; the generator state is registered with
-        the graph so a re-seeded generator drives the replayed Exp(1) draws."""
+        the graph so a re-seeded generator drives the replayed Exp(1) draws.
+        The captured kernels hold raw pointers into the packed model's shared workspaces (KV cache, block scratch) and
+        its bf16 weight copies: the graphs therefore live ON the PackedModel (they die with a repack) and carry the
+        workspace generation they were captured under; any later reallocation of a workspace (a call with another
+        batch size) bumps `ws_gen`, which drops every captured graph before it could replay into freed memory."""
         pm = self._model()
-        key = (id(pm), B, cfg, top_k, top_p, rng is not None)
-        if not hasattr(self, "_graphs"):
-            self._graphs = {}
-        ent = self._graphs.get(key)
+        key = (B, cfg, top_k, top_p, rng is not None)
+        if pm.graph_gen != pm.ws_gen:
+            pm.graphs.clear()
+        ent = pm.graphs.get(key)
         if ent is None:
             static_labels = labels.clone()
             cur_stream = torch.cuda.current_stream()
@@ -460,14 +476,19 @@ class VAR(nn.Module):
                 self._ar_loop(B, static_labels, rng, cfg, top_k, top_p)
             cur_stream.wait_stream(side)
             torch.cuda.synchronize()
+            if pm.graph_gen != pm.ws_gen:  # the warm-up (re)allocated a workspace: older graphs point into freed memory
+                pm.graphs.clear()
+            gen = pm.ws_gen
             graph = torch.cuda.CUDAGraph()
             if rng is not None:
                 graph.register_generator_state(rng)
             with torch.cuda.graph(graph):
                 f_hat = self._ar_loop(B, static_labels, rng, cfg, top_k, top_p)
+            if pm.ws_gen != gen:
+                raise L.VarB200Error("a workspace was reallocated during CUDA-graph capture")
+            pm.graph_gen = gen
             ent = (graph, static_labels, f_hat)
-            self._graphs = {k: v for k, v in self._graphs.items() if k[0] == id(pm)}  # drop graphs of stale weights
-            self._graphs[key] = ent
+            pm.graphs[key] = ent
         graph, static_labels, f_hat = ent
         static_labels.copy_(labels)
         if rng is not None:
@@ -546,7 +567,12 @@ class PackedModel:
         self.w_ada, self.b_ada = t["w_ada"], t["b_ada"]
         self.depth, self.C, self.H, self.V, self.Cvae, self.L, self.first_l = self.var_cfg
         self.ada_ld = self.lib.var_b200_ada_ld(C.byref(m))
+        from . import ops
+        self.handle = ops.register_model(self)  # what the var_b200:: custom ops take as `model`
         self._ws = {}
+        self.ws_gen = 0       # bumped whenever a workspace buffer is (re)allocated
+        self.graphs = {}      # captured AR loops (VAR._ar_graph_replay), valid while graph_gen == ws_gen
+        self.graph_gen = 0
 
     # ---- scratch management: buffers are cached per (tag) and grown on demand
     def _buf(self, tag: str, nbytes: int) -> torch.Tensor:
@@ -554,16 +580,12 @@ class PackedModel:
         if b is None or b.numel() < nbytes:
             b = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=self.dev)
             self._ws[tag] = b
+            self.ws_gen += 1
         return b
 
+    # ---- every call below goes through the torch.library custom-op layer (var_b200/ops.py -> C-ABI)
     def ada_params(self, labels_i32: torch.Tensor) -> torch.Tensor:
-        n = labels_i32.numel()
-        out = torch.empty((n, self.ada_ld), dtype=torch.float32, device=self.dev)
-        wsb = self.lib.var_b200_ada_workspace(C.byref(self.m), n)
-        ws = self._buf("ada", wsb)
-        L.check(self.lib.var_b200_ada_params(C.byref(self.m), labels_i32.data_ptr(), n, out.data_ptr(), ws.data_ptr(),
-                                             ws.numel(), L.current_stream()), "ada_params")
-        return out
+        return torch.ops.var_b200.ada_params(self.handle, labels_i32)
 
     def head_ada_from_cond(self, cond: torch.Tensor) -> torch.Tensor:
         """adaLN table with only the head_nm columns filled: Linear(SiLU(cond)) (basic_var.py:173) on the GEMM kernel."""
@@ -581,21 +603,15 @@ class PackedModel:
         return ada
 
     def embed(self, x_in, n_x, labels_i32, n_seq, l, first_rows, pos0) -> torch.Tensor:
-        out = torch.empty((n_seq, l, self.C), dtype=torch.float32, device=self.dev)
-        l_in = x_in.shape[1] if x_in is not None else 0
-        L.check(self.lib.var_b200_embed(C.byref(self.m), L.ptr(x_in), n_x, l_in, labels_i32.data_ptr(), n_seq, l,
-                                        first_rows, pos0, out.data_ptr(), L.current_stream()), "embed")
-        return out
+        return torch.ops.var_b200.embed(self.handle, x_in, labels_i32, n_seq, l, first_rows, pos0)
 
     def _blocks_ws(self, n_seq, l, score=False):
         fn = self.lib.var_b200_score_workspace if score else self.lib.var_b200_blocks_workspace
         return self._buf("blocks", fn(C.byref(self.m), n_seq, l))
 
     def blocks_teacher(self, x, ada, n_seq, dump=None):
-        ws = self._blocks_ws(n_seq, self.L)
         kv = self._buf("kv_scratch", 2 * n_seq * self.C * self.L * 2)
-        L.check(self.lib.var_b200_blocks(C.byref(self.m), x.data_ptr(), ada.data_ptr(), n_seq, self.L, 0, kv.data_ptr(), 0,
-                                         self.L, L.ptr(dump), ws.data_ptr(), ws.numel(), L.current_stream()), "blocks")
+        torch.ops.var_b200.blocks(self.handle, x, ada, n_seq, self.L, 0, kv, 0, self.L, dump)
 
     def kv_cache(self, n_seq: int) -> torch.Tensor:
         """Preallocated zero-initialised cache [depth][2][n_seq,H,L,64] bf16 (replaces torch.cat, basic_var.py:107-109)."""
@@ -603,46 +619,33 @@ class PackedModel:
         kv = self._ws.get("kv_cache")
         if kv is None or kv.numel() != n:
             self._ws["kv_cache"] = None
+            self.graphs.clear()  # frees the graphs' private pools before the (large) new cache is allocated
             kv = torch.zeros(n, dtype=torch.bfloat16, device=self.dev)
             self._ws["kv_cache"] = kv
+            self.ws_gen += 1
         return kv
 
     def blocks_cached(self, x, ada, n_seq, l, pos0, kv):
-        ws = self._blocks_ws(n_seq, l)
-        stride = 2 * n_seq * self.C * self.L
-        L.check(self.lib.var_b200_blocks(C.byref(self.m), x.data_ptr(), ada.data_ptr(), n_seq, l, pos0, kv.data_ptr(),
-                                         stride, self.L, None, ws.data_ptr(), ws.numel(), L.current_stream()), "blocks")
+        torch.ops.var_b200.blocks(self.handle, x, ada, n_seq, l, pos0, kv, 2 * n_seq * self.C * self.L, self.L, None)
 
     def head_logits(self, x, ada, n_seq, l) -> torch.Tensor:
-        ws = self._blocks_ws(n_seq, l)
-        out = torch.empty((n_seq, l, self.V), dtype=torch.float32, device=self.dev)
-        L.check(self.lib.var_b200_head_logits(C.byref(self.m), x.data_ptr(), ada.data_ptr(), n_seq, l, out.data_ptr(),
-                                              ws.data_ptr(), ws.numel(), L.current_stream()), "head_logits")
-        return out
+        return torch.ops.var_b200.head_logits(self.handle, x, ada, n_seq, l)
 
     def head_score(self, x, ada, n_seq, gt_i32, first_pos=0, per_scale=False, tok_logp=False):
-        ws = self._blocks_ws(n_seq, self.L, score=True)
-        scores = torch.empty(n_seq, dtype=torch.float32, device=self.dev)
-        ps = torch.empty((n_seq, self.m.n_scales), dtype=torch.float32, device=self.dev) if per_scale else None
-        tl = torch.empty((n_seq, self.L), dtype=torch.float32, device=self.dev) if tok_logp else None
-        L.check(self.lib.var_b200_head_score(C.byref(self.m), x.data_ptr(), ada.data_ptr(), n_seq, self.L,
-                                             gt_i32.data_ptr(), gt_i32.numel(), first_pos, scores.data_ptr(), L.ptr(ps),
-                                             L.ptr(tl), ws.data_ptr(), ws.numel(), L.current_stream()), "head_score")
-        return scores, ps, tl
+        scores, ps, tl = torch.ops.var_b200.head_score(self.handle, x, ada, n_seq, gt_i32, first_pos, per_scale, tok_logp)
+        return scores, (ps if per_scale else None), (tl if tok_logp else None)
 
     def sample(self, logits, B, l, t, q, top_k, top_p, mixed=None, use_cfg=True) -> torch.Tensor:
-        idx = torch.empty((B, l), dtype=torch.int64, device=self.dev)
-        L.check(self.lib.var_b200_cfg_topk_sample(logits.data_ptr(), B, l, self.V, int(use_cfg), float(t), q.data_ptr(),
-                                                  int(top_k), float(top_p), idx.data_ptr(), L.ptr(mixed),
-                                                  L.current_stream()), "cfg_topk_sample")
+        idx, mx = torch.ops.var_b200.cfg_topk_sample(logits, B, l, bool(use_cfg), float(t), q, int(top_k), float(top_p),
+                                                     mixed is not None)
+        if mixed is not None:
+            mixed.copy_(mx)
         return idx
 
     def sample_smooth(self, logits, B, l, t, q, top_k, top_p, q_gumbel, tau, logit_mul, codebook, mixed=None):
         """Sampler + more_smooth soft embedding (var.py:178-180): returns (idx [B,l], h [B,l,Cvae])."""
-        idx = torch.empty((B, l), dtype=torch.int64, device=self.dev)
-        h = torch.empty((B, l, codebook.shape[1]), dtype=torch.float32, device=self.dev)
-        L.check(self.lib.var_b200_cfg_topk_sample_smooth(
-            logits.data_ptr(), B, l, self.V, 1, float(t), q.data_ptr(), int(top_k), float(top_p), idx.data_ptr(), L.ptr(mixed),
-            q_gumbel.data_ptr(), float(tau), float(logit_mul), codebook.data_ptr(), int(codebook.shape[1]), h.data_ptr(),
-            L.current_stream()), "cfg_topk_sample_smooth")
+        idx, h, mx = torch.ops.var_b200.cfg_topk_sample_smooth(logits, B, l, float(t), q, int(top_k), float(top_p), q_gumbel,
+                                                               float(tau), float(logit_mul), codebook, mixed is not None)
+        if mixed is not None:
+            mixed.copy_(mx)
         return idx, h
