@@ -11,6 +11,7 @@ from __future__ import annotations
 
 from typing import Tuple
 
+from . import ops  # noqa: F401  (registers the var_b200:: torch.library ops)
 from .quant import VectorQuantizer2
 from .var import VAR
 from .vqvae import VQVAE
