@@ -86,11 +86,25 @@ typedef struct var_b200_gemm_args {
   float* part;       /* [M, VAR_B200_GEMM_EPI_PARTS*ceil(N / var_b200_gemm_tile_n(N)), 2]: (max, sumexp) per row, tile and
                         epilogue warp of the row's lane quarter */
   float* gt_logit;   /* [M] */
+  /* Deferred LayerNorm (see var_b200_blocks). Producer, GATE_RESID only, enabled by ln_a_out != NULL: */
+  void* ln_a_out;         /* bf16 [M,N] = out * (1 + ln_scale[m / rows_per_seq]) */
+  const float* ln_scale;  /* ln_scale[(m / rows_per_seq) * gate_ld + n]: adaLN scale of the LayerNorm that follows */
+  float* ln_part_out;     /* [M, var_b200_gemm_ln_parts(M,N), 2]: partial (sum, sum of squares) of the new out rows */
+  /* Consumer, QKV / GELU_BF16 only, enabled by ln_part_in != NULL: acc + bias is replaced by
+   * rstd_m * (acc - mean_m * ln_u[label]) + ln_v[label], (mean, rstd) over ln_C columns from the partials. */
+  const float* ln_part_in;
+  int ln_parts, ln_C;
+  float ln_eps;
+  const float* ln_u;        /* [n_classes, N] */
+  const float* ln_v;        /* [n_classes, N] (carries the bias) */
+  const int32_t* ln_labels; /* [M / rows_per_seq] */
 } var_b200_gemm_args_t;
 
 VAR_B200_API int var_b200_gemm_bf16(const var_b200_gemm_args_t* args, void* stream);
 /* Tile width (128/192/256) the GEMM uses for a given N. */
 VAR_B200_API int var_b200_gemm_tile_n(int N);
+/* Partials per row that a deferred-LayerNorm producer launch (GATE_RESID with ln_a_out) of this shape writes. */
+VAR_B200_API int var_b200_gemm_ln_parts(int M, int N);
 
 /* Hardware probe used by the test-suite to pin UMMA shared-memory descriptor encodings:
  * D[128,N] = A[128,64] * B, B = [N,64] (K-major) or [64,N] (MN-major). */
@@ -176,6 +190,12 @@ typedef struct var_b200_block_weights {
   const float* b_fc1;   /* [4C] */
   const void* w_fc2;    /* bf16 [C,4C] */
   const float* b_fc2;   /* [C] */
+  /* Deferred-LayerNorm tables (var_b200_ln_tables), per class c in [0, num_classes]; all four NULL = not built, the
+   * block then runs a separate LayerNorm-modulate pass in front of the QKV and fc1 GEMMs. */
+  const float* u_qkv;   /* [num_classes+1, 3C] = W_qkv (1 + scale1_c) */
+  const float* v_qkv;   /* [num_classes+1, 3C] = W_qkv shift1_c + b_qkv */
+  const float* u_fc1;   /* [num_classes+1, 4C] = W_fc1 (1 + scale2_c) */
+  const float* v_fc1;   /* [num_classes+1, 4C] = W_fc1 shift2_c + b_fc1 */
 } var_b200_block_weights_t;
 
 typedef struct var_b200_model {
@@ -221,9 +241,19 @@ VAR_B200_API int var_b200_embed(const var_b200_model_t* m, const float* x_in, in
  * KV-cached step: l = pn^2, pos0 = tokens already cached, kv = [depth][2][n_seq,H,Lmax,64]
  * (kv_layer_stride = 2*n_seq*H*Lmax*64 elements). x_dump: NULL or [depth, n_seq*l, C] copies of x after each block. */
 VAR_B200_API size_t var_b200_blocks_workspace(const var_b200_model_t* m, int n_seq, int l);
-VAR_B200_API int var_b200_blocks(const var_b200_model_t* m, float* x, const float* ada, int n_seq, int l, int pos0,
-                                 void* kv, size_t kv_layer_stride, int Lmax, float* x_dump, void* work,
+/* labels: NULL, or the int32 class of every sequence (the labels `ada` was computed from). With labels and the
+ * blocks' u_/v_ tables present the adaLN LayerNorms (basic_var.py:157-158) cost no pass of their own: the proj / fc2
+ * epilogues emit x_new * (1 + scale_next) in bf16 plus per-row partial sums, and the QKV / fc1 epilogues finish
+ * LN(x)(1+scale)+shift = rstd * (acc - mean * U[label]) + V[label]. Only block 0's first LayerNorm runs as a pass. */
+VAR_B200_API int var_b200_blocks(const var_b200_model_t* m, float* x, const float* ada, const int32_t* labels, int n_seq,
+                                 int l, int pos0, void* kv, size_t kv_layer_stride, int Lmax, float* x_dump, void* work,
                                  size_t work_bytes, void* stream);
+/* Builds block `block`'s deferred-LayerNorm tables from the adaLN table of ALL classes: ada_all[n_cls, ada_ld] =
+ * var_b200_ada_params(labels = 0..n_cls-1). Outputs fp32 [n_cls,3C], [n_cls,3C], [n_cls,4C], [n_cls,4C]; work:
+ * var_b200_ln_tables_workspace(m, n_cls) bytes. Four small GEMMs on the tcgen05 kernel; run once per weight pack. */
+VAR_B200_API size_t var_b200_ln_tables_workspace(const var_b200_model_t* m, int n_cls);
+VAR_B200_API int var_b200_ln_tables(const var_b200_model_t* m, int block, const float* ada_all, int n_cls, float* u_qkv,
+                                    float* v_qkv, float* u_fc1, float* v_fc1, void* work, size_t work_bytes, void* stream);
 
 /* get_logits (var.py:118-124): logits[n_seq*l, V] fp32 = head(LN(x)*(1+scale)+shift). work: blocks workspace. */
 VAR_B200_API int var_b200_head_logits(const var_b200_model_t* m, const float* x, const float* ada, int n_seq, int l,

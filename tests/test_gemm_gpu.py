@@ -117,6 +117,73 @@ def test_gemm_qkv_scatter():
     assert kc[:, :, :pos0].abs().max().item() == 0 and vc[:, :, pos0 + l:].abs().max().item() == 0
 
 
+@pytest.mark.parametrize("n_seq,l,Cdim,K", [(6, 100, 1024, 1024), (3, 256, 1920, 7680), (40, 4, 1024, 4096), (130, 1, 640, 640),
+                                            (5, 169, 2304, 2304)])
+def test_gemm_deferred_layernorm_chain(n_seq, l, Cdim, K):
+    """Deferred LayerNorm (gemm_sm100.cuh, LNF): the GATE_RESID producer's extra outputs (x*(1+scale) in bf16, per-row
+    partial sums) and the GELU / QKV consumers that finish LN(x)(1+s)+sh = rstd*(acc - mean*U) + V, against plain fp32
+    torch math: LayerNorm -> modulate -> Linear (basic_var.py:157-158)."""
+    torch.manual_seed(n_seq * 1000 + l)
+    lib = L.load()
+    M, n_cls, H = n_seq * l, 9, Cdim // 64
+    A = (torch.randn(M, K, device="cuda") / math.sqrt(K)).bfloat16()
+    W = torch.randn(Cdim, K, device="cuda").bfloat16()
+    bias = torch.randn(Cdim, device="cuda")
+    x = torch.randn(M, Cdim, device="cuda") * 3 + 0.7          # residual stream with a DC offset
+    labels = torch.randint(0, n_cls, (n_seq,), device="cuda", dtype=torch.int32)
+    ada_cls = torch.randn(n_cls, 6 * Cdim, device="cuda") * 0.3   # per-class gamma1,gamma2,scale1,scale2,shift1,shift2
+    ada = ada_cls[labels.long()].contiguous()
+    x_ref = x + (_ref(A, W) + bias) * ada[:, Cdim:2 * Cdim].repeat_interleave(l, dim=0)
+    parts = lib.var_b200_gemm_ln_parts(M, Cdim)
+    a_out = torch.full((M, Cdim), float("nan"), device="cuda", dtype=torch.bfloat16)
+    part = torch.full((M, parts, 2), float("nan"), device="cuda")
+    _gemm(A, W, L.EPI_GATE_RESID, bias=bias, out=x, resid=x, gate=ada[:, Cdim:], rows_per_seq=l, gate_ld=6 * Cdim,
+          ln_a_out=a_out, ln_scale=ada[:, 3 * Cdim:], ln_part_out=part)
+    assert (x - x_ref).abs().max().item() < 5e-3
+    scale2 = ada[:, 3 * Cdim:4 * Cdim].repeat_interleave(l, dim=0)
+    shift2 = ada[:, 5 * Cdim:6 * Cdim].repeat_interleave(l, dim=0)
+    assert (a_out.float() - x_ref * (1 + scale2)).abs().max().item() < 2 ** -8 * (x_ref * (1 + scale2)).abs().max().item() + 1e-2
+    assert (part[..., 0].sum(1) - x_ref.sum(1)).abs().max().item() < 2e-2 * math.sqrt(Cdim)
+    assert (part[..., 1].sum(1) - (x_ref * x_ref).sum(1)).abs().max().item() < 1e-4 * (x_ref * x_ref).sum(1).max().item()
+    # reference of the consumer: Linear(LN(x)(1+scale)+shift), everything fp32
+    a_ref = torch.nn.functional.layer_norm(x_ref, (Cdim,), eps=1e-6) * (1 + scale2) + shift2
+    # --- GELU consumer (fc1)
+    N1 = 4 * Cdim
+    W1 = (torch.randn(N1, Cdim, device="cuda") / math.sqrt(Cdim)).bfloat16()
+    b1 = torch.randn(N1, device="cuda") * 0.1
+    u = ((1 + ada_cls[:, 3 * Cdim:4 * Cdim]).bfloat16().float() @ W1.float().t()).contiguous()
+    v = (ada_cls[:, 5 * Cdim:6 * Cdim].bfloat16().float() @ W1.float().t() + b1).contiguous()
+    h = torch.full((M, N1), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _gemm(a_out, W1, L.EPI_GELU_BF16, bias=b1, out=h, rows_per_seq=l, ln_part_in=part, ln_parts=parts, ln_C=Cdim, ln_eps=1e-6,
+          ln_u=u, ln_v=v, ln_labels=labels)
+    pre = a_ref @ W1.float().t() + b1
+    ref_h = torch.nn.functional.gelu(pre, approximate="tanh")
+    # the unfused path rounds the normalised operand to bf16 as well: compare the two error levels
+    unf = torch.nn.functional.gelu(a_ref.bfloat16().float() @ W1.float().t() + b1, approximate="tanh")
+    e_f, e_u = (h.float() - ref_h).abs().max().item(), (unf.bfloat16().float() - ref_h).abs().max().item()
+    print(f"deferred-LN GELU consumer n_seq={n_seq} l={l} C={Cdim}: max err {e_f:.4f} (unfused bf16 operand: {e_u:.4f})")
+    assert torch.isfinite(h.float()).all() and e_f < max(2.5 * e_u, 4e-2)
+    # --- QKV consumer
+    Wq = (torch.randn(3 * Cdim, Cdim, device="cuda") / math.sqrt(Cdim)).bfloat16()
+    bq = torch.randn(3 * Cdim, device="cuda") * 0.1
+    bq[Cdim:2 * Cdim] = 0
+    uq = ((1 + ada_cls[:, 3 * Cdim:4 * Cdim]).bfloat16().float() @ Wq.float().t()).contiguous()
+    vq = (ada_cls[:, 5 * Cdim:6 * Cdim].bfloat16().float() @ Wq.float().t() + bq).contiguous()
+    qs = torch.rand(H, device="cuda") * 5 + 1
+    Lmax, pos0 = l + 7, 3
+    q = torch.zeros(n_seq, H, l, 64, device="cuda", dtype=torch.bfloat16)
+    kc = torch.zeros(n_seq, H, Lmax, 64, device="cuda", dtype=torch.bfloat16)
+    vc = torch.zeros_like(kc)
+    _gemm(a_out, Wq, L.EPI_QKV, bias=bq, q_out=q, k_cache=kc, v_cache=vc, q_scale=qs, C=Cdim, H=H, pos0=pos0, Lmax=Lmax,
+          rows_per_seq=l, ln_part_in=part, ln_parts=parts, ln_C=Cdim, ln_eps=1e-6, ln_u=uq, ln_v=vq, ln_labels=labels)
+    qkv = (a_ref @ Wq.float().t() + bq).view(n_seq, l, 3, H, 64).permute(2, 0, 3, 1, 4)
+    qr = torch.nn.functional.normalize(qkv[0], dim=-1) * qs.view(1, H, 1, 1)
+    kr = torch.nn.functional.normalize(qkv[1], dim=-1)
+    assert (q.float() - qr).abs().max().item() < 6e-2
+    assert (kc[:, :, pos0:pos0 + l].float() - kr).abs().max().item() < 1.5e-2
+    assert (vc[:, :, pos0:pos0 + l].float() - qkv[2]).abs().max().item() < 6e-2
+
+
 def test_gemm_score_partials():
     torch.manual_seed(4)
     M, N, K = 700, 4096, 1024

@@ -267,6 +267,41 @@ def test_var_forward_vs_oracle(depth, shared):
         var(torch.tensor([1, 2, 3]).to(DEV), vin[:2].to(DEV))
 
 
+@pytest.mark.parametrize("depth,shared", [(2, False), (4, False), (2, True)])
+def test_deferred_layernorm_matches_layernorm_pass(depth, shared, monkeypatch):
+    """The deferred-LayerNorm block path (no LayerNorm pass in front of QKV / fc1) against the same model packed with
+    VAR_B200_LNF=0 (separate ln_modulate passes): teacher-forced logits, per-block activations, and the KV-cached loop
+    with forced tokens. Both are bf16 paths of the same fp32 function, so they agree to well inside the tolerance each
+    has against the oracle."""
+    g = golden("quant_forward_d2.npz")
+    _, var = seeded_models(depth=depth, shared_aln=shared, device=DEV)
+    labels, vin = torch.from_numpy(g["labels"]).to(DEV), torch.from_numpy(g["var_input"]).to(DEV)
+    var.repack()
+    assert var._model().ln_fused
+    n0 = L.load().var_b200_launch_count()
+    got_f, acts_f = var(labels, vin, return_blocks=True)
+    n_fused = L.load().var_b200_launch_count() - n0
+    forced = [torch.from_numpy(i) for i in split_scales(golden("ar_d2.npz")["idx"])]
+    lab2 = torch.tensor([7, 481], device=DEV)
+    _, tr_f = var.autoregressive_infer_cfg(2, lab2, g_seed=1, cfg=1.5, top_k=900, forced_idx=forced, return_trace=True, decode=False)
+    monkeypatch.setenv("VAR_B200_LNF", "0")
+    var.repack()
+    assert not var._model().ln_fused
+    n0 = L.load().var_b200_launch_count()
+    got_u, acts_u = var(labels, vin, return_blocks=True)
+    n_unfused = L.load().var_b200_launch_count() - n0
+    _, tr_u = var.autoregressive_infer_cfg(2, lab2, g_seed=1, cfg=1.5, top_k=900, forced_idx=forced, return_trace=True, decode=False)
+    monkeypatch.delenv("VAR_B200_LNF")
+    var.repack()
+    assert n_unfused - n_fused == 2 * depth - 1, (n_fused, n_unfused)   # every LayerNorm pass but block 0's first
+    err = (got_f - got_u).abs().max().item()
+    rel = max(((a - b).abs().max() / b.abs().max()).item() for a, b in zip(acts_f, acts_u))
+    ar = max((a - b).abs().max().item() for a, b in zip(tr_f["logits"], tr_u["logits"]))
+    print(f"deferred LN vs LN pass (depth {depth}, shared_aln={shared}): logits {err:.4f}, blocks rel {rel:.5f}, AR mixed logits {ar:.4f}")
+    assert err < LOGIT_TOL and rel < 1e-2 and ar < 2.5 * LOGIT_TOL
+    assert torch.equal(tr_f["f_hat"], tr_u["f_hat"])
+
+
 def test_class_scores_vs_oracle():
     from var_b200.scoring import class_log_likelihoods
     g = golden("quant_forward_d2.npz")

@@ -60,7 +60,7 @@ void level_ends(const var_b200_model_t* m, int* out) {
 
 // workspace layout shared by blocks / head / score
 struct BlockWs {
-  void *a, *q, *kvscratch, *h, *part, *gtl;
+  void *a, *q, *kvscratch, *h, *part, *gtl, *lnp;
   size_t bytes;
 };
 BlockWs carve_blocks(const var_b200_model_t* m, int n_seq, int l, void* work, size_t cap, bool score) {
@@ -70,6 +70,7 @@ BlockWs carve_blocks(const var_b200_model_t* m, int n_seq, int l, void* work, si
   w.a = cv.take(M * C * 2);        // LN-modulated activations (bf16), reused as attention output
   w.q = cv.take(M * C * 2);        // q (bf16)
   w.h = cv.take(M * 4 * C * 2);    // FFN hidden (bf16)
+  w.lnp = cv.take(M * (size_t)gemm_ln_parts((int)M, m->C) * 8);  // deferred LayerNorm: partial (sum, sumsq) per row
   if (score) {
     const int nt = (m->V + gemm_pick_bn(m->V) - 1) / gemm_pick_bn(m->V);
     w.part = cv.take(M * nt * GEMM_EPI_SUB * 8);  // one (max, sumexp) per row, tile and epilogue sub-warp
@@ -139,9 +140,44 @@ extern "C" size_t var_b200_score_workspace(const var_b200_model_t* m, int n_seq,
   return carve_blocks(m, n_seq, l, nullptr, 0, true).bytes;
 }
 
-extern "C" int var_b200_blocks(const var_b200_model_t* m, float* x, const float* ada, int n_seq, int l, int pos0, void* kv,
-                               size_t kv_layer_stride, int Lmax, float* x_dump, void* work, size_t work_bytes,
-                               void* stream) {
+extern "C" size_t var_b200_ln_tables_workspace(const var_b200_model_t* m, int n_cls) {
+  if (!m || n_cls <= 0) return 0;
+  return align_up((size_t)4 * n_cls * m->C * 2);
+}
+
+extern "C" int var_b200_ln_tables(const var_b200_model_t* m, int block, const float* ada_all, int n_cls, float* u_qkv,
+                                  float* v_qkv, float* u_fc1, float* v_fc1, void* work, size_t work_bytes, void* stream) {
+  int rc = check_model(m);
+  if (rc) return rc;
+  VB_REQUIRE(block >= 0 && block < m->depth && ada_all && n_cls > 0 && u_qkv && v_qkv && u_fc1 && v_fc1 && work,
+             "ln_tables: bad arguments (block=%d n_cls=%d)", block, n_cls);
+  VB_REQUIRE(work_bytes >= var_b200_ln_tables_workspace(m, n_cls), "ln_tables: workspace %zu < %zu", work_bytes,
+             var_b200_ln_tables_workspace(m, n_cls));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int C = m->C, ld = var_b200_ada_ld(m);
+  const float* ab = ada_all + (size_t)6 * block * C;  // gamma1,gamma2,scale1,scale2,shift1,shift2
+  __nv_bfloat16* in = reinterpret_cast<__nv_bfloat16*>(work);
+  rc = ln_table_inputs(ab + 2 * C, ab + 4 * C, ab + 3 * C, ab + 5 * C, ld, in, n_cls, C, st);
+  if (rc) return rc;
+  const var_b200_block_weights_t& bw = m->blocks[block];
+  const size_t plane = (size_t)n_cls * C;
+  struct { const void* A; const void* W; int N; const float* bias; float* out; } g[4] = {
+      {in, bw.w_qkv, 3 * C, nullptr, u_qkv},
+      {in + plane, bw.w_qkv, 3 * C, bw.b_qkv, v_qkv},
+      {in + 2 * plane, bw.w_fc1, 4 * C, nullptr, u_fc1},
+      {in + 3 * plane, bw.w_fc1, 4 * C, bw.b_fc1, v_fc1}};
+  for (auto& t : g) {
+    GemmParams p{};
+    p.M = n_cls; p.N = t.N; p.K = C; p.bias = t.bias; p.out = t.out;
+    rc = gemm_launch(t.A, t.W, p, EPI_BIAS_F32, st);
+    if (rc) return rc;
+  }
+  return VB_OK;
+}
+
+extern "C" int var_b200_blocks(const var_b200_model_t* m, float* x, const float* ada, const int32_t* labels, int n_seq, int l,
+                               int pos0, void* kv, size_t kv_layer_stride, int Lmax, float* x_dump, void* work,
+                               size_t work_bytes, void* stream) {
   int rc = check_model(m);
   if (rc) return rc;
   VB_REQUIRE(x && ada && kv && work && n_seq > 0 && l > 0, "blocks: bad arguments");
@@ -157,18 +193,35 @@ extern "C" int var_b200_blocks(const var_b200_model_t* m, float* x, const float*
   at.q_log2 = m->attn_q_log2;
   level_ends(m, at.level_end);
   VB_REQUIRE(pos0 + l <= at.level_end[m->n_scales - 1], "blocks: positions beyond the pyramid");
+  // Deferred LayerNorm (gemm_sm100.cuh, LNF): possible when the caller names the class of every sequence and every block
+  // carries its per-class tables. Buffers: w.a = LN1 operand / attention output, w.q = q, then the LN2 operand (q is
+  // dead once the attention has run), w.lnp = the row statistics' partial sums (one consumer at a time).
+  bool fused = labels != nullptr;
+  for (int i = 0; i < m->depth && fused; ++i) {
+    const var_b200_block_weights_t& bw = m->blocks[i];
+    fused = bw.u_qkv && bw.v_qkv && bw.u_fc1 && bw.v_fc1;
+  }
+  const int ln_parts = gemm_ln_parts(M, C);
+  auto consume = [&](GemmParams& p, const float* u, const float* v) {
+    p.ln_part_in = reinterpret_cast<const float2*>(w.lnp); p.ln_parts = ln_parts; p.ln_C = C; p.ln_eps = m->norm_eps;
+    p.ln_u = u; p.ln_v = v; p.ln_labels = labels; p.rows_per_seq = l;
+  };
   for (int i = 0; i < m->depth; ++i) {
     const var_b200_block_weights_t& bw = m->blocks[i];
     const float* ab = ada + (size_t)6 * i * C;  // gamma1,gamma2,scale1,scale2,shift1,shift2
     __nv_bfloat16* kc = reinterpret_cast<__nv_bfloat16*>(kv) + (size_t)i * kv_layer_stride;
     __nv_bfloat16* vc = kc + cache_elems;
     // x += gamma1 * proj(attn(LN(x)(1+scale1)+shift1))
-    rc = ln_modulate(x, ab + 2 * C, ab + 4 * C, ld, l, w.a, M, C, m->norm_eps, st);
-    if (rc) return rc;
+    const bool ln1_deferred = fused && i > 0;  // the previous block's fc2 epilogue left x*(1+scale1) in w.a
+    if (!ln1_deferred) {
+      rc = ln_modulate(x, ab + 2 * C, ab + 4 * C, ld, l, w.a, M, C, m->norm_eps, st);
+      if (rc) return rc;
+    }
     GemmParams p{};
     p.M = M; p.N = 3 * C; p.K = C; p.bias = bw.b_qkv;
     p.q_out = reinterpret_cast<__nv_bfloat16*>(w.q); p.k_cache = kc; p.v_cache = vc; p.q_scale = bw.q_scale;
     p.C = C; p.H = m->H; p.pos0 = pos0; p.Lmax = Lmax; p.rows_per_seq = l;
+    if (ln1_deferred) consume(p, bw.u_qkv, bw.v_qkv);
     rc = gemm_launch(w.a, bw.w_qkv, p, EPI_QKV, st);
     if (rc) return rc;
     at.q = w.q; at.k = kc; at.v = vc; at.out = w.a;
@@ -176,18 +229,29 @@ extern "C" int var_b200_blocks(const var_b200_model_t* m, float* x, const float*
     if (rc) return rc;
     p = GemmParams{};
     p.M = M; p.N = C; p.K = C; p.bias = bw.b_proj; p.out = x; p.resid = x; p.gate = ab; p.rows_per_seq = l; p.gate_ld = ld;
+    if (fused) {
+      p.ln_a_out = reinterpret_cast<__nv_bfloat16*>(w.q); p.ln_scale = ab + 3 * C;
+      p.ln_part_out = reinterpret_cast<float2*>(w.lnp);
+    }
     rc = gemm_launch(w.a, bw.w_proj, p, EPI_GATE_RESID, st);
     if (rc) return rc;
     // x += gamma2 * fc2(gelu(fc1(LN(x)(1+scale2)+shift2)))
-    rc = ln_modulate(x, ab + 3 * C, ab + 5 * C, ld, l, w.a, M, C, m->norm_eps, st);
-    if (rc) return rc;
+    if (!fused) {
+      rc = ln_modulate(x, ab + 3 * C, ab + 5 * C, ld, l, w.a, M, C, m->norm_eps, st);
+      if (rc) return rc;
+    }
     p = GemmParams{};
     p.M = M; p.N = 4 * C; p.K = C; p.bias = bw.b_fc1; p.out = w.h;
-    rc = gemm_launch(w.a, bw.w_fc1, p, EPI_GELU_BF16, st);
+    if (fused) consume(p, bw.u_fc1, bw.v_fc1);
+    rc = gemm_launch(fused ? w.q : w.a, bw.w_fc1, p, EPI_GELU_BF16, st);
     if (rc) return rc;
     p = GemmParams{};
     p.M = M; p.N = C; p.K = 4 * C; p.bias = bw.b_fc2; p.out = x; p.resid = x; p.gate = ab + C; p.rows_per_seq = l;
     p.gate_ld = ld;
+    if (fused && i + 1 < m->depth) {  // operand and statistics of the NEXT block's first LayerNorm
+      p.ln_a_out = reinterpret_cast<__nv_bfloat16*>(w.a); p.ln_scale = ab + 6 * C + 2 * C;
+      p.ln_part_out = reinterpret_cast<float2*>(w.lnp);
+    }
     rc = gemm_launch(w.h, bw.w_fc2, p, EPI_GATE_RESID, st);
     if (rc) return rc;
     if (x_dump)

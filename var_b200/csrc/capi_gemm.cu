@@ -24,10 +24,17 @@ extern "C" int var_b200_gemm_bf16(const var_b200_gemm_args_t* a, void* stream) {
   p.gt_mod = a->gt_mod > 0 ? a->gt_mod : a->M;
   p.part = reinterpret_cast<float2*>(a->part);
   p.gt_logit = a->gt_logit;
+  p.ln_a_out = reinterpret_cast<__nv_bfloat16*>(a->ln_a_out);
+  p.ln_scale = a->ln_scale;
+  p.ln_part_out = reinterpret_cast<float2*>(a->ln_part_out);
+  p.ln_part_in = reinterpret_cast<const float2*>(a->ln_part_in);
+  p.ln_parts = a->ln_parts; p.ln_C = a->ln_C; p.ln_eps = a->ln_eps;
+  p.ln_u = a->ln_u; p.ln_v = a->ln_v; p.ln_labels = a->ln_labels;
   return gemm_launch(a->A, a->W, p, a->epilogue, (cudaStream_t)stream, a->force_bn);
 }
 
 extern "C" int var_b200_gemm_tile_n(int N) { return vb::gemm_pick_bn(N); }
+extern "C" int var_b200_gemm_ln_parts(int M, int N) { return (M > 0 && N > 0) ? vb::gemm_ln_parts(M, N) : 0; }
 
 extern "C" int var_b200_conv3x3_nhwc(const void* x, const void* w_packed, const float* bias, const void* resid, void* out,
                                      int B, int H, int W, int Cin, int Cout, void* stream) {

@@ -99,6 +99,32 @@ int ln_modulate(const float* x, const float* scale, const float* shift, int ada_
 }
 
 // ------------------------------------------------------------------------------------------------
+// A operands of the four table GEMMs of var_b200_ln_tables: bf16(1 + scale1), bf16(shift1), bf16(1 + scale2), bf16(shift2)
+// ------------------------------------------------------------------------------------------------
+__global__ void ln_table_inputs_kernel(const float* __restrict__ s1, const float* __restrict__ h1, const float* __restrict__ s2,
+                                       const float* __restrict__ h2, int ada_ld, __nv_bfloat16* __restrict__ out, int n, int C) {
+  const int r = blockIdx.x;
+  const size_t plane = (size_t)n * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const size_t src = (size_t)r * ada_ld + c, dst = (size_t)r * C + c;
+    out[dst] = __float2bfloat16(1.f + s1[src]);
+    out[plane + dst] = __float2bfloat16(h1[src]);
+    out[2 * plane + dst] = __float2bfloat16(1.f + s2[src]);
+    out[3 * plane + dst] = __float2bfloat16(h2[src]);
+  }
+}
+
+int ln_table_inputs(const float* s1, const float* h1, const float* s2, const float* h2, int ada_ld, void* out, int n, int C,
+                    cudaStream_t st) {
+  VB_REQUIRE(s1 && h1 && s2 && h2 && out && n > 0 && C > 0, "ln_table_inputs: bad arguments");
+  vb::ProfScope prof_scope(vb::PK_OTHER, st);
+  ln_table_inputs_kernel<<<n, 256, 0, st>>>(s1, h1, s2, h2, ada_ld, reinterpret_cast<__nv_bfloat16*>(out), n, C);
+  VB_CUDA_CHECK(cudaGetLastError());
+  vb::count_launch();
+  return VB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // cond = class_emb[label] ; A = bf16(SiLU(cond))      (basic_var.py:146-147 input of every ada_lin)
 // ------------------------------------------------------------------------------------------------
 __global__ void cond_silu_kernel(const float* __restrict__ class_emb, const int* __restrict__ labels,

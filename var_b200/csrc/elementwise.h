@@ -14,6 +14,9 @@ struct AttnLevelsPOD {
 // out bf16[M,C] = LN(x[M,C]) * (1 + scale[m / rows_per_seq]) + shift[m / rows_per_seq]; scale/shift row stride ada_ld
 int ln_modulate(const float* x, const float* scale, const float* shift, int ada_ld, int rows_per_seq, void* out, int M,
                 int C, float eps, cudaStream_t st);
+// deferred-LayerNorm table inputs: out[4][n, C] bf16 = (1 + s1, h1, 1 + s2, h2) for columns taken from ada[n, ada_ld]
+int ln_table_inputs(const float* s1, const float* h1, const float* s2, const float* h2, int ada_ld, void* out, int n, int C,
+                    cudaStream_t st);
 // out bf16[n_seq,C] = SiLU(class_emb[labels])
 int cond_silu(const float* class_emb, const int* labels, void* out, int n_seq, int C, cudaStream_t st);
 int expand_shared_aln(const float* shared, int shared_ld, const float* gss, float* ada, int ada_ld, int depth, int C,

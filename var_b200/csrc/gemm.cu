@@ -7,7 +7,7 @@
 
 namespace vb {
 
-template <int BN, int EPI, int CTAS>
+template <int BN, int EPI, int CTAS, bool LNF = false>
 static int launch_one(const void* A, const void* W, const GemmParams& p, cudaStream_t st) {
   using Cfg = GemmCfg<BN, CTAS>;
   CUtensorMap tmA, tmB;
@@ -34,7 +34,7 @@ static int launch_one(const void* A, const void* W, const GemmParams& p, cudaStr
     int r = make_tmap_bf16_sw128(&tmB, W, 2, dims, str, box);
     if (r) return r;
   }
-  auto kern = gemm_bf16_kernel<BN, EPI, CTAS>;
+  auto kern = gemm_bf16_kernel<BN, EPI, CTAS, LNF>;
   static SmemAttrCache attr_cache;  // per instantiation, per device
   if (ensure_dyn_smem(attr_cache, Cfg::SMEM_BYTES, kern)) return VB_ERR_CUDA;
   const int m_tiles = (p.M + GEMM_BM * CTAS - 1) / (GEMM_BM * CTAS);
@@ -66,9 +66,12 @@ static int launch_bn(const void* A, const void* W, const GemmParams& p, int epi,
   switch (epi) {
     case EPI_BIAS_F32: return launch_one<BN, EPI_BIAS_F32, CTAS>(A, W, p, st);
     case EPI_BIAS_BF16: return launch_one<BN, EPI_BIAS_BF16, CTAS>(A, W, p, st);
-    case EPI_GELU_BF16: return launch_one<BN, EPI_GELU_BF16, CTAS>(A, W, p, st);
-    case EPI_GATE_RESID: return launch_one<BN, EPI_GATE_RESID, CTAS>(A, W, p, st);
-    case EPI_QKV: return launch_one<BN, EPI_QKV, CTAS>(A, W, p, st);
+    case EPI_GELU_BF16:
+      return p.ln_part_in ? launch_one<BN, EPI_GELU_BF16, CTAS, true>(A, W, p, st) : launch_one<BN, EPI_GELU_BF16, CTAS>(A, W, p, st);
+    case EPI_GATE_RESID:
+      return p.ln_a_out ? launch_one<BN, EPI_GATE_RESID, CTAS, true>(A, W, p, st) : launch_one<BN, EPI_GATE_RESID, CTAS>(A, W, p, st);
+    case EPI_QKV:
+      return p.ln_part_in ? launch_one<BN, EPI_QKV, CTAS, true>(A, W, p, st) : launch_one<BN, EPI_QKV, CTAS>(A, W, p, st);
     case EPI_SCORE: return launch_one<BN, EPI_SCORE, CTAS>(A, W, p, st);
   }
   set_error("gemm: unknown epilogue %d", epi);
@@ -102,6 +105,11 @@ static int gemm_pick_bn_mn(int M, int N, int epi) {
   return bn;
 }
 
+int gemm_ln_parts(int M, int N) {
+  const int bn = gemm_pick_bn_mn(M, N, EPI_GATE_RESID);
+  return (N + bn - 1) / bn * GEMM_EPI_SUB;
+}
+
 int gemm_launch(const void* A, const void* W, const GemmParams& p, int epi, cudaStream_t st, int force_bn) {
   VB_REQUIRE(A && W, "gemm: null operand");
   VB_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
@@ -119,8 +127,16 @@ int gemm_launch(const void* A, const void* W, const GemmParams& p, int epi, cuda
     VB_REQUIRE(p.gt && p.part && p.gt_logit && p.bias && p.gt_mod > 0, "gemm/score: null pointer or gt_mod=%d", p.gt_mod);
   } else {
     VB_REQUIRE(p.out, "gemm: null output");
-    if (epi == EPI_GATE_RESID)
+    if (epi == EPI_GATE_RESID) {
       VB_REQUIRE(p.resid && p.gate && p.rows_per_seq > 0, "gemm/gate: null pointer or rows_per_seq=%d", p.rows_per_seq);
+      VB_REQUIRE(!p.ln_a_out || (p.ln_scale && p.ln_part_out && !force_bn), "gemm/gate: deferred LayerNorm needs ln_scale, "
+                 "ln_part_out and the automatic tile width");
+    }
+  }
+  if (p.ln_part_in) {
+    VB_REQUIRE(epi == EPI_QKV || epi == EPI_GELU_BF16, "gemm: deferred LayerNorm input is built for the QKV and GELU epilogues");
+    VB_REQUIRE(p.ln_u && p.ln_v && p.ln_labels && p.ln_parts > 0 && p.ln_C > 0 && p.rows_per_seq > 0,
+               "gemm: deferred LayerNorm needs ln_u, ln_v, ln_labels, ln_parts, ln_C, rows_per_seq");
   }
   const int bn = force_bn ? (force_bn & 0xffff) : gemm_pick_bn_mn(p.M, p.N, epi);
   // CTA-pair tiles (256 x BN) unless the problem is a single 128-row tile or the caller forces 1-CTA (bit 16)

@@ -46,11 +46,24 @@ struct GemmParams {
   // activation tensor [B, conv_H, conv_W, Cin] seen through a 4-D tensor map, row m = pixel ((b*H + y)*W + x);
   // K = 9 taps x conv_kpt 64-channel blocks (weights packed [N, 9, conv_kpt*64], zero padded). 0 = plain GEMM.
   int conv_kpt, conv_H, conv_W;
+  // Deferred LayerNorm (gemm_sm100.cuh, LNF). Producer side (EPI_GATE_RESID, set ln_a_out):
+  __nv_bfloat16* ln_a_out;  // [M,N] bf16 = x_new * (1 + ln_scale[seq]): the A operand of the next QKV / fc1 GEMM
+  const float* ln_scale;    // the NEXT LayerNorm's adaLN scale, ln_scale[(m / rows_per_seq) * gate_ld + n]
+  float2* ln_part_out;      // [M, gemm_ln_parts(M,N)] partial (sum, sum of squares) of x_new per row, tile and sub-warp
+  // Consumer side (EPI_QKV / EPI_GELU_BF16, set ln_part_in): out = rstd*(acc - mean*U[label]) + V[label] replaces acc + bias
+  const float2* ln_part_in;
+  int ln_parts, ln_C;       // partials per row, row length the statistics are taken over
+  float ln_eps;
+  const float* ln_u;        // [n_classes, N]: W (1 + scale_class)
+  const float* ln_v;        // [n_classes, N]: W shift_class + bias
+  const int* ln_labels;     // [M / rows_per_seq] class of every sequence
   int conv_cin;  // true channel count of the activation tensor (the tensor map's innermost extent; tails read as zeros)
 };
 
 // Tile width the launcher will use for a given N (needed to size EPI_SCORE partials: n_tiles = ceil(N / bn)).
 int gemm_pick_bn(int N);
+// Partials per row a deferred-LayerNorm producer launch (EPI_GATE_RESID with ln_a_out) of this shape writes.
+int gemm_ln_parts(int M, int N);
 // A: [M,K] bf16 row-major, W: [N,K] bf16 row-major (nn.Linear layout). force_bn: 0 = auto, else 128/192/256,
 // optionally | 0x10000 to force the 1-CTA kernel (the default is the CTA-pair kernel whenever M > 128).
 int gemm_launch(const void* A, const void* W, const GemmParams& p, int epi, cudaStream_t st, int force_bn = 0);

@@ -32,7 +32,12 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024;  // +1024: manual alignment slack
 };
 
-template <int BN, int EPI, int CTAS>
+// LNF = deferred LayerNorm ("adaLN without a LayerNorm pass"):
+//   producer (EPI_GATE_RESID): besides x_new the epilogue writes a' = bf16(x_new * (1 + scale_next[seq])) and, per row,
+//     tile and epilogue sub-warp, the partial (sum, sum of squares) of x_new;
+//   consumer (EPI_QKV, EPI_GELU_BF16): the GEMM runs on a' and the epilogue finishes the normalisation,
+//     LN(x)(1+s)+sh = rstd*(a'W^T - mean*U[label]) + V[label], U = W(1+s), V = W sh + bias precomputed per class.
+template <int BN, int EPI, int CTAS, bool LNF = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using Cfg = GemmCfg<BN, CTAS>;
@@ -170,8 +175,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      mbar_wait(tfull_bar(as), aphase);
-      tc_fence_after();
       const int row = m_blk * TILE_M + rank * GEMM_BM + quarter * 32 + lane;
       const bool row_ok = row < p.M;
       const uint32_t taddr = tmem_base + as * 256 + ((uint32_t)(quarter * 32) << 16);
@@ -181,6 +184,31 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                    (warp - 2) * (32 * EPI_STG_LD);
       const int rsub = lane >> 2, cg = lane & 3;
       const int row_w0 = m_blk * TILE_M + rank * GEMM_BM + quarter * 32;  // first row of this warp
+      // deferred LayerNorm, consumer side: this thread's row statistics from the producer's partial sums, and the
+      // rows of the per-class tables U, V (requested before the accumulator barrier: their latency overlaps the wait)
+      float ln_rstd = 1.f, ln_nmr = 0.f;  // rstd and -mean * rstd
+      const float* ln_urow = nullptr;
+      const float* ln_vrow = nullptr;
+      if constexpr (LNF && (EPI == EPI_QKV || EPI == EPI_GELU_BF16)) {
+        const int rr = row_ok ? row : p.M - 1;
+        const float2* pp = p.ln_part_in + (size_t)rr * p.ln_parts;
+        float sx = 0.f, sxx = 0.f;
+        for (int j = 0; j < p.ln_parts; ++j) {
+          const float2 t = __ldg(pp + j);
+          sx += t.x;
+          sxx += t.y;
+        }
+        const float inv_c = 1.f / (float)p.ln_C;
+        const float mean = sx * inv_c;
+        ln_rstd = rsqrtf(fmaxf(sxx * inv_c - mean * mean, 0.f) + p.ln_eps);
+        ln_nmr = -mean * ln_rstd;
+        const size_t lab = (size_t)__ldg(p.ln_labels + rr / p.rows_per_seq) * p.N;
+        ln_urow = p.ln_u + lab;
+        ln_vrow = p.ln_v + lab;
+      }
+
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
 
       if constexpr (EPI == EPI_QKV) {
         // destination row offsets of the four row groups this lane stores (fixed for the whole tile)
@@ -203,20 +231,46 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int which = n0 / p.C;  // 0 q, 1 k, 2 v
           const int head = (n0 - which * p.C) >> 6;
           const float qs = which == 0 ? __ldg(p.q_scale + head) : 1.f;
-          float4 bq[16];  // the chunk's bias, requested while the accumulator is still on its way from TMEM
-#pragma unroll
-          for (int j = 0; j < 16; ++j) bq[j] = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j);
-          tmem_ld_wait_dep(v);
-          tmem_ld_wait_dep(v + 32);
           float2 ss2 = make_float2(0.f, 0.f);
+          if constexpr (LNF) {
+            // qkv = rstd * acc - mean * rstd * U[label] + V[label]   (V holds W sh + [q_bias, 0, v_bias]); 32 columns at a time
+            const float2 r2 = make_float2(ln_rstd, ln_rstd), m2 = make_float2(ln_nmr, ln_nmr);
 #pragma unroll
-          for (int j = 0; j < 64; j += 4) {
-            const float4 b = bq[j >> 2];
-            const float2 a0 = __fadd2_rn(make_float2(v[j], v[j + 1]), make_float2(b.x, b.y));
-            const float2 a1 = __fadd2_rn(make_float2(v[j + 2], v[j + 3]), make_float2(b.z, b.w));
-            ss2 = __ffma2_rn(a0, a0, ss2);
-            ss2 = __ffma2_rn(a1, a1, ss2);
-            v[j] = a0.x; v[j + 1] = a0.y; v[j + 2] = a1.x; v[j + 3] = a1.y;
+            for (int hh = 0; hh < 2; ++hh) {
+              float4 uq[8], vq[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                uq[j] = __ldg(reinterpret_cast<const float4*>(ln_urow + n0 + 32 * hh) + j);
+                vq[j] = __ldg(reinterpret_cast<const float4*>(ln_vrow + n0 + 32 * hh) + j);
+              }
+              tmem_ld_wait_dep(v + 32 * hh);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int e = 32 * hh + 4 * j;
+                const float2 t0 = __ffma2_rn(m2, make_float2(uq[j].x, uq[j].y), make_float2(vq[j].x, vq[j].y));
+                const float2 t1 = __ffma2_rn(m2, make_float2(uq[j].z, uq[j].w), make_float2(vq[j].z, vq[j].w));
+                const float2 a0 = __ffma2_rn(make_float2(v[e], v[e + 1]), r2, t0);
+                const float2 a1 = __ffma2_rn(make_float2(v[e + 2], v[e + 3]), r2, t1);
+                ss2 = __ffma2_rn(a0, a0, ss2);
+                ss2 = __ffma2_rn(a1, a1, ss2);
+                v[e] = a0.x; v[e + 1] = a0.y; v[e + 2] = a1.x; v[e + 3] = a1.y;
+              }
+            }
+          } else {
+            float4 bq[16];  // the chunk's bias, requested while the accumulator is still on its way from TMEM
+#pragma unroll
+            for (int j = 0; j < 16; ++j) bq[j] = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j);
+            tmem_ld_wait_dep(v);
+            tmem_ld_wait_dep(v + 32);
+#pragma unroll
+            for (int j = 0; j < 64; j += 4) {
+              const float4 b = bq[j >> 2];
+              const float2 a0 = __fadd2_rn(make_float2(v[j], v[j + 1]), make_float2(b.x, b.y));
+              const float2 a1 = __fadd2_rn(make_float2(v[j + 2], v[j + 3]), make_float2(b.z, b.w));
+              ss2 = __ffma2_rn(a0, a0, ss2);
+              ss2 = __ffma2_rn(a1, a1, ss2);
+              v[j] = a0.x; v[j + 1] = a0.y; v[j + 2] = a1.x; v[j + 3] = a1.y;
+            }
           }
           float mul = 1.f;
           if (which < 2) mul = qs / fmaxf(sqrtf(ss2.x + ss2.y), 1e-12f);  // F.normalize(dim=-1), eps 1e-12
@@ -291,6 +345,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int seqs[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) seqs[i] = (row_w0 + rsub + 8 * i) / p.rows_per_seq;
+        float ln_s1[4] = {0.f, 0.f, 0.f, 0.f}, ln_s2[4] = {0.f, 0.f, 0.f, 0.f};  // LNF: partial row sums of x_new
 #pragma unroll 1
         for (int c = half; c < BN / 32; c += GEMM_EPI_SUB) {
           const int n0 = n_base + c * 32;
@@ -308,13 +363,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             __syncwarp();
             const int col = n0 + 16 * h2 + 4 * cg;
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-            float4 g4[4], rs4[4];
+            float4 g4[4], rs4[4], sc4[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {  // all loads before the stores: resid may alias out
               const int rg = row_w0 + rsub + 8 * i;
               if (rg < p.M) {
                 g4[i] = __ldg(reinterpret_cast<const float4*>(p.gate + (size_t)seqs[i] * p.gate_ld + col));
                 rs4[i] = *reinterpret_cast<const float4*>(p.resid + (size_t)rg * p.N + col);
+                if constexpr (LNF) sc4[i] = __ldg(reinterpret_cast<const float4*>(p.ln_scale + (size_t)seqs[i] * p.gate_ld + col));
               }
             }
 #pragma unroll
@@ -324,12 +380,34 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               if (rg < p.M) {
                 const float4 a = *reinterpret_cast<const float4*>(stg + r * EPI_STG_LD + 4 * cg);
                 const float4 rs = rs4[i];
-                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)rg * p.N + col) =
-                    make_float4(fmaf(a.x + b4.x, g4[i].x, rs.x), fmaf(a.y + b4.y, g4[i].y, rs.y),
-                                fmaf(a.z + b4.z, g4[i].z, rs.z), fmaf(a.w + b4.w, g4[i].w, rs.w));
+                const float4 o = make_float4(fmaf(a.x + b4.x, g4[i].x, rs.x), fmaf(a.y + b4.y, g4[i].y, rs.y),
+                                             fmaf(a.z + b4.z, g4[i].z, rs.z), fmaf(a.w + b4.w, g4[i].w, rs.w));
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)rg * p.N + col) = o;
+                if constexpr (LNF) {
+                  ln_s1[i] += (o.x + o.y) + (o.z + o.w);
+                  ln_s2[i] += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
+                  const float4 sc = sc4[i];
+                  *reinterpret_cast<uint2*>(p.ln_a_out + (size_t)rg * p.N + col) =
+                      make_uint2(pack_bf16x2(fmaf(o.x, sc.x, o.x), fmaf(o.y, sc.y, o.y)),
+                                 pack_bf16x2(fmaf(o.z, sc.z, o.z), fmaf(o.w, sc.w, o.w)));
+                }
               }
             }
             __syncwarp();
+          }
+        }
+        if constexpr (LNF) {
+          // one partial (sum, sum of squares) per row, N tile and sub-warp; a sub-warp without columns writes zeros
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float a = ln_s1[i], b = ln_s2[i];
+            a += __shfl_xor_sync(0xffffffffu, a, 1);
+            b += __shfl_xor_sync(0xffffffffu, b, 1);
+            a += __shfl_xor_sync(0xffffffffu, a, 2);
+            b += __shfl_xor_sync(0xffffffffu, b, 2);
+            const int rg = row_w0 + rsub + 8 * i;
+            if (cg == 0 && rg < p.M)
+              p.ln_part_out[(size_t)rg * (n_tiles * GEMM_EPI_SUB) + n_blk * GEMM_EPI_SUB + half] = make_float2(a, b);
           }
         }
       } else {
@@ -342,7 +420,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < NCH; ++i)
           if ((half + GEMM_EPI_SUB * i) * 32 < BN && n_base + (half + GEMM_EPI_SUB * i) * 32 < p.N) n_valid = i + 1;
-        const bool has_bias = p.bias != nullptr;
+        const bool has_bias = !(LNF && EPI == EPI_GELU_BF16) && p.bias != nullptr;
         if (n_valid > 0) {
           __syncwarp();
           tmem_ld_32x32(taddr + half * 32, vbuf[0]);
@@ -356,6 +434,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (i >= n_valid) break;
           float* v = vbuf[i & 1];
           const int n0 = n_base + (half + GEMM_EPI_SUB * i) * 32;
+          float4 uq[4], vq[4];  // LNF: 16 columns of the class's U / V rows (L1/L2 hits, shared by the tile's warps)
+          if constexpr (LNF && EPI == EPI_GELU_BF16) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uq[j] = __ldg(reinterpret_cast<const float4*>(ln_urow + n0) + j);
+              vq[j] = __ldg(reinterpret_cast<const float4*>(ln_vrow + n0) + j);
+            }
+          }
           tmem_ld_wait_dep(v);
           if (i + 1 < n_valid) {
             __syncwarp();
@@ -371,6 +457,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int j = 0; j < 8; ++j) {
               const float4 b = bbuf[i & 1][j];
               v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+            }
+          }
+          if constexpr (LNF && EPI == EPI_GELU_BF16) {  // fc1 pre-activation = rstd * acc - mean * rstd * U + V
+            const float2 r2 = make_float2(ln_rstd, ln_rstd), m2 = make_float2(ln_nmr, ln_nmr);
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int e = 16 * hh + 4 * j;
+                const float2 t0 = __ffma2_rn(m2, make_float2(uq[j].x, uq[j].y), make_float2(vq[j].x, vq[j].y));
+                const float2 t1 = __ffma2_rn(m2, make_float2(uq[j].z, uq[j].w), make_float2(vq[j].z, vq[j].w));
+                const float2 a0 = __ffma2_rn(make_float2(v[e], v[e + 1]), r2, t0);
+                const float2 a1 = __ffma2_rn(make_float2(v[e + 2], v[e + 3]), r2, t1);
+                v[e] = a0.x; v[e + 1] = a0.y; v[e + 2] = a1.x; v[e + 3] = a1.y;
+              }
+              if (hh == 0) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  uq[j] = __ldg(reinterpret_cast<const float4*>(ln_urow + n0 + 16) + j);
+                  vq[j] = __ldg(reinterpret_cast<const float4*>(ln_vrow + n0 + 16) + j);
+                }
+              }
             }
           }
           if (!row_ok) {

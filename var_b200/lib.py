@@ -32,6 +32,9 @@ class GemmArgs(C.Structure):
         ("q_out", C.c_void_p), ("k_cache", C.c_void_p), ("v_cache", C.c_void_p), ("q_scale", C.c_void_p),
         ("C", C.c_int), ("H", C.c_int), ("pos0", C.c_int), ("Lmax", C.c_int),
         ("gt", C.c_void_p), ("gt_mod", C.c_int), ("part", C.c_void_p), ("gt_logit", C.c_void_p),
+        ("ln_a_out", C.c_void_p), ("ln_scale", C.c_void_p), ("ln_part_out", C.c_void_p), ("ln_part_in", C.c_void_p),
+        ("ln_parts", C.c_int), ("ln_C", C.c_int), ("ln_eps", C.c_float), ("ln_u", C.c_void_p), ("ln_v", C.c_void_p),
+        ("ln_labels", C.c_void_p),
     ]
 
 
@@ -49,7 +52,8 @@ class QuantDesc(C.Structure):
 
 class BlockWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
-                ("w_qkv", "b_qkv", "q_scale", "w_proj", "b_proj", "w_fc1", "b_fc1", "w_fc2", "b_fc2")]
+                ("w_qkv", "b_qkv", "q_scale", "w_proj", "b_proj", "w_fc1", "b_fc1", "w_fc2", "b_fc2",
+                 "u_qkv", "v_qkv", "u_fc1", "v_fc1")]
 
 
 class ModelDesc(C.Structure):
@@ -97,6 +101,7 @@ def _declare(lib: C.CDLL) -> None:
     sigs = {
         "var_b200_gemm_bf16": [C.POINTER(GemmArgs), vp],
         "var_b200_gemm_tile_n": [i32],
+        "var_b200_gemm_ln_parts": [i32, i32],
         "var_b200_umma_probe": [vp, vp, vp, i32, i32, vp],
     }
     sigs.update(_EXTRA_SIGS(vp, i32, i64, f32))
@@ -108,6 +113,8 @@ def _declare(lib: C.CDLL) -> None:
         fn = getattr(lib, name)
         fn.argtypes = [C.POINTER(ModelDesc), i32] if name == "var_b200_ada_workspace" else [C.POINTER(ModelDesc), i32, i32]
         fn.restype = C.c_size_t
+    lib.var_b200_ln_tables_workspace.argtypes = [C.POINTER(ModelDesc), i32]
+    lib.var_b200_ln_tables_workspace.restype = C.c_size_t
     lib.var_b200_gn_workspace.argtypes = [i32, i32, i32, i32]
     lib.var_b200_gn_workspace.restype = C.c_size_t
     lib.var_b200_quant_encode_workspace.argtypes = [C.POINTER(QuantDesc), i32]
@@ -142,7 +149,8 @@ def _EXTRA_SIGS(vp, i32, i64, f32):
         "var_b200_ada_ld": [C.POINTER(ModelDesc)],
         "var_b200_ada_params": [C.POINTER(ModelDesc), vp, i32, vp, vp, sz, vp],
         "var_b200_embed": [C.POINTER(ModelDesc), vp, i32, i32, vp, i32, i32, i32, i32, vp, vp],
-        "var_b200_blocks": [C.POINTER(ModelDesc), vp, vp, i32, i32, i32, vp, sz, i32, vp, vp, sz, vp],
+        "var_b200_blocks": [C.POINTER(ModelDesc), vp, vp, vp, i32, i32, i32, vp, sz, i32, vp, vp, sz, vp],
+        "var_b200_ln_tables": [C.POINTER(ModelDesc), i32, vp, i32, vp, vp, vp, vp, vp, sz, vp],
         "var_b200_head_logits": [C.POINTER(ModelDesc), vp, vp, i32, i32, vp, vp, sz, vp],
         "var_b200_head_score": [C.POINTER(ModelDesc), vp, vp, i32, i32, vp, i32, i32, vp, vp, vp, vp, sz, vp],
     }

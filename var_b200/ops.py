@@ -86,14 +86,15 @@ def embed(model: int, x_in: Optional[torch.Tensor], labels: torch.Tensor, n_seq:
     return out
 
 
-@_op("blocks(int model, Tensor(a!) x, Tensor ada, int n_seq, int l, int pos0, Tensor(b!) kv, int kv_layer_stride, "
-     "int Lmax, Tensor(c!)? dump) -> ()")
-def blocks(model: int, x: torch.Tensor, ada: torch.Tensor, n_seq: int, l: int, pos0: int, kv: torch.Tensor,
-           kv_layer_stride: int, Lmax: int, dump: Optional[torch.Tensor]) -> None:
-    """var_b200_blocks: all AdaLNSelfAttn blocks in place on x (basic_var.py:152-159), K/V appended at pos0."""
+@_op("blocks(int model, Tensor(a!) x, Tensor ada, Tensor? labels, int n_seq, int l, int pos0, Tensor(b!) kv, "
+     "int kv_layer_stride, int Lmax, Tensor(c!)? dump) -> ()")
+def blocks(model: int, x: torch.Tensor, ada: torch.Tensor, labels: Optional[torch.Tensor], n_seq: int, l: int, pos0: int,
+           kv: torch.Tensor, kv_layer_stride: int, Lmax: int, dump: Optional[torch.Tensor]) -> None:
+    """var_b200_blocks: all AdaLNSelfAttn blocks in place on x (basic_var.py:152-159), K/V appended at pos0. labels
+    (int32, the classes `ada` was computed from) enable the deferred-LayerNorm path (no LayerNorm pass per block)."""
     pm = _pm(model)
     ws = pm._blocks_ws(n_seq, l)
-    L.check(pm.lib.var_b200_blocks(C.byref(pm.m), x.data_ptr(), ada.data_ptr(), n_seq, l, pos0, kv.data_ptr(),
+    L.check(pm.lib.var_b200_blocks(C.byref(pm.m), x.data_ptr(), ada.data_ptr(), L.ptr(labels), n_seq, l, pos0, kv.data_ptr(),
                                    kv_layer_stride, Lmax, L.ptr(dump), ws.data_ptr(), ws.numel(), L.current_stream()),
             "blocks")
 

@@ -58,7 +58,7 @@ def class_log_likelihoods(var: VAR, gt_idx_list: Sequence[torch.Tensor], labels:
         n = lab.numel()
         x = pm.embed(x_in, 1, lab, n, var.L, var.first_l, 0)
         ada = pm.ada_params(lab)
-        pm.blocks_teacher(x, ada, n)
+        pm.blocks_teacher(x, ada, n, labels=lab)
         s, ps, _ = pm.head_score(x, ada, n, gt, first_pos=first_pos, per_scale=per_scale)
         scores[lo:lo + n] = s
         if per_scale:
@@ -91,7 +91,7 @@ def class_log_likelihoods_cfg(var: VAR, gt_idx_list: Sequence[torch.Tensor], lab
         n = lab.numel()
         x = pm.embed(x_in, 1, lab, n, var.L, var.first_l, 0)
         ada = pm.ada_params(lab)
-        pm.blocks_teacher(x, ada, n)
+        pm.blocks_teacher(x, ada, n, labels=lab)
         return pm.head_logits(x, ada, n, var.L)
 
     lu = logits_of(torch.tensor([var.num_classes], device=dev, dtype=torch.int32))
@@ -136,7 +136,7 @@ def class_expected_distances(var: VAR, gt_idx_list: Sequence[torch.Tensor], labe
         n = lab.numel()
         x = pm.embed(x_in, 1, lab, n, var.L, var.first_l, 0)
         ada = pm.ada_params(lab)
-        pm.blocks_teacher(x, ada, n)
+        pm.blocks_teacher(x, ada, n, labels=lab)
         return pm.head_logits(x, ada, n, var.L)
 
     lu = logits_of(torch.tensor([var.num_classes], device=dev, dtype=torch.int32)) if cfg > 0 else None

@@ -236,7 +236,7 @@ class VAR(nn.Module):
         x = pm.embed(x_in, B, labels, B, self.L, self.first_l, 0)
         ada = pm.ada_params(labels)
         dump = torch.empty((self.depth, B * self.L, self.C), device=dev) if return_blocks else None
-        pm.blocks_teacher(x, ada, B, dump)
+        pm.blocks_teacher(x, ada, B, dump, labels)
         logits = pm.head_logits(x, ada, B, self.L)
         if return_blocks:
             return logits, [dump[i].view(B, self.L, self.C) for i in range(self.depth)]
@@ -372,7 +372,7 @@ class VAR(nn.Module):
             l = pn * pn
             ratio = si / self.num_stages_minus_1 if self.num_stages_minus_1 > 0 else 0.0
             x = pm.embed(None, 0, labels, 2 * B, l, self.first_l, 0) if si == 0 else pm.embed(nxt, B, labels, 2 * B, l, 0, cur)
-            pm.blocks_cached(x, ada, 2 * B, l, cur, kv)
+            pm.blocks_cached(x, ada, 2 * B, l, cur, kv, labels)
             logits = pm.head_logits(x, ada, 2 * B, l)
             idx = torch.empty((B, l), dtype=torch.int64, device=dev)
             lp = torch.empty((B, l), dtype=torch.float32, device=dev)
@@ -422,7 +422,7 @@ class VAR(nn.Module):
                 x = pm.embed(None, 0, labels, 2 * B, l, self.first_l, 0)
             else:
                 x = pm.embed(nxt, B, labels, 2 * B, l, 0, cur)
-            pm.blocks_cached(x, ada, 2 * B, l, cur, kv)
+            pm.blocks_cached(x, ada, 2 * B, l, cur, kv, labels)
             if all_kept is not None and all_kept[si]:
                 idx, mixed = gt_tokens[:, cur:cur + l].contiguous(), None
             else:
@@ -573,6 +573,35 @@ class PackedModel:
         self.ws_gen = 0       # bumped whenever a workspace buffer is (re)allocated
         self.graphs = {}      # captured AR loops (VAR._ar_graph_replay), valid while graph_gen == ws_gen
         self.graph_gen = 0
+        self.ln_fused = False
+        self._build_ln_tables(var)
+
+    def _build_ln_tables(self, var: "VAR"):
+        """Deferred LayerNorm (include/var_b200.h: var_b200_ln_tables): per block and class the vectors
+        U = W (1 + scale_c), V = W shift_c + bias for the QKV and fc1 GEMMs, so that no LayerNorm pass runs in front of
+        them (basic_var.py:157-158). 14 C floats per block and class (d30: 3.2 GB for the 1001 classes); skipped when
+        VAR_B200_LNF=0 or the tables would exceed VAR_B200_LNF_MAX_GB (default 12): the blocks then run the LayerNorm
+        pass as before."""
+        import os
+        n_cls = var.num_classes + 1
+        per_block = n_cls * 14 * self.C
+        if os.environ.get("VAR_B200_LNF", "1") == "0" or \
+                per_block * self.depth * 4 > float(os.environ.get("VAR_B200_LNF_MAX_GB", "12")) * 2 ** 30:
+            return
+        with torch.cuda.device(self.dev):
+            labels = torch.arange(n_cls, dtype=torch.int32, device=self.dev)
+            ada_all = self.ada_params(labels)
+            ws = torch.empty(self.lib.var_b200_ln_tables_workspace(C.byref(self.m), n_cls), dtype=torch.uint8, device=self.dev)
+            for i in range(self.depth):
+                t = torch.empty(per_block, dtype=torch.float32, device=self.dev)
+                parts = torch.split(t, [n_cls * 3 * self.C, n_cls * 3 * self.C, n_cls * 4 * self.C, n_cls * 4 * self.C])
+                L.check(self.lib.var_b200_ln_tables(C.byref(self.m), i, ada_all.data_ptr(), n_cls, *[p.data_ptr() for p in parts],
+                                                    ws.data_ptr(), ws.numel(), L.current_stream()), "ln_tables")
+                for name, p in zip(("u_qkv", "v_qkv", "u_fc1", "v_fc1"), parts):
+                    setattr(self.blocks_arr[i], name, p.data_ptr())
+                self._keep.append(t)
+            torch.cuda.current_stream().synchronize()  # ws / ada_all are released on return
+        self.ln_fused = True
 
     # ---- scratch management: buffers are cached per (tag) and grown on demand
     def _buf(self, tag: str, nbytes: int) -> torch.Tensor:
@@ -609,9 +638,9 @@ class PackedModel:
         fn = self.lib.var_b200_score_workspace if score else self.lib.var_b200_blocks_workspace
         return self._buf("blocks", fn(C.byref(self.m), n_seq, l))
 
-    def blocks_teacher(self, x, ada, n_seq, dump=None):
+    def blocks_teacher(self, x, ada, n_seq, dump=None, labels=None):
         kv = self._buf("kv_scratch", 2 * n_seq * self.C * self.L * 2)
-        torch.ops.var_b200.blocks(self.handle, x, ada, n_seq, self.L, 0, kv, 0, self.L, dump)
+        torch.ops.var_b200.blocks(self.handle, x, ada, labels if self.ln_fused else None, n_seq, self.L, 0, kv, 0, self.L, dump)
 
     def kv_cache(self, n_seq: int) -> torch.Tensor:
         """Preallocated zero-initialised cache [depth][2][n_seq,H,L,64] bf16 (replaces torch.cat, basic_var.py:107-109)."""
@@ -625,8 +654,9 @@ class PackedModel:
             self.ws_gen += 1
         return kv
 
-    def blocks_cached(self, x, ada, n_seq, l, pos0, kv):
-        torch.ops.var_b200.blocks(self.handle, x, ada, n_seq, l, pos0, kv, 2 * n_seq * self.C * self.L, self.L, None)
+    def blocks_cached(self, x, ada, n_seq, l, pos0, kv, labels=None):
+        torch.ops.var_b200.blocks(self.handle, x, ada, labels if self.ln_fused else None, n_seq, l, pos0, kv,
+                                  2 * n_seq * self.C * self.L, self.L, None)
 
     def head_logits(self, x, ada, n_seq, l) -> torch.Tensor:
         return torch.ops.var_b200.head_logits(self.handle, x, ada, n_seq, l)
