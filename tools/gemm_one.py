@@ -43,12 +43,30 @@ def base(N, K, epi):
     return a, (A, W, bias)
 
 
+# deferred-LayerNorm inputs (gemm_sm100.cuh LNF): partial row sums as a producer launch writes them, class tables
+N_CLS = 1001
+parts = lib.var_b200_gemm_ln_parts(M, Cd)
+ln_part = torch.rand(M, parts, 2, device="cuda")
+ln_part[..., 1] += 2.0
+labels = torch.randint(0, N_CLS, (n_seq,), device="cuda", dtype=torch.int32)
+
+
+def consumer(a, N):
+    u = torch.randn(N_CLS, N, device="cuda") * 0.1
+    v = torch.randn(N_CLS, N, device="cuda") * 0.1
+    a.ln_part_in, a.ln_parts, a.ln_C, a.ln_eps = ln_part.data_ptr(), parts, Cd, 1e-6
+    a.ln_u, a.ln_v, a.ln_labels, a.rows_per_seq = u.data_ptr(), v.data_ptr(), labels.data_ptr(), l
+    return u, v
+
+
 # fc1 (GELU)
 a, keep = base(4 * Cd, Cd, L.EPI_GELU_BF16)
 out = torch.empty(M, 4 * Cd, device="cuda", dtype=torch.bfloat16)
 a.out = out.data_ptr()
 timed(a, 2.0 * M * 4 * Cd * Cd, "fc1  (GELU -> bf16)")
-del out
+keep2 = consumer(a, 4 * Cd)
+timed(a, 2.0 * M * 4 * Cd * Cd, "fc1  + deferred LN")
+del out, keep2
 # qkv
 a, keep = base(3 * Cd, Cd, L.EPI_QKV)
 q = torch.empty(n_seq, H, l, 64, device="cuda", dtype=torch.bfloat16)
@@ -58,7 +76,9 @@ scale = torch.full((H,), 4.0, device="cuda")
 a.q_out, a.k_cache, a.v_cache, a.q_scale = q.data_ptr(), kc.data_ptr(), vc.data_ptr(), scale.data_ptr()
 a.C, a.H, a.pos0, a.Lmax, a.rows_per_seq = Cd, H, Lmax - l, Lmax, l
 timed(a, 2.0 * M * 3 * Cd * Cd, "qkv  (norm/scale/scatter)")
-del q, kc, vc
+keep2 = consumer(a, 3 * Cd)
+timed(a, 2.0 * M * 3 * Cd * Cd, "qkv  + deferred LN")
+del q, kc, vc, keep2
 # proj / fc2 (gate + residual, fp32 in place)
 for K, name in ((Cd, "proj (resid + g*acc, fp32)"), (4 * Cd, "fc2  (resid + g*acc, fp32)")):
     a, keep = base(Cd, K, L.EPI_GATE_RESID)
@@ -66,4 +86,9 @@ for K, name in ((Cd, "proj (resid + g*acc, fp32)"), (4 * Cd, "fc2  (resid + g*ac
     gate = torch.ones(n_seq, Cd, device="cuda")
     a.out, a.resid, a.gate, a.gate_ld, a.rows_per_seq = x.data_ptr(), x.data_ptr(), gate.data_ptr(), Cd, l
     timed(a, 2.0 * M * Cd * K, name)
+    if not FORCE_BN:
+        a_out = torch.empty(M, Cd, device="cuda", dtype=torch.bfloat16)
+        a.ln_a_out, a.ln_scale, a.ln_part_out = a_out.data_ptr(), gate.data_ptr(), ln_part.data_ptr()
+        timed(a, 2.0 * M * Cd * K, name[:4] + " + deferred LN outputs")
+        del a_out
     del x

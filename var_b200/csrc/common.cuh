@@ -78,6 +78,16 @@ static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
 }
+// Call-free variant for code that runs after setmaxnreg.inc: ptxas gives up its per-region register allocation as soon
+// as the region contains a function call (the out-of-line retry loop above, printf), and falls back to the smallest
+// register count of the kernel. Same bounded wait, trap without the message.
+__device__ __forceinline__ void mbar_wait_nocall(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_parked(bar, parity)) {
+    if (clock64() - t0 > 8000000000LL) __trap();
+  }
+}
 
 // generic-proxy writes to smem -> visible to the async proxy (TMA / UMMA operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
@@ -324,6 +334,16 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t* r)
 // named barrier among `nthreads` threads (ids 1..15; 0 is __syncthreads)
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// Warpgroup-wide register reallocation (all four warps of the warpgroup execute it): dec releases registers to the
+// SM's pool, inc blocks until the requested count is available. Counts are multiples of 8 in [24, 256].
+template <uint32_t N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <uint32_t N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 

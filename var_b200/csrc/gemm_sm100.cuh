@@ -18,7 +18,13 @@ namespace vb {
 constexpr int GEMM_BM = 128;        // accumulator rows per CTA (TMEM lanes)
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_EPI_WARPS = 4 * GEMM_EPI_SUB;
-constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;   // warp0: TMA, warp1: MMA + TMEM owner, then the epilogue warps
+// Warp roles by warpgroup: warpgroup 0 = {TMA producer, MMA issuer + TMEM owner, two idle warps}, warpgroups 1.. = the
+// epilogue warps. The split is on warpgroup boundaries so that setmaxnreg can move registers from the service
+// warpgroup (few live values) to the epilogue warps: with 12 warps every SM sub-partition hosts 3 of them, which caps
+// a uniform allocation at 168 registers per thread; after the hand-over the epilogue warps own 224.
+constexpr int GEMM_SVC_WARPS = 4;
+constexpr int GEMM_THREADS = 32 * (GEMM_SVC_WARPS + GEMM_EPI_WARPS);
+constexpr uint32_t GEMM_SVC_REGS = 72, GEMM_EPI_REGS = 216;  // 128 * svc + 256 * epi == 384 * 168 (the CTA's pool)
 constexpr int EPI_STG_LD = 20;      // floats per staging row (16 + 4 pad: 16-byte aligned)
 
 template <int BN, int CTAS>
@@ -85,6 +91,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
+  // The two register regimes never merge again: each branch carries its own copy of the teardown and returns.
+  auto teardown = [&]() {
+    tc_fence_before();
+    if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();
+    if (warp == 1) {
+      tc_fence_after();
+      if constexpr (CTAS == 2) tmem_dealloc_cg2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
+    }
+  };
+  if (warp < GEMM_SVC_WARPS) {
+  setmaxnreg_dec<GEMM_SVC_REGS>();
   if (warp == 0) {
     // ------------------------------ TMA producer (every CTA loads its own operand slices) ------------------------------
     if (lane == 0) {
@@ -162,14 +179,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if constexpr (CTAS == 2) umma_commit_cg2_mc(tfull_bar(as), 3); else umma_commit(tfull_bar(as));
       }
     }
+  }
+  teardown();
+  return;
   } else {
+    setmaxnreg_inc<GEMM_EPI_REGS>();
     // ------------------------------ epilogue warps ------------------------------
     // GEMM_EPI_SUB warps per TMEM lane quarter, dealing the column chunks of the tile round-robin between them. The
     // epilogue is latency bound (one accumulator row per thread): the GELU epilogue costs a K=1024 tile 14 % (d16 fc1:
     // 1206 TFLOP/s against 1408 with the plain bias epilogue, tools/gemm_k_sweep.py); a third warp per quarter wins
     // back only 2-3 % of that and loses it again in the QKV epilogue (see gemm.h).
     const int quarter = warp & 3;          // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;      // which of the GEMM_EPI_SUB warps of that quarter (chunk c = half, half+SUB, ..)
+    const int half = (warp - GEMM_SVC_WARPS) >> 2;  // which of the GEMM_EPI_SUB warps of that quarter (chunk c = half, half+SUB, ..)
     int it = 0;
     for (int tile = cid; tile < total_tiles; tile += ncl, ++it) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
@@ -181,7 +202,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int n_base = n_blk * BN;
       // private 32 x 20-float staging tile of this warp (transposes accumulator rows into coalesced global accesses)
       float* stg = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + STAGES * Cfg::STAGE_BYTES) +
-                   (warp - 2) * (32 * EPI_STG_LD);
+                   (warp - GEMM_SVC_WARPS) * (32 * EPI_STG_LD);
       const int rsub = lane >> 2, cg = lane & 3;
       const int row_w0 = m_blk * TILE_M + rank * GEMM_BM + quarter * 32;  // first row of this warp
       // deferred LayerNorm, consumer side: this thread's row statistics from the producer's partial sums, and the
@@ -206,8 +227,35 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         ln_urow = p.ln_u + lab;
         ln_vrow = p.ln_v + lab;
       }
+      // 32 columns of the row's U / V vectors. The window is consumed at the very start of a chunk (two FMAs per element)
+      // and refilled for the next chunk right away, so the L2 latency of the refill hides behind the rest of the chunk's
+      // work (GELU / normalisation, packing, stores); the first window of a tile is requested before the accumulator
+      // barrier. No second register set is needed.
+      float4 lq_u[8], lq_v[8];
+      auto ln_fetch = [&](int col) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          lq_u[j] = __ldg(reinterpret_cast<const float4*>(ln_urow + col) + j);
+          lq_v[j] = __ldg(reinterpret_cast<const float4*>(ln_vrow + col) + j);
+        }
+      };
+      auto ln_apply = [&](float* v) {  // v[0..32) = rstd * v - mean * rstd * U + V
+        const float2 r2 = make_float2(ln_rstd, ln_rstd), m2 = make_float2(ln_nmr, ln_nmr);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float2 t0 = __ffma2_rn(m2, make_float2(lq_u[j].x, lq_u[j].y), make_float2(lq_v[j].x, lq_v[j].y));
+          const float2 t1 = __ffma2_rn(m2, make_float2(lq_u[j].z, lq_u[j].w), make_float2(lq_v[j].z, lq_v[j].w));
+          const float2 a0 = __ffma2_rn(make_float2(v[4 * j], v[4 * j + 1]), r2, t0);
+          const float2 a1 = __ffma2_rn(make_float2(v[4 * j + 2], v[4 * j + 3]), r2, t1);
+          v[4 * j] = a0.x; v[4 * j + 1] = a0.y; v[4 * j + 2] = a1.x; v[4 * j + 3] = a1.y;
+        }
+      };
+      if constexpr (LNF && (EPI == EPI_QKV || EPI == EPI_GELU_BF16)) {
+        const int first = n_base + half * (EPI == EPI_QKV ? 64 : 32);
+        if (first < p.N) ln_fetch(first);
+      }
 
-      mbar_wait(tfull_bar(as), aphase);
+      mbar_wait_nocall(tfull_bar(as), aphase);
       tc_fence_after();
 
       if constexpr (EPI == EPI_QKV) {
@@ -234,28 +282,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           float2 ss2 = make_float2(0.f, 0.f);
           if constexpr (LNF) {
             // qkv = rstd * acc - mean * rstd * U[label] + V[label]   (V holds W sh + [q_bias, 0, v_bias]); 32 columns at a time
-            const float2 r2 = make_float2(ln_rstd, ln_rstd), m2 = make_float2(ln_nmr, ln_nmr);
+            tmem_ld_wait_dep(v);
+            ln_apply(v);
+            ln_fetch(n0 + 32);
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              float4 uq[8], vq[8];
+            for (int j = 0; j < 32; j += 2) ss2 = __ffma2_rn(make_float2(v[j], v[j + 1]), make_float2(v[j], v[j + 1]), ss2);
+            tmem_ld_wait_dep(v + 32);
+            ln_apply(v + 32);
+            if (c + GEMM_EPI_SUB < BN / 64 && n0 + GEMM_EPI_SUB * 64 < p.N) ln_fetch(n0 + GEMM_EPI_SUB * 64);  // next chunk
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                uq[j] = __ldg(reinterpret_cast<const float4*>(ln_urow + n0 + 32 * hh) + j);
-                vq[j] = __ldg(reinterpret_cast<const float4*>(ln_vrow + n0 + 32 * hh) + j);
-              }
-              tmem_ld_wait_dep(v + 32 * hh);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const int e = 32 * hh + 4 * j;
-                const float2 t0 = __ffma2_rn(m2, make_float2(uq[j].x, uq[j].y), make_float2(vq[j].x, vq[j].y));
-                const float2 t1 = __ffma2_rn(m2, make_float2(uq[j].z, uq[j].w), make_float2(vq[j].z, vq[j].w));
-                const float2 a0 = __ffma2_rn(make_float2(v[e], v[e + 1]), r2, t0);
-                const float2 a1 = __ffma2_rn(make_float2(v[e + 2], v[e + 3]), r2, t1);
-                ss2 = __ffma2_rn(a0, a0, ss2);
-                ss2 = __ffma2_rn(a1, a1, ss2);
-                v[e] = a0.x; v[e + 1] = a0.y; v[e + 2] = a1.x; v[e + 3] = a1.y;
-              }
-            }
+            for (int j = 32; j < 64; j += 2) ss2 = __ffma2_rn(make_float2(v[j], v[j + 1]), make_float2(v[j], v[j + 1]), ss2);
           } else {
             float4 bq[16];  // the chunk's bias, requested while the accumulator is still on its way from TMEM
 #pragma unroll
@@ -434,14 +470,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (i >= n_valid) break;
           float* v = vbuf[i & 1];
           const int n0 = n_base + (half + GEMM_EPI_SUB * i) * 32;
-          float4 uq[4], vq[4];  // LNF: 16 columns of the class's U / V rows (L1/L2 hits, shared by the tile's warps)
-          if constexpr (LNF && EPI == EPI_GELU_BF16) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uq[j] = __ldg(reinterpret_cast<const float4*>(ln_urow + n0) + j);
-              vq[j] = __ldg(reinterpret_cast<const float4*>(ln_vrow + n0) + j);
-            }
-          }
           tmem_ld_wait_dep(v);
           if (i + 1 < n_valid) {
             __syncwarp();
@@ -460,26 +488,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
           if constexpr (LNF && EPI == EPI_GELU_BF16) {  // fc1 pre-activation = rstd * acc - mean * rstd * U + V
-            const float2 r2 = make_float2(ln_rstd, ln_rstd), m2 = make_float2(ln_nmr, ln_nmr);
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int e = 16 * hh + 4 * j;
-                const float2 t0 = __ffma2_rn(m2, make_float2(uq[j].x, uq[j].y), make_float2(vq[j].x, vq[j].y));
-                const float2 t1 = __ffma2_rn(m2, make_float2(uq[j].z, uq[j].w), make_float2(vq[j].z, vq[j].w));
-                const float2 a0 = __ffma2_rn(make_float2(v[e], v[e + 1]), r2, t0);
-                const float2 a1 = __ffma2_rn(make_float2(v[e + 2], v[e + 3]), r2, t1);
-                v[e] = a0.x; v[e + 1] = a0.y; v[e + 2] = a1.x; v[e + 3] = a1.y;
-              }
-              if (hh == 0) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  uq[j] = __ldg(reinterpret_cast<const float4*>(ln_urow + n0 + 16) + j);
-                  vq[j] = __ldg(reinterpret_cast<const float4*>(ln_vrow + n0 + 16) + j);
-                }
-              }
-            }
+            ln_apply(v);
+            if (i + 1 < n_valid) ln_fetch(n0 + GEMM_EPI_SUB * 32);
           }
           if (!row_ok) {
             // nothing to store for rows beyond M (the TMEM loads stay warp-convergent)
@@ -541,13 +551,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         else mbar_arrive_relaxed(tempty_bar(as));
       }
     }
-  }
-
-  tc_fence_before();
-  if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    if constexpr (CTAS == 2) tmem_dealloc_cg2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
+    teardown();
   }
 }
 
