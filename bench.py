@@ -36,6 +36,7 @@ PATCH_NUMS = (1, 2, 3, 4, 5, 6, 8, 10, 13, 16)
 PATCH_NUMS_512 = (1, 2, 3, 4, 6, 9, 13, 18, 24, 32)  # utils/arg_util.py:246-247
 L_SEQ = sum(p * p for p in PATCH_NUMS)
 V, CVAE = 4096, 32
+PROFILE_STEP = os.environ.get("VAR_B200_PROFILE_STEP") == "1"
 
 
 def flops_per_seq(depth: int, patch_nums=PATCH_NUMS) -> float:
@@ -406,8 +407,20 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n0 = lib.var_b200_launch_count()
         e0.record(st)
-        for _ in range(steps):
+        for i in range(steps):
+            # VAR_B200_PROFILE_STEP=1: cudaProfilerStart/Stop around the last timed step, for
+            # `ncu --profile-from-start off` launch lists (a number printed by a run under ncu is never a bench value)
+            prof = PROFILE_STEP and i == steps - 1
+            if prof:
+                if wl["kind"] == "sample":
+                    from var_b200 import var as _var_mod
+                    _var_mod._PROFILE_ARMED[0] = True  # the AR loop starts the profiler at VAR_B200_PROFILE_FROM_SCALE
+                else:
+                    torch.cuda.profiler.start()
             step()
+            if prof:
+                torch.cuda.synchronize()
+                torch.cuda.profiler.stop()
         e1.record(st)
         barrier()
         launches = lib.var_b200_launch_count() - n0

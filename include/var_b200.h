@@ -305,6 +305,17 @@ VAR_B200_API int var_b200_scale_sums(const float* tok_logp, int n_seq, int L, in
 VAR_B200_API int var_b200_conv3x3_nhwc(const void* x, const void* w_packed, const float* bias, const void* resid,
                                        void* out, int B, int H, int W, int Cin, int Cout, void* stream);
 
+/* Downsample2x of the VQVAE encoder (models/basic_vae.py:31-37): zero pad (0,1,0,1) then 3x3 / stride 2 / no padding, as
+ * the same implicit GEMM with a traversal stride of 2 in the TMA box. x: bf16 [B,H,W,Cin] -> out: bf16 [B,H/2,W/2,Cout].
+ * Requires H, W even, W/2 | 128 or W/2 == 128, (H/2 * W/2) % 128 == 0, Cout % 32 == 0, Cin % 8 == 0. */
+VAR_B200_API int var_b200_conv3x3_s2_nhwc(const void* x, const void* w_packed, const float* bias, void* out, int B, int H,
+                                          int W, int Cin, int Cout, void* stream);
+/* 1x1 convolution (basic_vae.py:47 nin_shortcut, :69-71 AttnBlock, vqvae.py:48-49 quant_conv / post_quant_conv) = GEMM
+ * over the pixels. x: bf16 [n_pixels, Cin]; w_packed: bf16 [Cout, ceil(Cin/64)*64] (columns >= Cin zero); resid: NULL or
+ * bf16 [n_pixels, Cout]; out: bf16 [n_pixels, Cout]. Requires Cin % 8 == 0, Cout % 32 == 0. */
+VAR_B200_API int var_b200_conv1x1_nhwc(const void* x, const void* w_packed, const float* bias, const void* resid, void* out,
+                                       long long n_pixels, int Cin, int Cout, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * GroupNorm (+SiLU) on NHWC bf16 tensors: glue of the VQVAE CNN decoder/encoder around the cuDNN convolutions
  * (models/basic_vae.py:18-19,57-58,159,225). x, y: bf16 [B, HW, C]; gamma, beta: fp32 [C]. Deterministic. */
@@ -319,6 +330,16 @@ VAR_B200_API int var_b200_add_bias_nhwc(const void* a, const float* bias_a, cons
                                         long long n_pixels, int C, void* stream);
 /* y[B,2H,2W,C] = nearest-2x(x[B,H,W,C]) (+ bias[c]) (basic_vae.py:22-28). */
 VAR_B200_API int var_b200_upsample2x_nhwc(const void* x, const float* bias, void* y, int B, int H, int W, int C, void* stream);
+
+/* AttnBlock.forward of the VQVAE CNN (models/basic_vae.py:63-92) on NHWC bf16 activations, on var_b200's own kernels:
+ * out = x + proj_out(softmax(q k^T * C^-0.5) v) with [q,k,v] = qkv(GroupNorm(x)) (single head over the HW pixels of
+ * each image). x, out: bf16 [B, HW, C] (out may alias x); w_qkv: bf16 [3C, C] (the 1x1 convolution's weight, rows q, k,
+ * v); w_proj: bf16 [C, C]; biases and GroupNorm affine fp32. The q k^T and P v products of all images run as ONE GEMM
+ * launch each (block-diagonal batching of the tcgen05 GEMM). Requires HW % 256 == 0, HW <= 4096, C % 64 == 0. */
+VAR_B200_API size_t var_b200_vae_attn_workspace(int B, int HW, int C, int groups);
+VAR_B200_API int var_b200_vae_attn_block(const void* x, const float* gn_gamma, const float* gn_beta, int groups, float eps,
+                                         const void* w_qkv, const float* b_qkv, const void* w_proj, const float* b_proj,
+                                         void* out, int B, int HW, int C, void* work, size_t work_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -235,3 +235,100 @@ def test_conv3x3_nhwc_vs_torch(B, H, W, Cin, Cout, resid):
         ref = ref.bfloat16().float() + r.float()
     err = (out.float() - ref).abs().max().item()
     assert torch.isfinite(out.float()).all() and err <= 2 ** -7 * ref.abs().max().item() + 1e-2, f"max err {err}"  # bf16 ulp
+
+
+@pytest.mark.parametrize("B,HW,Cdim", [(3, 256, 640), (2, 256, 128), (1, 1024, 64), (5, 256, 320)])
+def test_vae_attn_block_vs_torch(B, HW, Cdim):
+    """AttnBlock.forward (models/basic_vae.py:63-92) on var_b200's kernels (GroupNorm, five GEMM launches with the
+    per-image products as block-diagonal batches, row softmax) vs the fp32 PyTorch module on the same bf16 input."""
+    from var_b200.basic_vae import AttnBlock
+    torch.manual_seed(B + HW + Cdim)
+    side = int(math.isqrt(HW))
+    blk = AttnBlock(Cdim).cuda()
+    for prm in blk.parameters():
+        torch.nn.init.normal_(prm, std=0.5 if prm.dim() == 1 else 1.5 / math.sqrt(Cdim))
+    with torch.no_grad():
+        blk.norm.weight.add_(1.0)
+    x = (torch.randn(B, Cdim, side, side, device="cuda") * 1.3 + 0.2).bfloat16()
+    with torch.no_grad():
+        ref = blk(x.float())                                                       # [B, C, H, W] fp32
+    xn = x.permute(0, 2, 3, 1).contiguous()                                        # NHWC
+    out = torch.full_like(xn, float("nan"))
+    lib = L.load()
+    ws = torch.empty(lib.var_b200_vae_attn_workspace(B, HW, Cdim, 32), dtype=torch.uint8, device="cuda")
+    wq = blk.qkv.weight.detach().reshape(3 * Cdim, Cdim).bfloat16().contiguous()
+    wp = blk.proj_out.weight.detach().reshape(Cdim, Cdim).bfloat16().contiguous()
+    f32 = lambda t: t.detach().float().contiguous()
+    args = (f32(blk.norm.weight), f32(blk.norm.bias), f32(blk.qkv.bias), f32(blk.proj_out.bias))
+    L.check(lib.var_b200_vae_attn_block(xn.data_ptr(), args[0].data_ptr(), args[1].data_ptr(), 32, blk.norm.eps, wq.data_ptr(),
+                                        args[2].data_ptr(), wp.data_ptr(), args[3].data_ptr(), out.data_ptr(), B, HW, Cdim,
+                                        ws.data_ptr(), ws.numel(), L.current_stream()), "vae_attn_block")
+    torch.cuda.synchronize()
+    got = out.float().permute(0, 3, 1, 2)
+    err = (got - ref).abs()
+    # five chained bf16 roundings (g, q/k, P, O, out) on values of size ~|ref|: a few bf16 ulps
+    tol = 4 * 2 ** -8 * ref.abs().max().item() + 2e-2
+    print(f"vae attn B={B} HW={HW} C={Cdim}: max err {err.max():.4f} mean {err.mean():.5f} (|ref| max {ref.abs().max():.2f})")
+    assert torch.isfinite(got).all() and err.max().item() <= tol, f"max err {err.max().item()} > {tol}"
+    # the attention term itself must be there (not just the shortcut)
+    assert (ref - x.float()).abs().mean().item() > 10 * err.mean().item()
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 256, 256, 160, 160), (1, 128, 128, 160, 160), (3, 64, 64, 320, 320),
+                                            (2, 32, 32, 320, 320), (1, 32, 32, 64, 32)])
+def test_conv3x3_stride2_nhwc_vs_torch(B, H, W, Cin, Cout):
+    """Downsample2x (models/basic_vae.py:31-37: zero pad (0,1,0,1), 3x3, stride 2) through stride-2 TMA boxes vs torch."""
+    torch.manual_seed(B + H + Cin)
+    x = torch.randn(B, H, W, Cin, device="cuda").bfloat16()
+    w = (torch.randn(Cout, Cin, 3, 3, device="cuda") / math.sqrt(9 * Cin)).bfloat16()
+    bias = torch.randn(Cout, device="cuda")
+    out = torch.full((B, H // 2, W // 2, Cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    L.check(L.load().var_b200_conv3x3_s2_nhwc(x.data_ptr(), pack_conv3x3(w).data_ptr(), bias.data_ptr(), out.data_ptr(), B, H, W,
+                                              Cin, Cout, L.current_stream()), "conv3x3_s2")
+    torch.cuda.synchronize()
+    xp = torch.nn.functional.pad(x.float().permute(0, 3, 1, 2), (0, 1, 0, 1))
+    ref = torch.nn.functional.conv2d(xp, w.float(), bias, stride=2).permute(0, 2, 3, 1)
+    err = (out.float() - ref).abs().max().item()
+    assert torch.isfinite(out.float()).all() and err <= 2 ** -7 * ref.abs().max().item() + 1e-2, f"max err {err}"
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 256, 256, 160, 32), (1, 16, 16, 640, 32), (2, 64, 64, 8, 160)])
+def test_conv3x3_narrow_channels(B, H, W, Cin, Cout):
+    """32-wide output tiles (decoder conv_out padded 3 -> 32, encoder conv_out 640 -> 32) and an 8-channel input (the
+    image padded 3 -> 8): channel tails are TMA zero fill on the activation side and zero rows / columns in the weights."""
+    torch.manual_seed(H + Cin + Cout)
+    x = torch.randn(B, H, W, Cin, device="cuda").bfloat16()
+    w = (torch.randn(Cout, Cin, 3, 3, device="cuda") / math.sqrt(9 * Cin)).bfloat16()
+    if Cout == 32:
+        w[3:] = 0  # as the padded conv_out weights
+    bias = torch.randn(Cout, device="cuda")
+    out = torch.full((B, H, W, Cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    L.check(L.load().var_b200_conv3x3_nhwc(x.data_ptr(), pack_conv3x3(w).data_ptr(), bias.data_ptr(), None, out.data_ptr(), B, H,
+                                           W, Cin, Cout, L.current_stream()), "conv3x3")
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1).permute(0, 2, 3, 1)
+    err = (out.float() - ref).abs().max().item()
+    assert torch.isfinite(out.float()).all() and err <= 2 ** -7 * ref.abs().max().item() + 1e-2, f"max err {err}"
+
+
+@pytest.mark.parametrize("n_pix,Cin,Cout,resid", [(512, 32, 32, False), (3 * 1024, 640, 320, False), (300, 320, 160, True),
+                                                  (128 * 128, 160, 32, False)])
+def test_conv1x1_nhwc_vs_torch(n_pix, Cin, Cout, resid):
+    """1x1 convolution = GEMM over the pixels; Cin below / not a multiple of the 64-wide K block is zero-filled by TMA."""
+    torch.manual_seed(n_pix + Cin)
+    x = torch.randn(n_pix, Cin, device="cuda").bfloat16()
+    w = (torch.randn(Cout, Cin, device="cuda") / math.sqrt(Cin)).bfloat16()
+    kp = (Cin + 63) // 64 * 64
+    wp = torch.zeros(Cout, kp, device="cuda", dtype=torch.bfloat16)
+    wp[:, :Cin] = w
+    bias = torch.randn(Cout, device="cuda")
+    r = torch.randn(n_pix, Cout, device="cuda").bfloat16() if resid else None
+    out = torch.full((n_pix, Cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    L.check(L.load().var_b200_conv1x1_nhwc(x.data_ptr(), wp.data_ptr(), bias.data_ptr(), r.data_ptr() if resid else None,
+                                           out.data_ptr(), n_pix, Cin, Cout, L.current_stream()), "conv1x1")
+    torch.cuda.synchronize()
+    ref = x.float() @ w.float().t() + bias
+    if resid:
+        ref = ref.bfloat16().float() + r.float()
+    err = (out.float() - ref).abs().max().item()
+    assert torch.isfinite(out.float()).all() and err <= 2 ** -7 * ref.abs().max().item() + 1e-2, f"max err {err}"

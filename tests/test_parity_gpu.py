@@ -705,3 +705,29 @@ def test_more_smooth_soft_embedding_op_and_end_to_end():
     with pytest.raises(NotImplementedError):
         var.inpainting(torch.zeros(2, 680, dtype=torch.long, device=DEV), torch.ones(2, 680, dtype=torch.bool, device=DEV),
                        label=labels, more_smooth=True)
+
+
+def test_nhwc_plans_use_only_own_kernels(monkeypatch):
+    """with the 16-bit plans every convolution (3x3, stride-2, 1x1, 3- and 32-channel ends) and the
+    16x16 AttnBlock run on var_b200's kernels: no cuDNN convolution and no SDPA call is left in either direction."""
+    import torch.nn.functional as F
+    vae, _ = seeded_models(device=DEV)
+    g = torch.Generator().manual_seed(5)
+    img = (torch.rand(2, 3, 256, 256, generator=g) * 2 - 1).to(DEV)
+    f_hat = torch.randn(2, 32, 16, 16, generator=g).to(DEV)
+
+    def boom(*a, **k):
+        raise AssertionError("library convolution / attention called inside the NHWC plan")
+    vae.encoder_dtype = vae.decoder_dtype = torch.bfloat16
+    try:
+        n0 = L.load().var_b200_launch_count()
+        with monkeypatch.context() as mp:
+            mp.setattr(F, "conv2d", boom)
+            mp.setattr(F, "scaled_dot_product_attention", boom)
+            post = vae.img_to_post(img)
+            rec = vae.fhat_to_img(f_hat)
+        assert L.load().var_b200_launch_count() - n0 > 150
+    finally:
+        vae.encoder_dtype = vae.decoder_dtype = None
+    assert post.shape == (2, 32, 16, 16) and rec.shape == (2, 3, 256, 256)
+    assert bool(torch.isfinite(post).all()) and bool(torch.isfinite(rec).all())

@@ -182,44 +182,72 @@ class NHWCDecoder:
 
     # ---- own tcgen05 convolutions
     def _own_ok(self, x, m: nn.Conv2d) -> bool:
+        """Can this convolution run on var_b200's implicit-GEMM kernels? (3x3 stride 1 pad 1, the 3x3 stride-2
+        Downsample2x on a (0,1,0,1)-padded input, 1x1.) Channel counts are padded where the packing allows it: 3 input
+        channels to 8 (conv_in of the encoder), 3 output channels to 32 (conv_out of the decoder)."""
         B, Cin, H, W = x.shape if isinstance(x, torch.Tensor) else x
-        if not self.own_conv or m.stride != (1, 1) or m.out_channels % 32 or Cin % 8:
+        if not self.own_conv or (m.out_channels % 32 and m.out_channels != 3) or (Cin % 8 and Cin != 3):
             return False
         if m.kernel_size == (1, 1):
-            return m.padding == (0, 0) and Cin % 64 == 0
-        return (m.kernel_size == (3, 3) and m.padding == (1, 1) and (H * W) % 128 == 0
+            return m.padding == (0, 0) and m.stride == (1, 1)
+        if m.kernel_size != (3, 3):
+            return False
+        if m.stride == (2, 2):  # Downsample2x: H, W are the unpadded input extent
+            Ho, Wo = H // 2, W // 2
+            return m.padding == (0, 0) and H % 2 == 0 and W % 2 == 0 and Wo <= 128 and 128 % Wo == 0 and (Ho * Wo) % 128 == 0
+        return (m.stride == (1, 1) and m.padding == (1, 1) and (H * W) % 128 == 0
                 and (128 % W == 0 if W <= 128 else W % 128 == 0))
 
     def _packed(self, m: nn.Conv2d):
+        """bf16 weights [Cout', taps, ceil64(Cin')] (tap-major, zero padded; Cin' = Cin rounded up to 8, Cout' = Cout
+        rounded up to 32) + fp32 bias [Cout']"""
         key = ("own", id(m))
         w = self._w.get(key)
         if w is None or w[2] != (m.weight._version, m.bias._version):
             Cout, Cin, kh, kw = m.weight.shape
             kp = (Cin + 63) // 64 * 64
-            wp = torch.zeros((Cout, kh * kw, kp), dtype=torch.bfloat16, device=m.weight.device)
-            wp[:, :, :Cin] = m.weight.detach().permute(0, 2, 3, 1).reshape(Cout, kh * kw, Cin).to(torch.bfloat16)
-            w = (wp.reshape(Cout, kh * kw * kp).contiguous(), m.bias.detach().float().contiguous(),
-                 (m.weight._version, m.bias._version))
+            cop = (Cout + 31) // 32 * 32
+            wp = torch.zeros((cop, kh * kw, kp), dtype=torch.bfloat16, device=m.weight.device)
+            wp[:Cout, :, :Cin] = m.weight.detach().permute(0, 2, 3, 1).reshape(Cout, kh * kw, Cin).to(torch.bfloat16)
+            bias = torch.zeros(cop, dtype=torch.float32, device=m.weight.device)
+            bias[:Cout] = m.bias.detach().float()
+            w = (wp.reshape(cop, kh * kw * kp).contiguous(), bias, (m.weight._version, m.bias._version))
             self._w[key] = w
         return w
 
     def _own_conv(self, x, m: nn.Conv2d, resid=None):
-        """conv + bias (+ resid) on the tcgen05 kernels; x / resid / result: bf16 channels_last"""
+        """conv + bias (+ resid) on the tcgen05 kernels; x / resid / result: bf16 channels_last. A 3-channel output comes
+        back as the 32-channel padded tensor's first three channels (a view)."""
         B, Cin, H, W = x.shape
-        Cout = m.out_channels
         assert x.is_contiguous(memory_format=torch.channels_last) and x.dtype == torch.bfloat16
+        if Cin % 8:  # 3 image channels -> 8 (zeros): TMA rows are at least 16 bytes
+            x8 = torch.zeros((B, 8, H, W), dtype=x.dtype, device=x.device).contiguous(memory_format=torch.channels_last)
+            x8[:, :Cin] = x
+            x, Cin = x8, 8
         wp, bias, _ = self._packed(m)
-        y = torch.empty((B, Cout, H, W), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
-        if m.kernel_size == (3, 3):
-            self.L.check(self.lib.var_b200_conv3x3_nhwc(x.data_ptr(), wp.data_ptr(), bias.data_ptr(), self.L.ptr(resid),
-                                                        y.data_ptr(), B, H, W, Cin, Cout, self.L.current_stream()), "conv3x3_nhwc")
-        else:  # 1x1: a plain GEMM over the pixels
+        Cout = wp.shape[0]  # padded to a multiple of 32
+        st = self.L.current_stream()
+        if m.kernel_size == (3, 3) and m.stride == (2, 2):
             assert resid is None
-            a = self.L.GemmArgs()
-            a.A, a.W, a.M, a.N, a.K, a.epilogue = x.data_ptr(), wp.data_ptr(), B * H * W, Cout, Cin, self.L.EPI_BIAS_BF16
-            a.bias, a.out = bias.data_ptr(), y.data_ptr()
-            self.L.check(self.lib.var_b200_gemm_bf16(C.byref(a), self.L.current_stream()), "gemm_bf16 (1x1 conv)")
-        return y
+            y = torch.empty((B, Cout, H // 2, W // 2), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+            self.L.check(self.lib.var_b200_conv3x3_s2_nhwc(x.data_ptr(), wp.data_ptr(), bias.data_ptr(), y.data_ptr(), B, H, W,
+                                                           Cin, Cout, st), "conv3x3_s2_nhwc")
+        elif m.kernel_size == (3, 3):
+            y = torch.empty((B, Cout, H, W), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+            self.L.check(self.lib.var_b200_conv3x3_nhwc(x.data_ptr(), wp.data_ptr(), bias.data_ptr(), self.L.ptr(resid),
+                                                        y.data_ptr(), B, H, W, Cin, Cout, st), "conv3x3_nhwc")
+        else:  # 1x1: a plain GEMM over the pixels
+            y = torch.empty((B, Cout, H, W), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+            self.L.check(self.lib.var_b200_conv1x1_nhwc(x.data_ptr(), wp.data_ptr(), bias.data_ptr(), self.L.ptr(resid),
+                                                        y.data_ptr(), B * H * W, Cin, Cout, st), "conv1x1_nhwc")
+        return y if Cout == m.out_channels else y[:, :m.out_channels]
+
+    def _conv_any(self, x, m: nn.Conv2d):
+        """conv + bias: own kernel when the shape allows it, else cuDNN + the bias-add glue kernel"""
+        if self._own_ok(x, m):
+            return self._own_conv(x, m)
+        y = self._conv(x, m)
+        return self._add(y, self._bias(m), None, None, out=y)
 
     def _gn(self, x, m: nn.GroupNorm, silu: bool, pre_bias=None):
         B, Cc, H, W = x.shape
@@ -266,6 +294,26 @@ class NHWCDecoder:
 
     def _attn(self, x, blk: AttnBlock):
         B, Cc, H, W = x.shape
+        if self.own_conv and (H * W) % 256 == 0 and H * W <= 4096 and Cc % 64 == 0:
+            # the whole block on var_b200's kernels (csrc/vae_attn.cu): GroupNorm, the 1x1 convolutions and both
+            # per-image products on the tcgen05 GEMM (block-diagonal batching), row softmax, shortcut in the epilogue
+            key = ("attn", id(blk))
+            w = self._w.get(key)
+            ver = tuple(p_._version for p_ in blk.parameters())
+            if w is None or w[-1] != ver:
+                f32 = lambda t: t.detach().float().contiguous()
+                w = (blk.qkv.weight.detach().reshape(3 * Cc, Cc).to(torch.bfloat16).contiguous(), f32(blk.qkv.bias),
+                     blk.proj_out.weight.detach().reshape(Cc, Cc).to(torch.bfloat16).contiguous(), f32(blk.proj_out.bias),
+                     f32(blk.norm.weight), f32(blk.norm.bias), ver)
+                self._w[key] = w
+            y = torch.empty_like(x)
+            ws = torch.empty(self.lib.var_b200_vae_attn_workspace(B, H * W, Cc, blk.norm.num_groups), dtype=torch.uint8,
+                             device=x.device)
+            self.L.check(self.lib.var_b200_vae_attn_block(x.data_ptr(), w[4].data_ptr(), w[5].data_ptr(), blk.norm.num_groups,
+                                                          blk.norm.eps, w[0].data_ptr(), w[1].data_ptr(), w[2].data_ptr(),
+                                                          w[3].data_ptr(), y.data_ptr(), B, H * W, Cc, ws.data_ptr(), ws.numel(),
+                                                          self.L.current_stream()), "vae_attn_block")
+            return y
         qkv = self._conv(self._gn(x, blk.norm, False), blk.qkv)               # [B,3C,H,W] channels_last, no bias yet
         qkv = self._add(qkv, self._bias(blk.qkv), None, None, out=qkv)
         q, k, v = qkv.permute(0, 2, 3, 1).reshape(B, H * W, 3 * Cc).chunk(3, dim=-1)
@@ -286,22 +334,13 @@ class NHWCDecoder:
         up = torch.empty((B, Cc, 2 * H, 2 * W), dtype=h.dtype, device=h.device, memory_format=torch.channels_last)
         self.L.check(self.lib.var_b200_upsample2x_nhwc(h.data_ptr(), None, up.data_ptr(), B, H, W, Cc,
                                                        self.L.current_stream()), "upsample2x_nhwc")
-        if self._own_ok(up, conv):
-            return self._own_conv(up, conv)
-        y = self._conv(up, conv)
-        return self._add(y, self._bias(conv), None, None, out=y)
+        return self._conv_any(up, conv)
 
     @torch.no_grad()
     def __call__(self, f_hat: torch.Tensor) -> torch.Tensor:
         d = self.dec
         x = f_hat.to(self.dtype).contiguous(memory_format=torch.channels_last)
-        h = self._conv(x, self.post)
-        h = self._add(h, self._bias(self.post), None, None, out=h)
-        if self._own_ok(h, d.conv_in):
-            h = self._own_conv(h, d.conv_in)
-        else:
-            h = self._conv(h, d.conv_in)
-            h = self._add(h, self._bias(d.conv_in), None, None, out=h)
+        h = self._conv_any(self._conv_any(x, self.post), d.conv_in)
         h = self._res(h, d.mid.block_1)
         h = self._attn(h, d.mid.attn_1)
         h = self._res(h, d.mid.block_2)
@@ -309,8 +348,12 @@ class NHWCDecoder:
             h = self._level(h, lvl)
             if hasattr(lvl, "upsample"):
                 h = self._upsample(h, lvl.upsample.conv)
-        w, b, _ = self._cw(d.conv_out)
-        h = F.conv2d(self._gn(h, d.norm_out, True), w, b.to(self.dtype), padding=d.conv_out.padding)  # 3 channels: torch adds the bias
+        g = self._gn(h, d.norm_out, True)
+        if self._own_ok(g, d.conv_out):  # 3 output channels as a 32-wide tile of the implicit GEMM
+            h = self._own_conv(g, d.conv_out)
+        else:
+            w, b, _ = self._cw(d.conv_out)
+            h = F.conv2d(g, w, b.to(self.dtype), padding=d.conv_out.padding)
         return h.float().contiguous()
 
 
@@ -327,17 +370,22 @@ class NHWCEncoder(NHWCDecoder):
     def __call__(self, img: torch.Tensor) -> torch.Tensor:
         e = self.enc
         x = img.to(self.dtype).contiguous(memory_format=torch.channels_last)
-        w, b, _ = self._cw(e.conv_in)
-        h = F.conv2d(x, w, b.to(self.dtype), padding=e.conv_in.padding)  # 3 input channels: let torch add the bias
+        if self._own_ok(x, e.conv_in):  # 3 image channels zero-padded to 8
+            h = self._own_conv(x, e.conv_in)
+        else:
+            w, b, _ = self._cw(e.conv_in)
+            h = F.conv2d(x, w, b.to(self.dtype), padding=e.conv_in.padding)
         for lvl in e.down:
             h = self._level(h, lvl)
             if hasattr(lvl, "downsample"):
-                y = self._conv(F.pad(h, (0, 1, 0, 1)), lvl.downsample.conv)
-                h = self._add(y, self._bias(lvl.downsample.conv), None, None, out=y)
+                dc = lvl.downsample.conv
+                if self._own_ok(h, dc):  # stride-2 TMA boxes; the (0,1,0,1) zero pad is TMA's out-of-bounds fill
+                    h = self._own_conv(h, dc)
+                else:
+                    y = self._conv(F.pad(h, (0, 1, 0, 1)), dc)
+                    h = self._add(y, self._bias(dc), None, None, out=y)
         h = self._res(h, e.mid.block_1)
         h = self._attn(h, e.mid.attn_1)
         h = self._res(h, e.mid.block_2)
-        h = self._conv(self._gn(h, e.norm_out, True), e.conv_out)
-        h = self._conv(self._add(h, self._bias(e.conv_out), None, None, out=h), self.qconv)
-        h = self._add(h, self._bias(self.qconv), None, None, out=h)
+        h = self._conv_any(self._conv_any(self._gn(h, e.norm_out, True), e.conv_out), self.qconv)
         return h.float().contiguous()  # fp32 NCHW features for the quantizer

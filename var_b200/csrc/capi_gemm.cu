@@ -40,3 +40,24 @@ extern "C" int var_b200_conv3x3_nhwc(const void* x, const void* w_packed, const 
                                      int B, int H, int W, int Cin, int Cout, void* stream) {
   return vb::conv3x3_launch(x, w_packed, bias, resid, out, B, H, W, Cin, Cout, (cudaStream_t)stream);
 }
+
+extern "C" int var_b200_conv3x3_s2_nhwc(const void* x, const void* w_packed, const float* bias, void* out, int B, int H, int W,
+                                        int Cin, int Cout, void* stream) {
+  return vb::conv3x3_launch(x, w_packed, bias, nullptr, out, B, H, W, Cin, Cout, (cudaStream_t)stream, 2);
+}
+
+extern "C" int var_b200_conv1x1_nhwc(const void* x, const void* w_packed, const float* bias, const void* resid, void* out,
+                                     long long n_pixels, int Cin, int Cout, void* stream) {
+  using namespace vb;
+  VB_REQUIRE(x && w_packed && out && n_pixels > 0 && n_pixels < (1ll << 31), "conv1x1: bad arguments");
+  VB_REQUIRE(Cin > 0 && Cin % 8 == 0 && Cout % 32 == 0, "conv1x1: Cin=%d must be a multiple of 8, Cout=%d of 32", Cin, Cout);
+  GemmParams p{};
+  p.M = (int)n_pixels;
+  p.N = Cout;
+  p.K = (Cin + 63) / 64 * 64;  // the GEMM's K block; weights are packed [Cout, K] with zero columns beyond Cin
+  p.a_cols = Cin;                                   // the activation tail is zero-filled by TMA
+  p.bias = bias;
+  p.out = out;
+  p.resid_bf16 = reinterpret_cast<const __nv_bfloat16*>(resid);
+  return gemm_launch(x, w_packed, p, EPI_BIAS_BF16, (cudaStream_t)stream);
+}

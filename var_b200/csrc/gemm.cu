@@ -15,21 +15,25 @@ static int launch_one(const void* A, const void* W, const GemmParams& p, cudaStr
     // activations [B, H, W, Cin] as a 4-D map (C, W, H, B); a box = bw x bh pixels x 64 channels = one 128-row A tile
     const int Cin = p.conv_cin, nB = p.M / (p.conv_H * p.conv_W);
     const uint32_t bw = p.conv_W < GEMM_BM ? p.conv_W : GEMM_BM, bh = GEMM_BM / bw;
-    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)p.conv_W, (uint64_t)p.conv_H, (uint64_t)nB};
-    uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)p.conv_W * Cin * 2, (uint64_t)p.conv_H * p.conv_W * Cin * 2};
-    uint32_t box[4] = {GEMM_BK, bw, bh, 1};
-    int r = make_tmap_bf16_sw128(&tmA, A, 4, dims, str, box);
+    const uint32_t sd = p.conv_stride > 1 ? (uint32_t)p.conv_stride : 1u;
+    const uint64_t Wi = (uint64_t)p.conv_W * sd, Hi = (uint64_t)p.conv_H * sd;  // input extent
+    uint64_t dims[4] = {(uint64_t)Cin, Wi, Hi, (uint64_t)nB};
+    uint64_t str[3] = {(uint64_t)Cin * 2, Wi * Cin * 2, Hi * Wi * Cin * 2};
+    uint32_t box[4] = {GEMM_BK, bw * sd, bh * sd, 1};  // traversed extent; delivers bw x bh pixels
+    uint32_t es[4] = {1, sd, sd, 1};
+    int r = make_tmap_bf16_sw128(&tmA, A, 4, dims, str, box, sd > 1 ? es : nullptr);
     if (r) return r;
   } else {
-    uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.M};
-    uint64_t str[1] = {(uint64_t)p.K * 2};
+    const uint64_t acols = p.a_cols ? p.a_cols : p.K;
+    uint64_t dims[2] = {acols, (uint64_t)p.M};
+    uint64_t str[1] = {(uint64_t)(p.lda ? p.lda : acols) * 2};
     uint32_t box[2] = {GEMM_BK, GEMM_BM};
     int r = make_tmap_bf16_sw128(&tmA, A, 2, dims, str, box);
     if (r) return r;
   }
   {
-    uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.N};
-    uint64_t str[1] = {(uint64_t)p.K * 2};
+    uint64_t dims[2] = {(uint64_t)(p.w_cols ? p.w_cols : p.K), (uint64_t)(p.w_rows ? p.w_rows : p.N)};
+    uint64_t str[1] = {(uint64_t)(p.ldw ? p.ldw : (p.w_cols ? p.w_cols : p.K)) * 2};
     uint32_t box[2] = {GEMM_BK, (uint32_t)(BN / CTAS)};
     int r = make_tmap_bf16_sw128(&tmB, W, 2, dims, str, box);
     if (r) return r;
@@ -138,12 +142,24 @@ int gemm_launch(const void* A, const void* W, const GemmParams& p, int epi, cuda
     VB_REQUIRE(p.ln_u && p.ln_v && p.ln_labels && p.ln_parts > 0 && p.ln_C > 0 && p.rows_per_seq > 0,
                "gemm: deferred LayerNorm needs ln_u, ln_v, ln_labels, ln_parts, ln_C, rows_per_seq");
   }
-  const int bn = force_bn ? (force_bn & 0xffff) : gemm_pick_bn_mn(p.M, p.N, epi);
+  if (p.bd_rows > 0) {
+    VB_REQUIRE(p.conv_kpt == 0 && p.bd_rows % (2 * GEMM_BM) == 0 && p.M % p.bd_rows == 0,
+               "gemm: block-diagonal batching needs bd_rows=%d to be a multiple of %d and to divide M=%d", p.bd_rows,
+               2 * GEMM_BM, p.M);
+    VB_REQUIRE(epi == EPI_BIAS_F32 || epi == EPI_BIAS_BF16, "gemm: block-diagonal batching is built for the plain epilogues");
+  }
+  VB_REQUIRE(p.lda % 8 == 0 && p.ldw % 8 == 0, "gemm: lda=%d / ldw=%d must be multiples of 8 elements", p.lda, p.ldw);
+  int bn = force_bn ? (force_bn & 0xffff) : gemm_pick_bn_mn(p.M, p.N, epi);
+  if (!force_bn && epi == EPI_BIAS_BF16 && p.N <= 32) bn = 32;
   // CTA-pair tiles (256 x BN) unless the problem is a single 128-row tile or the caller forces 1-CTA (bit 16)
   const bool pair = !(force_bn & 0x10000) && p.M > GEMM_BM;
   if (bn == 160) {  // 160-wide tiles exist for the convolution epilogue only (channel counts 160 / 320 / 640 of the VQVAE)
     VB_REQUIRE(epi == EPI_BIAS_BF16, "gemm: tile width 160 is only built for EPI_BIAS_BF16");
     return pair ? launch_one<160, EPI_BIAS_BF16, 2>(A, W, p, st) : launch_one<160, EPI_BIAS_BF16, 1>(A, W, p, st);
+  }
+  if (bn == 32) {  // 32-wide tiles: the VQVAE's 3- and 32-channel convolutions (conv_out, quant_conv, post_quant_conv)
+    VB_REQUIRE(epi == EPI_BIAS_BF16, "gemm: tile width 32 is only built for EPI_BIAS_BF16");
+    return pair ? launch_one<32, EPI_BIAS_BF16, 2>(A, W, p, st) : launch_one<32, EPI_BIAS_BF16, 1>(A, W, p, st);
   }
   if (pair) {
     switch (bn) {
@@ -163,8 +179,14 @@ int gemm_launch(const void* A, const void* W, const GemmParams& p, int epi, cuda
 }
 
 int conv3x3_launch(const void* x, const void* w_packed, const float* bias, const void* resid, void* out, int B, int H,
-                   int W, int Cin, int Cout, cudaStream_t st) {
+                   int W, int Cin, int Cout, cudaStream_t st, int stride) {
   VB_REQUIRE(x && w_packed && out && B > 0 && H > 0 && W > 0, "conv3x3: bad arguments");
+  VB_REQUIRE(stride == 1 || stride == 2, "conv3x3: stride %d (1 or 2)", stride);
+  if (stride == 2) {  // H, W: input extent; the GEMM rows are the (H/2) x (W/2) output pixels
+    VB_REQUIRE(H % 2 == 0 && W % 2 == 0 && W / 2 <= 128, "conv3x3/s2: H=%d W=%d must be even, W <= 256", H, W);
+    H /= 2;
+    W /= 2;
+  }
   VB_REQUIRE(Cin > 0 && Cin % 8 == 0 && Cout % 32 == 0, "conv3x3: Cin=%d must be a multiple of 8, Cout=%d of 32", Cin, Cout);
   VB_REQUIRE((W <= GEMM_BM ? GEMM_BM % W == 0 : W % GEMM_BM == 0) && (H * W) % GEMM_BM == 0,
              "conv3x3: H=%d W=%d not tileable into 128-pixel row patches", H, W);
@@ -180,7 +202,8 @@ int conv3x3_launch(const void* x, const void* w_packed, const float* bias, const
   p.out = out;
   p.resid_bf16 = reinterpret_cast<const __nv_bfloat16*>(resid);
   p.conv_cin = Cin;
-  return gemm_launch(x, w_packed, p, EPI_BIAS_BF16, st, Cout % 160 == 0 ? 160 : 0);
+  p.conv_stride = stride;
+  return gemm_launch(x, w_packed, p, EPI_BIAS_BF16, st, Cout % 160 == 0 ? 160 : (Cout == 32 ? 32 : 0));
 }
 
 }  // namespace vb

@@ -46,6 +46,10 @@ struct GemmParams {
   // activation tensor [B, conv_H, conv_W, Cin] seen through a 4-D tensor map, row m = pixel ((b*H + y)*W + x);
   // K = 9 taps x conv_kpt 64-channel blocks (weights packed [N, 9, conv_kpt*64], zero padded). 0 = plain GEMM.
   int conv_kpt, conv_H, conv_W;
+  // conv_stride 2 = the reference's Downsample2x (basic_vae.py:31-37): zero pad (0,1,0,1), 3x3, stride 2, no padding.
+  // conv_H / conv_W are then the OUTPUT extent (rows m = output pixels), the input is 2*conv_H x 2*conv_W and tap
+  // (dy,dx) of output (y,x) reads input (2y+dy, 2x+dx): the same TMA box with a traversal stride of 2 in W and H.
+  int conv_stride;
   // Deferred LayerNorm (gemm_sm100.cuh, LNF). Producer side (EPI_GATE_RESID, set ln_a_out):
   __nv_bfloat16* ln_a_out;  // [M,N] bf16 = x_new * (1 + ln_scale[seq]): the A operand of the next QKV / fc1 GEMM
   const float* ln_scale;    // the NEXT LayerNorm's adaLN scale, ln_scale[(m / rows_per_seq) * gate_ld + n]
@@ -58,6 +62,13 @@ struct GemmParams {
   const float* ln_v;        // [n_classes, N]: W shift_class + bias
   const int* ln_labels;     // [M / rows_per_seq] class of every sequence
   int conv_cin;  // true channel count of the activation tensor (the tensor map's innermost extent; tails read as zeros)
+  // Operand leading dimensions in elements (0 = K): a column slice of a wider row-major matrix can be an operand.
+  int lda, ldw;
+  int a_cols;  // true column count of A when it is narrower than K (K padded to 64; the tail reads as zeros), 0 = K
+  // Block-diagonal batching (VQVAE AttnBlock, models/basic_vae.py:74-87: one bmm per image). Rows [j*bd_rows,
+  // (j+1)*bd_rows) of A use the W rows shifted by j*bd_w_row and the W columns shifted by j*bd_w_k; bd_rows must be a
+  // multiple of the M tile. w_rows / w_cols: full extent of the W matrix behind the tensor map (0 = N / K).
+  int bd_rows, bd_w_row, bd_w_k, w_rows, w_cols;
 };
 
 // Tile width the launcher will use for a given N (needed to size EPI_SCORE partials: n_tiles = ceil(N / bn)).
@@ -71,6 +82,6 @@ int gemm_launch(const void* A, const void* W, const GemmParams& p, int epi, cuda
 // (tap-major, channels zero-padded to kpt*64), out [B,H,W,Cout] bf16 = conv + bias (+ resid). Requires Cout % 32 == 0,
 // Cin % 8 == 0, W | 128 or 128 | W, (H*W) % 128 == 0.
 int conv3x3_launch(const void* x, const void* w_packed, const float* bias, const void* resid, void* out, int B, int H,
-                   int W, int Cin, int Cout, cudaStream_t st);
+                   int W, int Cin, int Cout, cudaStream_t st, int stride = 1);
 
 }  // namespace vb

@@ -120,6 +120,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           cy0 = rem / p.conv_W;
           cx0 = rem - cy0 * p.conv_W;
         }
+        // input coordinate of tap (0,0): stride 1 has zero padding 1 all round (x0-1, y0-1); the stride-2 convolution
+        // pads only right / bottom (2*x0, 2*y0)
+        const int cxs = p.conv_stride > 1 ? cx0 * p.conv_stride : cx0 - 1;
+        const int cys = p.conv_stride > 1 ? cy0 * p.conv_stride : cy0 - 1;
+        // block-diagonal batching: the W rows / columns this A row block multiplies (0, 0 for a plain GEMM)
+        const int bd = p.bd_rows > 0 ? (m_blk * TILE_M) / p.bd_rows : 0;
+        const int wn0 = n_blk * BN + bd * p.bd_w_row, wk0 = bd * p.bd_w_k;
         int tap = 0, kc = 0;  // conv mode: filter tap and channel block of k-block kb
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
@@ -129,17 +136,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint32_t fb = mapa_shared(full_bar(stage), 0);
             if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
             if (p.conv_kpt > 0)
-              tma_load_4d_cg2(&tmA, fb, sa, kc * GEMM_BK, cx0 + tap % 3 - 1, cy0 + tap / 3 - 1, cb);
+              tma_load_4d_cg2(&tmA, fb, sa, kc * GEMM_BK, cxs + tap % 3, cys + tap / 3, cb);
             else
               tma_load_2d_cg2(&tmA, fb, sa, kb * GEMM_BK, m0);
-            tma_load_2d_cg2(&tmB, fb, sa + Cfg::A_BYTES, kb * GEMM_BK, n_blk * BN + rank * (BN / 2));
+            tma_load_2d_cg2(&tmB, fb, sa + Cfg::A_BYTES, wk0 + kb * GEMM_BK, wn0 + rank * (BN / 2));
           } else {
             mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
             if (p.conv_kpt > 0)
-              tma_load_4d(&tmA, full_bar(stage), sa, kc * GEMM_BK, cx0 + tap % 3 - 1, cy0 + tap / 3 - 1, cb);
+              tma_load_4d(&tmA, full_bar(stage), sa, kc * GEMM_BK, cxs + tap % 3, cys + tap / 3, cb);
             else
               tma_load_2d(&tmA, full_bar(stage), sa, kb * GEMM_BK, m0);
-            tma_load_2d(&tmB, full_bar(stage), sa + Cfg::A_BYTES, kb * GEMM_BK, n_blk * BN);
+            tma_load_2d(&tmB, full_bar(stage), sa + Cfg::A_BYTES, wk0 + kb * GEMM_BK, wn0);
           }
           if (++kc == p.conv_kpt) { kc = 0; ++tap; }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }

@@ -45,13 +45,13 @@ static EncodeTiledFn get_encode() {
 // Descriptor cache: the block driver re-encodes the same (pointer, shape, box) maps on every call (weights and
 // workspace buffers keep their addresses), and cuTensorMapEncodeTiled costs microseconds of host time each.
 struct TmapKey {
-  uint64_t w[16];  // ptr | rank | dims[5] | box[5] | strides[4]
+  uint64_t w[21];  // ptr | rank | dims[5] | box[5] | strides[4] | element strides[5]
 };
 static std::unordered_map<std::string, CUtensorMap> g_tmaps;
 static std::mutex g_tmaps_mu;
 
 int make_tmap_bf16_sw128(CUtensorMap* out, const void* gptr, int rank, const uint64_t* dims,
-                         const uint64_t* strides_bytes, const uint32_t* box) {
+                         const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides) {
   TmapKey key{};
   key.w[0] = reinterpret_cast<uint64_t>(gptr);
   key.w[1] = (uint64_t)rank;
@@ -59,6 +59,7 @@ int make_tmap_bf16_sw128(CUtensorMap* out, const void* gptr, int rank, const uin
     key.w[2 + i] = dims[i];
     key.w[7 + i] = box[i];
     if (i + 1 < rank) key.w[12 + i] = strides_bytes[i];
+    key.w[16 + i] = elem_strides ? elem_strides[i] : 1;
   }
   const std::string ks(reinterpret_cast<const char*>(&key), sizeof(key));
   {
@@ -81,7 +82,7 @@ int make_tmap_bf16_sw128(CUtensorMap* out, const void* gptr, int rank, const uin
   for (int i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     bx[i] = box[i];
-    es[i] = 1;
+    es[i] = elem_strides ? elem_strides[i] : 1;
   }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(gptr), gdim, gstr, bx, es,

@@ -13,9 +13,11 @@ void set_error(const char* fmt, ...);
 const char* get_error();
 
 // Encodes a tiled bf16 tensor map with 128-byte swizzle. dims/box are innermost-first.
-// strides_bytes[i] is the byte stride of dimension i+1 (rank-1 entries). Returns 0 or VB_ERR_DRIVER.
+// strides_bytes[i] is the byte stride of dimension i+1 (rank-1 entries). elem_strides: NULL (all 1) or the traversal
+// stride per dimension: the box then covers box[i] elements of the tensor and delivers ceil(box[i] / elem_strides[i])
+// of them (strided convolutions). Returns 0 or VB_ERR_DRIVER.
 int make_tmap_bf16_sw128(CUtensorMap* out, const void* gptr, int rank, const uint64_t* dims,
-                         const uint64_t* strides_bytes, const uint32_t* box);
+                         const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides = nullptr);
 
 // SM count of the CURRENT device (cached per device).
 int sm_count();

@@ -142,10 +142,16 @@ sample_kernel(const float* __restrict__ logits, int B, int l, int V, int use_cfg
     float ps = 0.f;
     for (int i = tid; i < V; i += ST) ps += expf(sk[i] - m);
     const float sum = block_sum(ps, red);
+    // Entries already removed by top-k sort to the front as -inf and add exactly 0.0 to the cumulative sum: count them
+    // in parallel and start the (order-preserving, hence serial) double accumulation behind them. With top_k = 900 of
+    // 4096 that skips 78 % of the serial loop without changing a single rounding.
+    int ninf = 0;
+    for (int i = tid; i < V; i += ST) ninf += (sk[i] == -INFINITY) ? 1 : 0;
+    const int i0 = (int)(block_sum((float)ninf, red) + 0.5f);  // <= 4096 per thread: exact in fp32
     if (tid == 0) {
       double c = 0.0;
       const float lim = p_lim;
-      for (int i = 0; i < V - 1; ++i) {
+      for (int i = i0; i < V - 1; ++i) {
         c += (double)(expf(sk[i] - m) / sum);
         if ((float)c <= lim) xs[sv[i]] = -INFINITY; else break;  // cumsum is monotone: nothing later is removed
       }

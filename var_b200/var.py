@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import List, Optional, Sequence, Tuple, Union
 
 import torch
@@ -59,6 +60,12 @@ class _AdaLNBeforeHead(nn.Module):
     def __init__(self, C: int, D: int):
         super().__init__()
         self.ada_lin = nn.Sequential(nn.SiLU(inplace=False), nn.Linear(D, 2 * C))
+
+
+# Measurement hook: bench.py arms it for the one step an `ncu --profile-from-start off` launch list should cover; the AR
+# loop then calls cudaProfilerStart when it reaches scale VAR_B200_PROFILE_FROM_SCALE (default 0 = the whole step).
+_PROFILE_FROM_SCALE = int(os.environ.get("VAR_B200_PROFILE_FROM_SCALE", "0"))
+_PROFILE_ARMED = [False]
 
 
 class VAR(nn.Module):
@@ -418,6 +425,9 @@ class VAR(nn.Module):
             all_kept = torch.stack([keep_mask[:, a:b].all() for a, b in zip(offs[:-1], offs[1:])]).tolist()
         for si, pn in enumerate(self.patch_nums):
             l = pn * pn
+            if _PROFILE_ARMED[0] and si == _PROFILE_FROM_SCALE:  # measurement hook (bench.py VAR_B200_PROFILE_STEP)
+                _PROFILE_ARMED[0] = False
+                torch.cuda.profiler.start()
             if si == 0:
                 x = pm.embed(None, 0, labels, 2 * B, l, self.first_l, 0)
             else:
