@@ -177,7 +177,7 @@ embed_kernel(const float* __restrict__ x_in, int n_x, int l_in, const int* __res
              const float* __restrict__ class_emb, const float* __restrict__ pos_start,
              const float* __restrict__ lvl_pos, const float* __restrict__ w_word_t, const float* __restrict__ b_word,
              float* __restrict__ out, int n_rows, int l, int first_rows, int pos0, int C) {
-  __shared__ float xin[EMB_ROWS][32];
+  __shared__ __align__(16) float xin[EMB_ROWS][32];
   const int c = blockIdx.x * 256 + threadIdx.x;
   const int r0 = blockIdx.y * EMB_ROWS;
   const int nr = min(EMB_ROWS, n_rows - r0);
@@ -200,9 +200,17 @@ embed_kernel(const float* __restrict__ x_in, int n_x, int l_in, const int* __res
     if (t < first_rows) {
       v = (__ldg(class_emb + (size_t)__ldg(labels + s) * C + c) + __ldg(pos_start + (size_t)t * C + c)) + lp;
     } else {
+      // the row's 32 inputs as eight 16-byte broadcast loads (the scalar version was bound by its 32 LDS per output)
+      const float4* xr = reinterpret_cast<const float4*>(xin[i]);
       float acc = 0.f;
 #pragma unroll
-      for (int k = 0; k < 32; ++k) acc = fmaf(xin[i][k], w[k], acc);
+      for (int k = 0; k < 8; ++k) {
+        const float4 xv = xr[k];
+        acc = fmaf(xv.x, w[4 * k], acc);
+        acc = fmaf(xv.y, w[4 * k + 1], acc);
+        acc = fmaf(xv.z, w[4 * k + 2], acc);
+        acc = fmaf(xv.w, w[4 * k + 3], acc);
+      }
       v = (acc + bw) + lp;
     }
     out[(size_t)r * C + c] = v;
