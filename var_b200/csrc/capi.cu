@@ -353,6 +353,7 @@ extern "C" size_t var_b200_quant_encode_workspace(const var_b200_quant_t* qz, in
   b += align_up(nt * 64 * 2);              // pooled tokens bf16 (K padded to 64)
   b += align_up(nt * 4);                   // |z|^2
   b += align_up((size_t)qz->V * 64 * 2);   // codebook bf16 (K padded to 64)
+  b += align_up((size_t)qz->V * 4);        // |e_v|^2
   return b;
 }
 
@@ -374,6 +375,7 @@ extern "C" int var_b200_quant_encode(const var_b200_quant_t* qz, const float* f,
   void* zb = cv.take(nt * 64 * 2);
   float* zz = reinterpret_cast<float*>(cv.take(nt * 4));
   void* cb16 = cv.take((size_t)a.V * 64 * 2);
+  float* ee = reinterpret_cast<float*>(cv.take((size_t)a.V * 4));
   a.f_rest = rest_hat; a.f_hat = rest_hat + (size_t)B * img;
   a.idx_concat = 1; a.idx = idx_out; a.fhat_list = fhat_list;
   if (search_mode == 1) {  // fused single kernel, fp32 CUDA-core search
@@ -381,7 +383,7 @@ extern "C" int var_b200_quant_encode(const var_b200_quant_t* qz, const float* f,
     return quant_launch(a, st);
   }
   // tensor-core search: [pool s0] -> for every scale: [UMMA filter + exact re-rank] -> [update s, pool s+1]
-  rc = quant_prepare_codebook(a.codebook, cb16, a.V, st);
+  rc = quant_prepare_codebook(a.codebook, cb16, ee, a.V, st);
   if (rc) return rc;
   a.z_out = z; a.zb_out = zb; a.zz_out = zz;
   a.si_begin = 0; a.si_end = 1; a.f = f; a.zero_fhat = 1; a.split = 1;
@@ -392,7 +394,7 @@ extern "C" int var_b200_quant_encode(const var_b200_quant_t* qz, const float* f,
   for (int si = 0; si < a.S; ++si) {
     const int n_tok = B * a.ph[si] * a.pw[si];
     QuantSearchArgs sa{};
-    sa.zb = zb; sa.z = z; sa.zz = zz; sa.cb_bf16 = cb16; sa.codebook = a.codebook; sa.N = n_tok; sa.V = a.V;
+    sa.zb = zb; sa.z = z; sa.zz = zz; sa.cb_bf16 = cb16; sa.codebook = a.codebook; sa.ee = ee; sa.N = n_tok; sa.V = a.V;
     sa.idx_out = idx_out + off;
     rc = quant_search_launch(sa, st);
     if (rc) return rc;

@@ -1,4 +1,6 @@
 #include <stdlib.h>
+
+#include <algorithm>
 // Host launcher for the tcgen05 GEMM family + the raw C-ABI entry used by tests and by the block driver.
 #include "gemm.h"
 
@@ -95,18 +97,35 @@ int gemm_pick_bn(int N) {
   return best;
 }
 
-// M-aware refinement: with at least two full waves of 256 x 256 tiles the wider tile still wins at up to 7 % padding
-// (d30 proj / fc2, N = 1920: 1200 / 1449 vs 1160 / 1418 TFLOP/s at M = 131072); below that the narrower tile keeps
-// more CTA pairs busy. The SCORE epilogue sizes its partials with gemm_pick_bn(N) and keeps that choice.
+// Tile width by a small cost model (VAR_B200_GEMM_WIDE=0 restores gemm_pick_bn's N-only rule for A/B runs).
+// A launch takes  waves x k-blocks x (cycles one tile spends per 64-deep k-block)  with
+//   waves  = ceil(tiles / CTA pairs (or CTAs for the 1-CTA kernel)),
+//   cycles = max(tensor time 2*BN, operand ingress (128 + BN/CTAS) rows x 128 B at ~64 B/clk/SM)
+//          = 512 / 448 / 384 for BN = 256 / 192 / 128 on a CTA pair (profiles/r01_ncu_prof_gemm*.txt: the ingress cap).
+// With many waves this prefers the widest tile whose padding it can afford (d30 QKV / proj / fc2 at B=256: 256, as
+// measured); with few waves it removes the wave quantisation that the N-only rule left behind at 32 images per GPU
+// (BASELINE configs[4] on 8 GPUs: M = 64 * l): e.g. M = 2304, N = 1920 is 90 tiles of 256x192 = two waves on 74 pairs,
+// but 72 tiles of 256x256 = one. The SCORE epilogue sizes its partials with gemm_pick_bn(N) and keeps that choice.
 static int gemm_pick_bn_mn(int M, int N, int epi) {
-  const int bn = gemm_pick_bn(N);
-  if (bn == 256 || epi == EPI_SCORE) return bn;
+  const int bn0 = gemm_pick_bn(N);
+  if (epi == EPI_SCORE) return bn0;
   static const int wide = [] { const char* e = getenv("VAR_B200_GEMM_WIDE"); return e ? atoi(e) : 1; }();  // A/B switch
-  if (!wide) return bn;
-  const long long pad256 = ((N + 255) / 256) * 256LL;
-  const long long tiles256 = ((M + 255) / 256) * (pad256 / 256);
-  if (pad256 * 100 <= (long long)N * 107 && tiles256 >= 2LL * (vb::sm_count() / 2)) return 256;
-  return bn;
+  if (!wide) return bn0;
+  const bool pair = M > GEMM_BM;
+  const long long units = pair ? vb::sm_count() / 2 : vb::sm_count();
+  const long long m_tiles = pair ? (M + 2 * GEMM_BM - 1) / (2 * GEMM_BM) : 1;
+  int best = bn0;
+  long long best_cost = -1;
+  const int cands[3] = {256, 192, 128};
+  for (int bn : cands) {
+    const long long tiles = m_tiles * ((N + bn - 1) / bn);
+    const long long waves = (tiles + units - 1) / units;
+    const long long ingress = 2LL * (GEMM_BM + (pair ? bn / 2 : bn));
+    const long long cyc = std::max<long long>(2LL * bn, ingress);
+    const long long cost = waves * cyc;
+    if (best_cost < 0 || cost < best_cost) { best = bn; best_cost = cost; }  // ties: the wider tile (listed first)
+  }
+  return best;
 }
 
 int gemm_ln_parts(int M, int N) {

@@ -40,12 +40,13 @@ struct QuantSearchArgs {
   const float* zz;        // [N]
   const void* cb_bf16;    // [V, 64] bf16 codebook (K padded)
   const float* codebook;  // [V, 32] fp32
+  const float* ee;        // [V] |e_v|^2 (quant_prepare_codebook)
   int N, V;
   void* idx_out;          // int64 [N]
 };
 int quant_search_launch(const QuantSearchArgs& a, cudaStream_t st);
-// cb_bf16[v, 0:32] = bf16(codebook[v]), [32:64] = 0
-int quant_prepare_codebook(const float* codebook, void* cb_bf16, int V, cudaStream_t st);
+// cb_bf16[v, 0:32] = bf16(codebook[v]), [32:64] = 0; ee[v] = |e_v|^2 in the oracle's summation order
+int quant_prepare_codebook(const float* codebook, void* cb_bf16, float* ee, int V, cudaStream_t st);
 
 int quant_launch(const QuantArgs& a, cudaStream_t st);
 
