@@ -162,8 +162,10 @@ def _reference_models(depth: int):
     if depth not in _REF_STATE:
         from oracle import ref_loader
         from var_b200.init_utils import dense_init_
+        import contextlib
         build, _, _ = ref_loader.load()
-        vae, var = build(depth=depth)
+        with contextlib.redirect_stdout(sys.stderr):  # the reference prints its constructor banner: keep stdout = one JSON line
+            vae, var = build(depth=depth)
         dense_init_(vae, seed=1)
         dense_init_(var, seed=2)
         _REF_STATE.clear()  # one model at a time (d30 is 8 GB in fp32)
