@@ -255,6 +255,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   tc_fence_after();
   const uint32_t tmem = tmem_base_smem;
   const uint32_t tmem_o = tmem + ATT_SST * 64;  // S ring in columns [0,192), O in [192,256)
+  pdl_wait();               // PDL: q / K / V of the QKV GEMM are complete and visible from here on
+  pdl_launch_dependents();  // the proj GEMM may run its set-up while this grid drains
 
   if (warp == W_PROD) {
     // ------------------------------ TMA producer warp (warp-uniform loop, one elected lane issues) ------------------
@@ -769,12 +771,23 @@ int attn_launch(const AttnArgs& a, cudaStream_t st) {
   vb::ProfScope prof_scope(vb::PK_ATTN, st);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out);
   const float mb2 = a.max_score * 1.4426950408889634f;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(fast ? ATT_THREADS_FAST : ATT_THREADS);
+  cfg.dynamicSmemBytes = ATT_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // PDL: see pdl_wait() in the kernel
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  const int total_i = (int)total;
   if (fast && a.q_log2)
-    attn_kernel<true, true><<<grid, ATT_THREADS_FAST, ATT_SMEM, st>>>(tmQ, tmK, tmV, o, a.Lq, a.H, a.q_pos0, lv, n_qt, (int)total, mb2);
+    VB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, attn_kernel<true, true>, tmQ, tmK, tmV, o, a.Lq, a.H, a.q_pos0, lv, n_qt, total_i, mb2));
   else if (fast)
-    attn_kernel<true, false><<<grid, ATT_THREADS_FAST, ATT_SMEM, st>>>(tmQ, tmK, tmV, o, a.Lq, a.H, a.q_pos0, lv, n_qt, (int)total, mb2);
+    VB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, attn_kernel<true, false>, tmQ, tmK, tmV, o, a.Lq, a.H, a.q_pos0, lv, n_qt, total_i, mb2));
   else
-    attn_kernel<false, false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, o, a.Lq, a.H, a.q_pos0, lv, n_qt, (int)total, 0.f);
+    VB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, attn_kernel<false, false>, tmQ, tmK, tmV, o, a.Lq, a.H, a.q_pos0, lv, n_qt, total_i, 0.f));
   VB_CUDA_CHECK(cudaGetLastError());
   vb::count_launch();
   return VB_OK;

@@ -128,6 +128,13 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start while its predecessor in the stream is still draining. Everything before pdl_wait() (barrier init, TMEM
+// allocation, descriptor prefetch) overlaps the predecessor's tail; pdl_wait() returns once the predecessor has
+// completed and its memory is visible. pdl_launch_dependents() lets the successor do the same with this kernel.
+// Both are no-ops for a kernel launched without the attribute / without a dependent.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle, rows of exactly 128 bytes
 // (64 bf16), 8-row groups 1024 bytes apart (SBO). Bit layout: start>>4 [0,14), LBO>>4 [16,30),

@@ -53,13 +53,15 @@ static int launch_one(const void* A, const void* W, const GemmParams& p, cudaStr
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CTAS;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // PDL: see pdl_wait() in the kernel
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   vb::ProfScope prof_scope(EPI, st);
   VB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
   VB_CUDA_CHECK(cudaGetLastError());

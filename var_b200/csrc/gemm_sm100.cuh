@@ -90,6 +90,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  // PDL: the set-up above overlapped the previous kernel's tail; from here on global memory is read and written
+  pdl_wait();
+  pdl_launch_dependents();
 
   // The two register regimes never merge again: each branch carries its own copy of the teardown and returns.
   auto teardown = [&]() {

@@ -1,3 +1,4 @@
+#include <stdlib.h>
 // Host-side runtime helpers: last-error string, driver entry point for cuTensorMapEncodeTiled
 // (resolved at run time so the library loads on machines without libcuda), SM count.
 #include "host.h"
@@ -49,6 +50,11 @@ struct TmapKey {
 };
 static std::unordered_map<std::string, CUtensorMap> g_tmaps;
 static std::mutex g_tmaps_mu;
+
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("VAR_B200_PDL"); return e ? atoi(e) != 0 : true; }();
+  return on;
+}
 
 int make_tmap_bf16_sw128(CUtensorMap* out, const void* gptr, int rank, const uint64_t* dims,
                          const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides) {

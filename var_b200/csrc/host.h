@@ -60,6 +60,9 @@ struct ProfScope {
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute of a kernel: this cache remembers, per device,
 // the largest size already granted to the kernels of one launcher, and serialises the (rare) slow path, so the
 // launchers are safe with several GPUs in one process and with several host threads.
+// VAR_B200_PDL=0 launches the GEMM / attention chain without programmatic dependent launch (A/B runs).
+bool pdl_enabled();
+
 constexpr int VB_MAX_DEVICES = 64;
 struct SmemAttrCache {
   std::atomic<int> granted[VB_MAX_DEVICES];
