@@ -135,7 +135,20 @@ int gemm_ln_parts(int M, int N) {
   return (N + bn - 1) / bn * GEMM_EPI_SUB;
 }
 
-int gemm_launch(const void* A, const void* W, const GemmParams& p, int epi, cudaStream_t st, int force_bn) {
+// VAR_B200_L2HINT="<a><w>" with n / f / l = evict normal / first / last for the activation and the weight stream
+// (default "nl": weights evict-last, see gemm.h)
+static void l2_hints(unsigned long long* a, unsigned long long* w) {
+  static const char* e = getenv("VAR_B200_L2HINT");
+  auto dec = [](char c, unsigned long long dflt) {
+    return c == 'f' ? L2_EVICT_FIRST : c == 'l' ? L2_EVICT_LAST : c == 'n' ? L2_EVICT_NORMAL : dflt;
+  };
+  *a = dec(e && e[0] ? e[0] : 0, L2_EVICT_NORMAL);
+  *w = dec(e && e[0] && e[1] ? e[1] : 0, L2_EVICT_LAST);
+}
+
+int gemm_launch(const void* A, const void* W, const GemmParams& p_in, int epi, cudaStream_t st, int force_bn) {
+  GemmParams p = p_in;
+  if (!p.l2_hint_a && !p.l2_hint_w) l2_hints(&p.l2_hint_a, &p.l2_hint_w);
   VB_REQUIRE(A && W, "gemm: null operand");
   VB_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
   VB_REQUIRE(p.K % GEMM_BK == 0, "gemm: K=%d must be a multiple of %d", p.K, GEMM_BK);

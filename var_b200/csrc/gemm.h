@@ -64,6 +64,11 @@ struct GemmParams {
   int conv_cin;  // true channel count of the activation tensor (the tensor map's innermost extent; tails read as zeros)
   // Operand leading dimensions in elements (0 = K): a column slice of a wider row-major matrix can be an operand.
   int lda, ldw;
+  // L2 eviction priority of the two operand streams (TMA cache hints; 0 = normal). The weights are re-read by every
+  // M block for the whole launch: evict-last saves 0.2-0.7 GB of DRAM reads per d30 fc1 / fc2 launch. Measured and not
+  // kept (profiles/r02_gemm_dram_probe.txt): evict-first activations (the N tiles of an M block share them through
+  // L2: 2-5x the reads), evict-first epilogue traffic (no gain, proj slower), rotated K order per tile (more reads).
+  unsigned long long l2_hint_a, l2_hint_w;
   int a_cols;  // true column count of A when it is narrower than K (K padded to 64; the tail reads as zeros), 0 = K
   // Block-diagonal batching (VQVAE AttnBlock, models/basic_vae.py:74-87: one bmm per image). Rows [j*bd_rows,
   // (j+1)*bd_rows) of A use the W rows shifted by j*bd_w_row and the W columns shifted by j*bd_w_k; bd_rows must be a

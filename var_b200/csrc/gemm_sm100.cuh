@@ -110,6 +110,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      const uint64_t hint_a = p.l2_hint_a ? p.l2_hint_a : L2_EVICT_NORMAL, hint_w = p.l2_hint_w ? p.l2_hint_w : L2_EVICT_NORMAL;
       for (int tile = cid; tile < total_tiles; tile += ncl) {
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
         const int m0 = m_blk * TILE_M + rank * GEMM_BM;  // first accumulator row (pixel) of this CTA
@@ -141,15 +142,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (p.conv_kpt > 0)
               tma_load_4d_cg2(&tmA, fb, sa, kc * GEMM_BK, cxs + tap % 3, cys + tap / 3, cb);
             else
-              tma_load_2d_cg2(&tmA, fb, sa, kb * GEMM_BK, m0);
-            tma_load_2d_cg2(&tmB, fb, sa + Cfg::A_BYTES, wk0 + kb * GEMM_BK, wn0 + rank * (BN / 2));
+              tma_load_2d_cg2_hint(&tmA, fb, sa, kb * GEMM_BK, m0, hint_a);
+            tma_load_2d_cg2_hint(&tmB, fb, sa + Cfg::A_BYTES, wk0 + kb * GEMM_BK, wn0 + rank * (BN / 2), hint_w);
           } else {
             mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
             if (p.conv_kpt > 0)
               tma_load_4d(&tmA, full_bar(stage), sa, kc * GEMM_BK, cxs + tap % 3, cys + tap / 3, cb);
             else
-              tma_load_2d(&tmA, full_bar(stage), sa, kb * GEMM_BK, m0);
-            tma_load_2d(&tmB, full_bar(stage), sa + Cfg::A_BYTES, wk0 + kb * GEMM_BK, wn0);
+              tma_load_2d_hint(&tmA, full_bar(stage), sa, kb * GEMM_BK, m0, hint_a);
+            tma_load_2d_hint(&tmB, full_bar(stage), sa + Cfg::A_BYTES, wk0 + kb * GEMM_BK, wn0, hint_w);
           }
           if (++kc == p.conv_kpt) { kc = 0; ++tap; }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }

@@ -91,9 +91,15 @@ int make_tmap_bf16_sw128(CUtensorMap* out, const void* gptr, int rank, const uin
     es[i] = elem_strides ? elem_strides[i] : 1;
   }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  // VAR_B200_TMAP_L2PROMO = 0 / 64 / 128 / 256 (default 256): L2 promotion size of every tensor map (A/B runs)
+  static const CUtensorMapL2promotion promo = [] {
+    const char* e = getenv("VAR_B200_TMAP_L2PROMO");
+    const int v = e ? atoi(e) : 256;
+    return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+         : v == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+  }();
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(gptr), gdim, gstr, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed: CUresult=%d rank=%d dims=(%llu,%llu,%llu) box=(%u,%u,%u) ptr=%p", (int)r,
               rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
