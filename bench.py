@@ -56,8 +56,8 @@ def peaks():
     if p.exists():
         d = json.loads(p.read_text())
         return dict(burst=d["bf16_tflops"], sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), hbm=d["hbm_gbs"],
-                    src="measured")
-    return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, src="fallback")
+                    sustained_mhz=(d.get("clocks_under_load") or {}).get("sm_mhz_median"), src="measured")
+    return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, sustained_mhz=None, src="fallback")
 
 
 class ClockSampler:
@@ -466,8 +466,8 @@ def main():
     # (b) alone: fc1 at the step's largest shape, 20 launches, against the BURST measured peak.
     depth = wl["depth"]
     C_ = 64 * depth
-    ncu_path = ROOT / "profiles" / "r01_ncu_gemm_d30_fc1.json"
-    ncu_traffic = json.loads(ncu_path.read_text()) if ncu_path.exists() else {}
+    ncu_path = ROOT / "profiles" / "r02_ncu_gemm_lnf.json"  # ncu --set full of the d30 GEMM flavours (tools/gemm_prof_lnf.py)
+    ncu_traffic = json.loads(ncu_path.read_text()).get("fc2", {}) if ncu_path.exists() else {}
     n_seq_step = (2 * wl["batch"]) if wl["kind"] == "sample" else (shard_hi - shard_lo)
     gemm_flops = n_seq_step * (24.0 * C_ * C_ * depth * L_wl + 2.0 * C_ * V * L_wl + 12.0 * C_ * C_ * depth + 4.0 * C_ * C_)
     kp = kernel_split(hot)
@@ -482,10 +482,17 @@ def main():
     roofline = dict(bound="tensor", kernel="gemm_bf16_kernel<BN,EPI,2> (all fused epilogues of the step)",
                     achieved=gemm_tf_step, peak=pk["sustained"], unit="TFLOP/s", frac=gemm_tf_step / pk["sustained"],
                     traffic=ncu_traffic.get("traffic_GB") if wl["kind"] == "sample" and depth == 30 else None,
-                    traffic_note=("GB per launch of the largest GEMM of the step (" + ncu_traffic.get("kernel", "") + "), ncu "
-                                  "--set full dram read+write, vs %.3f GB algorithmic (profiles/r01_ncu_gemm_d30_fc1.json)"
-                                  % ncu_traffic.get("algorithmic_GB", 0.0)) if ncu_traffic else None,
+                    traffic_note=("GB per launch of the GEMM with the largest share of the step (" + ncu_traffic.get("kernel", "") +
+                                  "), ncu --set full dram read+write, vs %.3f GB algorithmic; tensor pipe %.1f %% active under ncu. "
+                                  "Writes equal the algorithmic bytes; the activation operand is re-read 1.6-3.8x depending on the "
+                                  "physical GPU's SM-to-die map (profiles/r02_gemm_dram_probe.txt, r02_ncu_gemm_lnf.json)"
+                                  % (ncu_traffic.get("algorithmic_GB", 0.0), ncu_traffic.get("tensor_active_pct", 0.0)))
+                    if ncu_traffic else None,
                     peak_source=f"{pk['src']} MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)",
+                    # the sustained peak was measured at pk["sustained_mhz"]; the step ran at clk["sm_mhz"] under the same
+                    # power cap: the same fraction against the peak scaled to the step's clock
+                    frac_at_step_clock=(gemm_tf_step / (pk["sustained"] * clk["sm_mhz"] / pk["sustained_mhz"])
+                                        if clk.get("sm_mhz") and pk.get("sustained_mhz") else None),
                     gemm_share_of_kernel_time=gemm_ms / all_ms,
                     kernel_ms={k: round(v, 3) for k, v in sorted(kp.ms.items(), key=lambda kv: -kv[1])},
                     kernel_launches=kp.n,

@@ -123,7 +123,7 @@ def test_embed_to_fhat_and_get_logits_match_reference_golden():
     h, labels = logits_inputs(var.C)
     got = var.get_logits(h.to(DEV), var.class_emb(labels.to(DEV)))
     err = (got[:, :, ::8].cpu() - torch.from_numpy(g["logits_sub"])).abs().max().item()
-    assert err < 6e-2, f"get_logits max-abs err {err} vs the reference"  # LOGIT_TOL: bf16 GEMM operands vs fp32 reference
+    assert err < 5e-2, f"get_logits max-abs err {err} vs the reference"  # LOGIT_TOL: bf16 GEMM operands vs fp32 reference
 
 
 def test_get_logits_matches_forward_head():
@@ -240,7 +240,8 @@ def test_ln_modulate():
 
 
 # ------------------------------------------------------------------------------------------------ transformer
-LOGIT_TOL = 6e-2   # max-abs on logits with std ~1 (bf16 GEMM operands, fp32 accumulate/residual) vs fp32 oracle
+LOGIT_TOL = 5e-2   # max-abs on logits with std ~1.1 (bf16 GEMM operands, fp32 accumulate/residual) vs fp32: measured
+                   # 0.021-0.030 over depths 2..30 (profiles/r02_parity_d16_measured.txt), asserted at about twice that
 
 
 @pytest.mark.parametrize("depth,shared", [(2, False), (2, True), (4, False)])
