@@ -324,6 +324,16 @@ VAR_B200_API size_t var_b200_gn_workspace(int B, int HW, int C, int groups);
 VAR_B200_API int var_b200_gn_silu_nhwc(const void* x, const float* pre_bias, const float* gamma, const float* beta, void* y,
                                        int B, int HW, int C, int groups, float eps, int apply_silu, void* work,
                                        size_t work_bytes, void* stream);
+/* The same convolution as var_b200_conv3x3_nhwc, whose epilogue also leaves the GroupNorm statistics of its output
+ * behind (basic_vae.py:57-58: every GroupNorm of the CNN follows a convolution): gn_sums[b, g] = (sum, sum of squares)
+ * over the pixels and the Cout/groups channels of group g of image b, computed from the stored bf16 values in a fixed
+ * order. var_b200_gn_apply_nhwc consumes them: no statistics pass over the tensor. Requires H*W % 256 == 0. */
+VAR_B200_API size_t var_b200_conv3x3_gn_workspace(int B, int H, int W, int Cout);
+VAR_B200_API int var_b200_conv3x3_gn_nhwc(const void* x, const void* w_packed, const float* bias, const void* resid, void* out,
+                                          int B, int H, int W, int Cin, int Cout, int groups, float* gn_sums /* [B,groups,2] */,
+                                          void* work, size_t work_bytes, void* stream);
+VAR_B200_API int var_b200_gn_apply_nhwc(const void* x, const float* gn_sums, const float* gamma, const float* beta, void* y,
+                                        int B, int HW, int C, int groups, float eps, int apply_silu, void* stream);
 /* out = a (+ bias_a[c]) + b (+ bias_b[c]) on bf16 NHWC tensors of n_pixels x C; b, bias_a, bias_b may be NULL; out may
  * alias a (residual add of ResnetBlock with the convolution biases folded in, basic_vae.py:60). */
 VAR_B200_API int var_b200_add_bias_nhwc(const void* a, const float* bias_a, const void* b, const float* bias_b, void* out,

@@ -332,3 +332,50 @@ def test_conv1x1_nhwc_vs_torch(n_pix, Cin, Cout, resid):
         ref = ref.bfloat16().float() + r.float()
     err = (out.float() - ref).abs().max().item()
     assert torch.isfinite(out.float()).all() and err <= 2 ** -7 * ref.abs().max().item() + 1e-2, f"max err {err}"
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,resid", [(2, 16, 16, 640, 640, True), (3, 32, 32, 320, 320, False),
+                                                  (1, 256, 256, 160, 160, True), (2, 64, 64, 640, 320, False)])
+def test_conv3x3_groupnorm_statistics_from_the_epilogue(B, H, W, Cin, Cout, resid):
+    """var_b200_conv3x3_gn_nhwc: same output as the plain convolution (bit for bit) plus the GroupNorm(32) (sum, sum of
+    squares) of exactly the stored bf16 values; var_b200_gn_apply_nhwc on them equals the two-pass GroupNorm kernel."""
+    torch.manual_seed(H + Cin + Cout)
+    lib = L.load()
+    x = torch.randn(B, H, W, Cin, device="cuda").bfloat16()
+    w = (torch.randn(Cout, Cin, 3, 3, device="cuda") / math.sqrt(9 * Cin)).bfloat16()
+    bias = torch.randn(Cout, device="cuda")
+    r = torch.randn(B, H, W, Cout, device="cuda").bfloat16() if resid else None
+    wp = pack_conv3x3(w)
+    ref_out = torch.empty((B, H, W, Cout), device="cuda", dtype=torch.bfloat16)
+    L.check(lib.var_b200_conv3x3_nhwc(x.data_ptr(), wp.data_ptr(), bias.data_ptr(), r.data_ptr() if resid else None,
+                                      ref_out.data_ptr(), B, H, W, Cin, Cout, L.current_stream()), "conv3x3")
+    out = torch.full_like(ref_out, float("nan"))
+    sums = torch.full((B, 32, 2), float("nan"), device="cuda")
+    ws = torch.empty(lib.var_b200_conv3x3_gn_workspace(B, H, W, Cout), dtype=torch.uint8, device="cuda")
+    L.check(lib.var_b200_conv3x3_gn_nhwc(x.data_ptr(), wp.data_ptr(), bias.data_ptr(), r.data_ptr() if resid else None,
+                                         out.data_ptr(), B, H, W, Cin, Cout, 32, sums.data_ptr(), ws.data_ptr(), ws.numel(),
+                                         L.current_stream()), "conv3x3_gn")
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref_out)
+    y = out.double().reshape(B, H * W, 32, Cout // 32)
+    ref_s = torch.stack((y.sum(dim=(1, 3)), (y * y).sum(dim=(1, 3))), dim=-1)
+    rel = ((sums.double() - ref_s).abs() / ref_s.abs().clamp_min(1.0)).max().item()
+    assert rel < 2e-5, f"statistics rel err {rel}"   # fp32 accumulation of up to 65536 x 5 values per group
+    # apply from the sums vs the two-pass kernel
+    gamma, beta = torch.randn(Cout, device="cuda"), torch.randn(Cout, device="cuda")
+    y1, y2 = torch.empty_like(out), torch.empty_like(out)
+    L.check(lib.var_b200_gn_apply_nhwc(out.data_ptr(), sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y1.data_ptr(), B, H * W,
+                                       Cout, 32, 1e-6, 1, L.current_stream()), "gn_apply")
+    ws2 = torch.empty(lib.var_b200_gn_workspace(B, H * W, Cout, 32), dtype=torch.uint8, device="cuda")
+    L.check(lib.var_b200_gn_silu_nhwc(out.data_ptr(), None, gamma.data_ptr(), beta.data_ptr(), y2.data_ptr(), B, H * W, Cout, 32,
+                                      1e-6, 1, ws2.data_ptr(), ws2.numel(), L.current_stream()), "gn_silu")
+    torch.cuda.synchronize()
+    d = (y1.float() - y2.float()).abs().max().item()
+    assert d <= 2 ** -6 * y2.float().abs().max().item(), f"GroupNorm from epilogue statistics differs from the two-pass kernel by {d}"
+    # deterministic
+    sums2 = torch.empty_like(sums)
+    L.check(lib.var_b200_conv3x3_gn_nhwc(x.data_ptr(), wp.data_ptr(), bias.data_ptr(), r.data_ptr() if resid else None,
+                                         out.data_ptr(), B, H, W, Cin, Cout, 32, sums2.data_ptr(), ws.data_ptr(), ws.numel(),
+                                         L.current_stream()), "conv3x3_gn")
+    torch.cuda.synchronize()
+    assert torch.equal(sums, sums2)

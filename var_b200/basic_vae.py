@@ -161,6 +161,7 @@ class NHWCDecoder:
         self.post = post_quant_conv
         self._w = {}
         self.own_conv = True   # False: every convolution through cuDNN (A/B measurements)
+        self.gn_from_conv = True  # GroupNorm statistics from the producing convolution's epilogue (False: statistics pass)
         from . import lib as L
         self.L, self.lib = L, L.load()
 
@@ -215,9 +216,25 @@ class NHWCDecoder:
             self._w[key] = w
         return w
 
-    def _own_conv(self, x, m: nn.Conv2d, resid=None):
+    def _own_conv(self, x, m: nn.Conv2d, resid=None, stats=False):
         """conv + bias (+ resid) on the tcgen05 kernels; x / resid / result: bf16 channels_last. A 3-channel output comes
-        back as the 32-channel padded tensor's first three channels (a view)."""
+        back as the 32-channel padded tensor's first three channels (a view). stats=True returns (y, sums): the
+        convolution's epilogue also leaves the GroupNorm(32) statistics of y behind (sums is None when the shape does not
+        allow it), so the GroupNorm that follows needs no statistics pass."""
+        if stats:
+            B, Cin, H, W = x.shape
+            if (self.gn_from_conv and m.kernel_size == (3, 3) and m.stride == (1, 1) and (H * W) % 256 == 0 and Cin % 8 == 0
+                    and m.out_channels % 32 == 0):
+                wp, bias, _ = self._packed(m)
+                Cout = m.out_channels
+                y = torch.empty((B, Cout, H, W), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+                sums = torch.empty((B, 32, 2), dtype=torch.float32, device=x.device)
+                ws = torch.empty(self.lib.var_b200_conv3x3_gn_workspace(B, H, W, Cout), dtype=torch.uint8, device=x.device)
+                self.L.check(self.lib.var_b200_conv3x3_gn_nhwc(x.data_ptr(), wp.data_ptr(), bias.data_ptr(), self.L.ptr(resid),
+                                                               y.data_ptr(), B, H, W, Cin, Cout, 32, sums.data_ptr(), ws.data_ptr(),
+                                                               ws.numel(), self.L.current_stream()), "conv3x3_gn_nhwc")
+                return y, sums
+            return self._own_conv(x, m, resid), None
         B, Cin, H, W = x.shape
         assert x.is_contiguous(memory_format=torch.channels_last) and x.dtype == torch.bfloat16
         if Cin % 8:  # 3 image channels -> 8 (zeros): TMA rows are at least 16 bytes
@@ -249,7 +266,7 @@ class NHWCDecoder:
         y = self._conv(x, m)
         return self._add(y, self._bias(m), None, None, out=y)
 
-    def _gn(self, x, m: nn.GroupNorm, silu: bool, pre_bias=None):
+    def _gn(self, x, m: nn.GroupNorm, silu: bool, pre_bias=None, sums=None):
         B, Cc, H, W = x.shape
         assert x.is_contiguous(memory_format=torch.channels_last) and x.dtype == torch.bfloat16
         p = self._w.get(id(m))
@@ -258,6 +275,11 @@ class NHWCDecoder:
                  (m.weight._version, m.bias._version))
             self._w[id(m)] = p
         y = torch.empty_like(x)  # preserves channels_last
+        if sums is not None and pre_bias is None and m.num_groups == 32:  # statistics came with the producing convolution
+            self.L.check(self.lib.var_b200_gn_apply_nhwc(x.data_ptr(), sums.data_ptr(), p[0].data_ptr(), p[1].data_ptr(),
+                                                         y.data_ptr(), B, H * W, Cc, m.num_groups, m.eps, int(silu),
+                                                         self.L.current_stream()), "gn_apply_nhwc")
+            return y
         ws = torch.empty(self.lib.var_b200_gn_workspace(B, H * W, Cc, m.num_groups), dtype=torch.uint8, device=x.device)
         self.L.check(self.lib.var_b200_gn_silu_nhwc(x.data_ptr(), self.L.ptr(pre_bias), p[0].data_ptr(), p[1].data_ptr(),
                                                     y.data_ptr(), B, H * W, Cc, m.num_groups, m.eps, int(silu),
@@ -271,12 +293,13 @@ class NHWCDecoder:
                                                      out.data_ptr(), B * H * W, Cc, self.L.current_stream()), "add_bias_nhwc")
         return out
 
-    def _res(self, x, blk: ResnetBlock):
-        g1 = self._gn(x, blk.norm1, True)
+    def _res(self, x, blk: ResnetBlock, x_sums=None):
+        """-> (block output, GroupNorm statistics of it or None). x_sums: statistics of x if its producer left them."""
+        g1 = self._gn(x, blk.norm1, True, sums=x_sums)
         B_, _, H_, W_ = g1.shape
         if self._own_ok(g1, blk.conv1) and self._own_ok((B_, blk.conv1.out_channels, H_, W_), blk.conv2):
-            h = self._own_conv(g1, blk.conv1)
-            g2 = self._gn(h, blk.norm2, True)
+            h, h_sums = self._own_conv(g1, blk.conv1, stats=True)
+            g2 = self._gn(h, blk.norm2, True, sums=h_sums)
             if isinstance(blk.nin_shortcut, nn.Identity):
                 sc = x
             elif self._own_ok(x, blk.nin_shortcut):
@@ -284,13 +307,13 @@ class NHWCDecoder:
             else:
                 sc = self._conv(x, blk.nin_shortcut)
                 sc = self._add(sc, self._bias(blk.nin_shortcut), None, None, out=sc)
-            return self._own_conv(g2, blk.conv2, resid=sc)
+            return self._own_conv(g2, blk.conv2, resid=sc, stats=True)
         h = self._conv(g1, blk.conv1)
         h = self._conv(self._gn(h, blk.norm2, True, pre_bias=self._bias(blk.conv1)), blk.conv2)
         if isinstance(blk.nin_shortcut, nn.Identity):
-            return self._add(h, self._bias(blk.conv2), x, None, out=h)
+            return self._add(h, self._bias(blk.conv2), x, None, out=h), None
         sc = self._conv(x, blk.nin_shortcut)
-        return self._add(h, self._bias(blk.conv2), sc, self._bias(blk.nin_shortcut), out=h)
+        return self._add(h, self._bias(blk.conv2), sc, self._bias(blk.nin_shortcut), out=h), None
 
     def _attn(self, x, blk: AttnBlock):
         B, Cc, H, W = x.shape
@@ -322,33 +345,36 @@ class NHWCDecoder:
         p = self._conv(o, blk.proj_out)
         return self._add(p, self._bias(blk.proj_out), x, None, out=p)
 
-    def _level(self, h, lvl):
+    def _level(self, h, lvl, sums=None):
         for i, blk in enumerate(lvl.block):
-            h = self._res(h, blk)
+            h, sums = self._res(h, blk, sums)
             if len(lvl.attn):
-                h = self._attn(h, lvl.attn[i])
-        return h
+                h, sums = self._attn(h, lvl.attn[i]), None
+        return h, sums
 
     def _upsample(self, h, conv: nn.Conv2d):
         B, Cc, H, W = h.shape
         up = torch.empty((B, Cc, 2 * H, 2 * W), dtype=h.dtype, device=h.device, memory_format=torch.channels_last)
         self.L.check(self.lib.var_b200_upsample2x_nhwc(h.data_ptr(), None, up.data_ptr(), B, H, W, Cc,
                                                        self.L.current_stream()), "upsample2x_nhwc")
-        return self._conv_any(up, conv)
+        if self._own_ok(up, conv):
+            return self._own_conv(up, conv, stats=True)
+        return self._conv_any(up, conv), None
 
     @torch.no_grad()
     def __call__(self, f_hat: torch.Tensor) -> torch.Tensor:
         d = self.dec
         x = f_hat.to(self.dtype).contiguous(memory_format=torch.channels_last)
-        h = self._conv_any(self._conv_any(x, self.post), d.conv_in)
-        h = self._res(h, d.mid.block_1)
+        h = self._conv_any(x, self.post)
+        h, sums = self._own_conv(h, d.conv_in, stats=True) if self._own_ok(h, d.conv_in) else (self._conv_any(h, d.conv_in), None)
+        h, _ = self._res(h, d.mid.block_1, sums)
         h = self._attn(h, d.mid.attn_1)
-        h = self._res(h, d.mid.block_2)
+        h, sums = self._res(h, d.mid.block_2)
         for lvl in reversed(d.up):
-            h = self._level(h, lvl)
+            h, sums = self._level(h, lvl, sums)
             if hasattr(lvl, "upsample"):
-                h = self._upsample(h, lvl.upsample.conv)
-        g = self._gn(h, d.norm_out, True)
+                h, sums = self._upsample(h, lvl.upsample.conv)
+        g = self._gn(h, d.norm_out, True, sums=sums)
         if self._own_ok(g, d.conv_out):  # 3 output channels as a 32-wide tile of the implicit GEMM
             h = self._own_conv(g, d.conv_out)
         else:
@@ -375,17 +401,19 @@ class NHWCEncoder(NHWCDecoder):
         else:
             w, b, _ = self._cw(e.conv_in)
             h = F.conv2d(x, w, b.to(self.dtype), padding=e.conv_in.padding)
+        sums = None
         for lvl in e.down:
-            h = self._level(h, lvl)
+            h, sums = self._level(h, lvl, sums)
             if hasattr(lvl, "downsample"):
                 dc = lvl.downsample.conv
+                sums = None
                 if self._own_ok(h, dc):  # stride-2 TMA boxes; the (0,1,0,1) zero pad is TMA's out-of-bounds fill
                     h = self._own_conv(h, dc)
                 else:
                     y = self._conv(F.pad(h, (0, 1, 0, 1)), dc)
                     h = self._add(y, self._bias(dc), None, None, out=y)
-        h = self._res(h, e.mid.block_1)
+        h, _ = self._res(h, e.mid.block_1, sums)
         h = self._attn(h, e.mid.attn_1)
-        h = self._res(h, e.mid.block_2)
-        h = self._conv_any(self._conv_any(self._gn(h, e.norm_out, True), e.conv_out), self.qconv)
+        h, sums = self._res(h, e.mid.block_2)
+        h = self._conv_any(self._conv_any(self._gn(h, e.norm_out, True, sums=sums), e.conv_out), self.qconv)
         return h.float().contiguous()  # fp32 NCHW features for the quantizer

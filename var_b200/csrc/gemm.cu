@@ -213,7 +213,7 @@ int gemm_launch(const void* A, const void* W, const GemmParams& p_in, int epi, c
 }
 
 int conv3x3_launch(const void* x, const void* w_packed, const float* bias, const void* resid, void* out, int B, int H,
-                   int W, int Cin, int Cout, cudaStream_t st, int stride) {
+                   int W, int Cin, int Cout, cudaStream_t st, int stride, float2* gn_part) {
   VB_REQUIRE(x && w_packed && out && B > 0 && H > 0 && W > 0, "conv3x3: bad arguments");
   VB_REQUIRE(stride == 1 || stride == 2, "conv3x3: stride %d (1 or 2)", stride);
   if (stride == 2) {  // H, W: input extent; the GEMM rows are the (H/2) x (W/2) output pixels
@@ -237,6 +237,7 @@ int conv3x3_launch(const void* x, const void* w_packed, const float* bias, const
   p.resid_bf16 = reinterpret_cast<const __nv_bfloat16*>(resid);
   p.conv_cin = Cin;
   p.conv_stride = stride;
+  p.gn_part = gn_part;
   return gemm_launch(x, w_packed, p, EPI_BIAS_BF16, st, Cout % 160 == 0 ? 160 : (Cout == 32 ? 32 : 0));
 }
 

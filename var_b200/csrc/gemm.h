@@ -69,6 +69,10 @@ struct GemmParams {
   // kept (profiles/r02_gemm_dram_probe.txt): evict-first activations (the N tiles of an M block share them through
   // L2: 2-5x the reads), evict-first epilogue traffic (no gain, proj slower), rotated K order per tile (more reads).
   unsigned long long l2_hint_a, l2_hint_w;
+  // EPI_BIAS_BF16, conv mode: per-channel (sum, sum of squares) of the stored bf16 outputs over every 128-row block
+  // (= 128 pixels of one image): gn_part[(m / 128) * N + n] as float2, fixed summation order. The GroupNorm that
+  // follows the convolution (models/basic_vae.py:57-58) takes its statistics from these instead of re-reading the tensor.
+  float2* gn_part;
   int a_cols;  // true column count of A when it is narrower than K (K padded to 64; the tail reads as zeros), 0 = K
   // Block-diagonal batching (VQVAE AttnBlock, models/basic_vae.py:74-87: one bmm per image). Rows [j*bd_rows,
   // (j+1)*bd_rows) of A use the W rows shifted by j*bd_w_row and the W columns shifted by j*bd_w_k; bd_rows must be a
@@ -87,6 +91,6 @@ int gemm_launch(const void* A, const void* W, const GemmParams& p, int epi, cuda
 // (tap-major, channels zero-padded to kpt*64), out [B,H,W,Cout] bf16 = conv + bias (+ resid). Requires Cout % 32 == 0,
 // Cin % 8 == 0, W | 128 or 128 | W, (H*W) % 128 == 0.
 int conv3x3_launch(const void* x, const void* w_packed, const float* bias, const void* resid, void* out, int B, int H,
-                   int W, int Cin, int Cout, cudaStream_t st, int stride = 1);
+                   int W, int Cin, int Cout, cudaStream_t st, int stride = 1, float2* gn_part = nullptr);
 
 }  // namespace vb

@@ -52,6 +52,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bars[2 * STAGES + 4];
   __shared__ uint32_t tmem_base_smem;
+  // GroupNorm statistics of the conv epilogue: [sub-warp][chunk parity][lane quarter][channel of the chunk] (sum, sumsq)
+  __shared__ float2 gn_red[EPI == EPI_BIAS_BF16 ? GEMM_EPI_SUB * 2 * 4 * 32 : 1];
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5;
@@ -530,6 +532,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               srow[j] = w;
             }
             __syncwarp();
+            float gs[8], gq[8];  // GroupNorm statistics (conv epilogue): this lane's 8 channels over its 4 rows
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { gs[e] = 0.f; gq[e] = 0.f; }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int r = rsub + 8 * i;
@@ -545,11 +550,46 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                     for (int e = 0; e < 4; ++e) a2[e] = __hadd2(a2[e], b2[e]);
                   }
+                  if (p.gn_part != nullptr) {  // statistics of exactly the values that are stored
+                    const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&w);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                      const float2 f = __bfloat1622float2(a2[e]);
+                      gs[2 * e] += f.x; gq[2 * e] = fmaf(f.x, f.x, gq[2 * e]);
+                      gs[2 * e + 1] += f.y; gq[2 * e + 1] = fmaf(f.y, f.y, gq[2 * e + 1]);
+                    }
+                  }
                 }
                 *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off) = w;
               }
             }
             __syncwarp();
+            if constexpr (EPI == EPI_BIAS_BF16) {
+              if (p.gn_part != nullptr) {
+                // rows of the warp: lanes with equal cg (xor 4, 8, 16); then the four lane quarters of the tile meet in
+                // shared memory (named barrier per sub-warp group) and quarter 0 writes the 128-row partial, fixed order
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+#pragma unroll
+                  for (int o = 4; o <= 16; o <<= 1) {
+                    gs[e] += __shfl_xor_sync(0xffffffffu, gs[e], o);
+                    gq[e] += __shfl_xor_sync(0xffffffffu, gq[e], o);
+                  }
+                }
+                float2* red = gn_red + ((half * 2 + (i & 1)) * 4) * 32;
+                if (lane < 4) {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) red[quarter * 32 + cg * 8 + e] = make_float2(gs[e], gq[e]);
+                }
+                named_bar_sync(1 + half, 128);
+                if (quarter == 0 && n0 + lane < p.N) {
+                  float2 t = red[lane];
+#pragma unroll
+                  for (int q = 1; q < 4; ++q) { t.x += red[q * 32 + lane].x; t.y += red[q * 32 + lane].y; }
+                  p.gn_part[(size_t)(row_w0 / GEMM_BM) * p.N + n0 + lane] = t;
+                }
+              }
+            }
           }
         }
       }

@@ -6,6 +6,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "gemm.h"
 #include "host.h"
 #include "../../include/var_b200.h"
 
@@ -134,6 +135,36 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ p
   }
 }
 
+// Statistics that the producing convolution's epilogue left behind (gemm_sm100.cuh, gn_part): per 128-pixel block and
+// channel (sum, sum of squares) -> per image and group, in a fixed order: thread (g, k) sums the blocks k, k+8, ... of
+// its group's channels, then the eight partial sums of a group are added in order. One CTA per image.
+__global__ void __launch_bounds__(256)
+gn_finalize_kernel(const float2* __restrict__ part, int T, int C, int G, float* __restrict__ sums) {
+  __shared__ float2 red[256];
+  const int b = blockIdx.x;
+  const int cpg = C / G;
+  const int g = threadIdx.x >> 3, k = threadIdx.x & 7;
+  float s = 0.f, q = 0.f;
+  if (g < G) {
+    for (int t = k; t < T; t += 8) {
+      const float2* pp = part + ((size_t)b * T + t) * C + g * cpg;
+      for (int c = 0; c < cpg; ++c) {
+        const float2 v = __ldg(pp + c);
+        s += v.x;
+        q += v.y;
+      }
+    }
+  }
+  red[threadIdx.x] = make_float2(s, q);
+  __syncthreads();
+  if (g < G && k == 0) {
+    float ss = 0.f, qq = 0.f;
+    for (int i = 0; i < 8; ++i) { ss += red[threadIdx.x + i].x; qq += red[threadIdx.x + i].y; }
+    sums[((size_t)b * G + g) * 2] = ss;
+    sums[((size_t)b * G + g) * 2 + 1] = qq;
+  }
+}
+
 // out = a (+ bias_a[c]) + b (+ bias_b[c]); any of b / bias_a / bias_b may be null. In place allowed (out == a).
 __global__ void __launch_bounds__(256)
 add_bias_nhwc_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ bias_a, const __nv_bfloat16* b,
@@ -246,5 +277,44 @@ extern "C" int var_b200_gn_silu_nhwc(const void* x, const float* pre_bias, const
       reinterpret_cast<__nv_bfloat16*>(y), HW, C, groups, eps, apply_silu, ppc);
   VB_CUDA_CHECK(cudaGetLastError());
   vb::count_launch(2);
+  return VB_OK;
+}
+
+extern "C" size_t var_b200_conv3x3_gn_workspace(int B, int H, int W, int Cout) {
+  if (B <= 0 || H <= 0 || W <= 0 || Cout <= 0) return 0;
+  return (size_t)B * ((size_t)H * W / 128) * Cout * sizeof(float2);
+}
+
+extern "C" int var_b200_conv3x3_gn_nhwc(const void* x, const void* w_packed, const float* bias, const void* resid, void* out,
+                                        int B, int H, int W, int Cin, int Cout, int groups, float* gn_sums, void* work,
+                                        size_t work_bytes, void* stream) {
+  using namespace vb;
+  VB_REQUIRE(gn_sums && work && groups > 0 && groups <= 32 && Cout % groups == 0, "conv3x3_gn: bad arguments (groups=%d)", groups);
+  VB_REQUIRE(work_bytes >= var_b200_conv3x3_gn_workspace(B, H, W, Cout), "conv3x3_gn: workspace too small");
+  VB_REQUIRE(((size_t)H * W) % 256 == 0, "conv3x3_gn: H*W=%d must be a multiple of 256 (a CTA pair's tile stays inside one image)", H * W);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = conv3x3_launch(x, w_packed, bias, resid, out, B, H, W, Cin, Cout, st, 1, reinterpret_cast<float2*>(work));
+  if (rc) return rc;
+  vb::ProfScope prof_scope(vb::PK_OTHER, st);
+  gn_finalize_kernel<<<B, 256, 0, st>>>(reinterpret_cast<const float2*>(work), H * W / 128, Cout, groups, gn_sums);
+  VB_CUDA_CHECK(cudaGetLastError());
+  vb::count_launch();
+  return VB_OK;
+}
+
+extern "C" int var_b200_gn_apply_nhwc(const void* x, const float* gn_sums, const float* gamma, const float* beta, void* y, int B,
+                                      int HW, int C, int groups, float eps, int apply_silu, void* stream) {
+  using namespace vb;
+  VB_REQUIRE(x && gn_sums && gamma && beta && y, "gn_apply: null pointer");
+  VB_REQUIRE(B > 0 && B <= 65535 && HW > 0 && C > 0 && C % 8 == 0 && groups > 0 && groups <= 64 && C % groups == 0 &&
+                 C / 8 <= GN_THREADS, "gn_apply: unsupported shape B=%d HW=%d C=%d groups=%d", B, HW, C, groups);
+  cudaStream_t st = (cudaStream_t)stream;
+  vb::ProfScope prof_scope(vb::PK_OTHER, st);
+  const int ppc = 256;
+  gn_apply_kernel<<<dim3((HW + ppc - 1) / ppc, B), GN_THREADS, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), nullptr, gn_sums, 1, gamma, beta, reinterpret_cast<__nv_bfloat16*>(y), HW, C,
+      groups, eps, apply_silu, ppc);
+  VB_CUDA_CHECK(cudaGetLastError());
+  vb::count_launch();
   return VB_OK;
 }

@@ -117,6 +117,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.var_b200_ln_tables_workspace.restype = C.c_size_t
     lib.var_b200_gn_workspace.argtypes = [i32, i32, i32, i32]
     lib.var_b200_gn_workspace.restype = C.c_size_t
+    lib.var_b200_conv3x3_gn_workspace.argtypes = [i32, i32, i32, i32]
+    lib.var_b200_conv3x3_gn_workspace.restype = C.c_size_t
     lib.var_b200_vae_attn_workspace.argtypes = [i32, i32, i32, i32]
     lib.var_b200_vae_attn_workspace.restype = C.c_size_t
     lib.var_b200_quant_encode_workspace.argtypes = [C.POINTER(QuantDesc), i32]
@@ -150,6 +152,8 @@ def _EXTRA_SIGS(vp, i32, i64, f32):
         "var_b200_upsample2x_nhwc": [vp, vp, vp, i32, i32, i32, i32, vp],
         "var_b200_conv3x3_s2_nhwc": [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
         "var_b200_conv1x1_nhwc": [vp, vp, vp, vp, vp, C.c_longlong, i32, i32, vp],
+        "var_b200_conv3x3_gn_nhwc": [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, sz, vp],
+        "var_b200_gn_apply_nhwc": [vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, i32, vp],
         "var_b200_vae_attn_block": [vp, vp, vp, i32, f32, vp, vp, vp, vp, vp, i32, i32, i32, vp, sz, vp],
         "var_b200_ada_ld": [C.POINTER(ModelDesc)],
         "var_b200_ada_params": [C.POINTER(ModelDesc), vp, i32, vp, vp, sz, vp],
