@@ -393,8 +393,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // loads in flight compete with the TMA operand stream for the SM's L2 ingress.)
         int seqs[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) seqs[i] = (row_w0 + rsub + 8 * i) / p.rows_per_seq;
+        for (int i = 0; i < 4; ++i) {  // rows beyond M (tile tail) are clamped: their loads stay in bounds, nothing is stored
+          const int rg = row_w0 + rsub + 8 * i;
+          seqs[i] = (rg < p.M ? rg : p.M - 1) / p.rows_per_seq;
+        }
         float ln_s1[4] = {0.f, 0.f, 0.f, 0.f}, ln_s2[4] = {0.f, 0.f, 0.f, 0.f};  // LNF: partial row sums of x_new
+        // The four row groups of a lane nearly always belong to one sequence (rows_per_seq >= 32 and aligned): gate and
+        // the next LayerNorm's scale are then one load per 16-column half instead of four, and the loads of BOTH halves
+        // of a chunk (bias, gate, scale, 8 residual vectors) are requested together, right behind the TMEM load, so that
+        // one memory round trip covers the chunk instead of two (same-box A/B, tools/gemm_one.py: proj + LN outputs d30
+        // 1065 -> 985 us, d16 275 -> 242 us; fc2 unchanged or better). Requesting the NEXT chunk's loads as well was
+        // measured too and is slower (d30 proj 1074-1240 us): that many loads in flight compete with the TMA operand
+        // stream for the SM's L2 ingress.
+        const bool one_seq = seqs[0] == seqs[3];
 #pragma unroll 1
         for (int c = half; c < BN / 32; c += GEMM_EPI_SUB) {
           const int n0 = n_base + c * 32;
@@ -402,6 +413,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           float v[32];
           __syncwarp();
           tmem_ld_32x32(taddr + c * 32, v);
+          float4 b4[2], g1[2], sc1[2], rs4[2][4];
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const int col = n0 + 16 * h2 + 4 * cg;
+            b4[h2] = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+            g1[h2] = __ldg(reinterpret_cast<const float4*>(p.gate + (size_t)seqs[0] * p.gate_ld + col));
+            if constexpr (LNF) sc1[h2] = __ldg(reinterpret_cast<const float4*>(p.ln_scale + (size_t)seqs[0] * p.gate_ld + col));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {  // all loads of the chunk before its stores: resid may alias out
+              const int rg = row_w0 + rsub + 8 * i;
+              if (rg < p.M) rs4[h2][i] = *reinterpret_cast<const float4*>(p.resid + (size_t)rg * p.N + col);
+            }
+          }
           tmem_ld_wait_dep(v);
 #pragma unroll
           for (int h2 = 0; h2 < 2; ++h2) {
@@ -411,31 +435,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               srow[j] = make_float4(v[16 * h2 + 4 * j], v[16 * h2 + 4 * j + 1], v[16 * h2 + 4 * j + 2], v[16 * h2 + 4 * j + 3]);
             __syncwarp();
             const int col = n0 + 16 * h2 + 4 * cg;
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-            float4 g4[4], rs4[4], sc4[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {  // all loads before the stores: resid may alias out
-              const int rg = row_w0 + rsub + 8 * i;
-              if (rg < p.M) {
-                g4[i] = __ldg(reinterpret_cast<const float4*>(p.gate + (size_t)seqs[i] * p.gate_ld + col));
-                rs4[i] = *reinterpret_cast<const float4*>(p.resid + (size_t)rg * p.N + col);
-                if constexpr (LNF) sc4[i] = __ldg(reinterpret_cast<const float4*>(p.ln_scale + (size_t)seqs[i] * p.gate_ld + col));
-              }
-            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int r = rsub + 8 * i;
               const int rg = row_w0 + r;
               if (rg < p.M) {
+                float4 g = g1[h2], sc = sc1[h2];
+                if (!one_seq) {  // a warp that straddles a sequence boundary (small scales): per-row-group vectors
+                  g = __ldg(reinterpret_cast<const float4*>(p.gate + (size_t)seqs[i] * p.gate_ld + col));
+                  if constexpr (LNF) sc = __ldg(reinterpret_cast<const float4*>(p.ln_scale + (size_t)seqs[i] * p.gate_ld + col));
+                }
                 const float4 a = *reinterpret_cast<const float4*>(stg + r * EPI_STG_LD + 4 * cg);
-                const float4 rs = rs4[i];
-                const float4 o = make_float4(fmaf(a.x + b4.x, g4[i].x, rs.x), fmaf(a.y + b4.y, g4[i].y, rs.y),
-                                             fmaf(a.z + b4.z, g4[i].z, rs.z), fmaf(a.w + b4.w, g4[i].w, rs.w));
+                const float4 rs = rs4[h2][i];
+                const float4 b = b4[h2];
+                const float4 o = make_float4(fmaf(a.x + b.x, g.x, rs.x), fmaf(a.y + b.y, g.y, rs.y),
+                                             fmaf(a.z + b.z, g.z, rs.z), fmaf(a.w + b.w, g.w, rs.w));
                 *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)rg * p.N + col) = o;
                 if constexpr (LNF) {
                   ln_s1[i] += (o.x + o.y) + (o.z + o.w);
                   ln_s2[i] += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
-                  const float4 sc = sc4[i];
                   *reinterpret_cast<uint2*>(p.ln_a_out + (size_t)rg * p.N + col) =
                       make_uint2(pack_bf16x2(fmaf(o.x, sc.x, o.x), fmaf(o.y, sc.y, o.y)),
                                  pack_bf16x2(fmaf(o.z, sc.z, o.z), fmaf(o.w, sc.w, o.w)));
