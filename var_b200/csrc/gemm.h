@@ -64,10 +64,10 @@ struct GemmParams {
   int conv_cin;  // true channel count of the activation tensor (the tensor map's innermost extent; tails read as zeros)
   // Operand leading dimensions in elements (0 = K): a column slice of a wider row-major matrix can be an operand.
   int lda, ldw;
-  // L2 eviction priority of the two operand streams (TMA cache hints; 0 = normal). The weights are re-read by every
-  // M block for the whole launch: evict-last saves 0.2-0.7 GB of DRAM reads per d30 fc1 / fc2 launch. Measured and not
-  // kept (profiles/r02_gemm_dram_probe.txt): evict-first activations (the N tiles of an M block share them through
-  // L2: 2-5x the reads), evict-first epilogue traffic (no gain, proj slower), rotated K order per tile (more reads).
+  // L2 eviction priority of the two operand streams (TMA cache hints; 0 = normal; VAR_B200_L2HINT for experiments).
+  // Measured (profiles/r02_gemm_dram_probe.txt): evict-last weights save 0.2-0.7 GB of DRAM reads per d30 fc1 / fc2
+  // launch but no step time; evict-first activations cost 2-5x the reads (the N tiles of an M block share them through
+  // L2); evict-first epilogue traffic and a rotated K order per tile do not help either. Default: no hints.
   unsigned long long l2_hint_a, l2_hint_w;
   // EPI_BIAS_BF16, conv mode: per-channel (sum, sum of squares) of the stored bf16 outputs over every 128-row block
   // (= 128 pixels of one image): gn_part[(m / 128) * N + n] as float2, fixed summation order. The GroupNorm that
