@@ -62,30 +62,58 @@ __device__ void bitonic_sort(float* key, int* val, int n) {
   }
 }
 
-// Exact k-th largest of xs[0..V) by a 4-pass radix select on order-preserving keys (whole CTA; hist[256] and the two
-// scalars live in shared memory). Ends with a barrier.
+// Exact k-th largest of xs[0..V) by a 4-pass radix select on order-preserving keys (whole CTA). hist is
+// [ST/32][256]: one histogram per warp, so a shared-memory atomic only ever collides with lanes of its own warp (the
+// top byte of a logit takes a handful of values: a single histogram serialised nearly all 4096 updates of the first
+// pass), and the bin that holds the k-th largest is found by warp 0 with a suffix scan over the summed bins (eight
+// bins per lane + one shuffle scan) instead of a 255-step loop on one thread. Ends with a barrier.
 __device__ float block_kth_largest(const float* xs, int V, int k, int* hist, uint32_t* sel_prefix, int* sel_k) {
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) { *sel_prefix = 0; *sel_k = k; }
+  int* my = hist + warp * 256;
   for (int pass = 0; pass < 4; ++pass) {
     const int shift = 24 - 8 * pass;
-    hist[tid] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) my[lane + 32 * i] = 0;
     __syncthreads();
     const uint32_t prefix = *sel_prefix;
     const uint32_t mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
     for (int v = tid; v < V; v += ST) {
       const uint32_t key = f2key(xs[v]);
-      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255], 1);
+      if ((key & mask) == prefix) atomicAdd(&my[(key >> shift) & 255], 1);
     }
     __syncthreads();
-    if (tid == 0) {
-      int need = *sel_k, bin = 255;
-      for (; bin > 0; --bin) {
-        if (hist[bin] >= need) break;
-        need -= hist[bin];
+    if (warp == 0) {
+      // lane L owns bins [8L, 8L+8): c[i] = count of bin 8L+i over all warps; suffix sums from the top bin down
+      int c[8], tot = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        int a = 0;
+#pragma unroll
+        for (int w = 0; w < ST / 32; ++w) a += hist[w * 256 + 8 * lane + i];
+        c[i] = a;
+        tot += a;
       }
-      *sel_k = need;
-      *sel_prefix = prefix | ((uint32_t)bin << shift);
+      int above = tot;  // inclusive suffix over lanes: counts of all bins >= 8L
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t2 = __shfl_down_sync(0xffffffffu, above, o);
+        if (lane + o < 32) above += t2;
+      }
+      above -= tot;  // bins strictly above this lane's eight
+      const int need = *sel_k;
+      // the wanted bin is the highest b with (count of bins > b) < need <= (count of bins >= b); exactly one lane has it
+      int acc = above, found = -1, need_out = 0;
+#pragma unroll
+      for (int i = 7; i >= 0; --i) {
+        if (found < 0 && acc < need && need <= acc + c[i]) { found = 8 * lane + i; need_out = need - acc; }
+        acc += c[i];
+      }
+      // fewer than `need` matching keys in total cannot happen (need <= remaining count by construction), but bin 0 is the
+      // fallback of the serial version: keep it
+      const unsigned has = __ballot_sync(0xffffffffu, found >= 0);
+      if (has == 0) { if (lane == 0) { *sel_prefix = prefix; } }
+      else if (found >= 0) { *sel_k = need_out; *sel_prefix = prefix | ((uint32_t)found << shift); }
     }
     __syncthreads();
   }
@@ -103,7 +131,7 @@ sample_kernel(const float* __restrict__ logits, int B, int l, int V, int use_cfg
   float* sk = xs + V;                               // [Vpow2] sort keys (top-p only)
   int* sv = reinterpret_cast<int*>(sk + Vpow2);     // [Vpow2] sort payload (top-p only)
   __shared__ float red[ST / 32];
-  __shared__ int hist[256];
+  __shared__ int hist[(ST / 32) * 256];
   __shared__ uint32_t sel_prefix;
   __shared__ int sel_k;
   __shared__ float bval[ST / 32];
@@ -261,7 +289,7 @@ expected_dist_kernel(const float* __restrict__ lc, const float* __restrict__ lu,
   extern __shared__ float sm[];
   float* xs = sm;  // [V]
   __shared__ float red[ST / 32];
-  __shared__ int hist[256];
+  __shared__ int hist[(ST / 32) * 256];
   __shared__ uint32_t sel_prefix;
   __shared__ int sel_k;
   const int t = blockIdx.x, s = blockIdx.y, tid = threadIdx.x;
