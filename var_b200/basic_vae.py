@@ -1,9 +1,11 @@
-"""CNN encoder / decoder of the VQVAE (PyTorch, cuDNN): boundary helpers, not hand-written kernels.
+"""CNN encoder / decoder of the VQVAE (models/basic_vae.py:99-226).
 
-`north_star` keeps these dense convolutions outside the hot path; they exist here
-because the drop-in boundary functions VQVAE.img_to_idxBl / fhat_to_img call them (models/vqvae.py:62-67). The
-module tree reproduces the reference's state_dict keys (models/basic_vae.py:99-226) so `vae_ch160v4096z32.pth`
-loads with strict=True.
+Two forms live here. The `nn.Module` tree (`Encoder`, `Decoder`, `ResnetBlock`, `AttnBlock`) reproduces the reference's
+state_dict keys so `vae_ch160v4096z32.pth` loads with strict=True, and is the fp32 PyTorch parity reference (its encoder
+produces the bit-exact token indices). The execution plans `NHWCDecoder` / `NHWCEncoder` run the same functions on bf16
+channels-last tensors entirely on var_b200's own kernels (implicit-GEMM convolutions on the tcgen05 GEMM, stride-2 TMA
+boxes, block-diagonally batched AttnBlock, GroupNorm with statistics from the producing convolution's epilogue); cuDNN is
+only the fallback for shapes the kernels do not tile and the `own_conv=False` A/B switch.
 """
 from __future__ import annotations
 
@@ -146,8 +148,9 @@ class Decoder(nn.Module):
 class NHWCDecoder:
     """16-bit channels-last execution plan of a `Decoder` (+ post_quant_conv). The 3x3 convolutions run on var_b200's own
     implicit-GEMM tcgen05 kernel (`var_b200_conv3x3_nhwc`: nine shifted TMA boxes per K sweep, bias and the ResnetBlock
-    shortcut fused into the epilogue) and the 1x1 shortcuts on the plain GEMM; shapes the kernel cannot tile
-    (`own_conv=False`, odd widths, 3 output channels) fall back to bias-free cuDNN NHWC convolutions. Everything between
+    shortcut fused into the epilogue; 3-channel ends padded to 8 inputs / 32 outputs) and the 1x1 convolutions on the plain
+    GEMM; shapes the kernel cannot tile (odd widths) and `own_conv=False` fall back to bias-free cuDNN NHWC convolutions.
+    The AttnBlock is `var_b200_vae_attn_block`. Everything between
     the convolutions is var_b200's NHWC glue (csrc/groupnorm.cu): GroupNorm+SiLU in two passes, residual adds with the
     convolution biases folded in, nearest-2x up-sampling. Same function as
     Decoder.forward(post_quant_conv(f_hat)) up to 16-bit rounding
