@@ -178,7 +178,8 @@ def _attn_ref(q, k, v, q_pos0, ends):
 
 @pytest.mark.parametrize("scale,bound,q_log2", [(6.0, 0.0, 0), (6.0, 6.0, 0), (6.0, 6.0, 1), (6.0, 43.0, 1), (40.0, 40.0, 1)],
                          ids=["general", "bounded", "bounded_log2", "bounded_loose_log2", "bounded_scale40_log2"])
-@pytest.mark.parametrize("n_seq,H,si", [(2, 2, None), (3, 16, None), (2, 4, 0), (4, 2, 3), (2, 30, 9), (1, 2, 8), (5, 3, 7)])
+@pytest.mark.parametrize("n_seq,H,si", [(2, 2, None), (3, 16, None), (2, 4, 0), (4, 2, 3), (2, 30, 9), (1, 2, 8), (5, 3, 7),
+                                        (7, 5, 1), (3, 30, 2), (64, 3, 4), (2, 2, 5), (2, 3, 6)])
 def test_attention_block_causal(n_seq, H, si, scale, bound, q_log2):
     """General kernel (per-row reference maximum, 4 softmax warps) and the bounded-score kernel (fixed reference =
     the caller's bound on |q.k|, 8 softmax warps) against fp32 softmax attention with the block-causal mask."""
@@ -199,6 +200,33 @@ def test_attention_block_causal(n_seq, H, si, scale, bound, q_log2):
                                         pos0, 10, arr, bound, q_log2, L.current_stream()), "attention")
     torch.cuda.synchronize()
     ref = _attn_ref(qb.float() / math.log2(math.e) if q_log2 else qb, kb, vb, pos0, ends)
+    err = (out.float() - ref).abs().max().item()
+    assert torch.isfinite(out.float()).all() and err < 3e-2, f"max err {err}"
+
+
+@pytest.mark.parametrize("Lq", [1, 5, 14, 30])
+@pytest.mark.parametrize("q_log2", [0, 1])
+def test_attention_small_prefix_spans_levels(Lq, q_log2):
+    """The warp-per-item kernel of the first scales (csrc/attn_small.cu: <= 32 queries, <= 64 visible keys) on a
+    teacher-forced PREFIX of the sequence: the query rows lie on different pyramid levels, every row has its own key
+    limit (1, 5, 14, 30), checked against fp32 softmax attention with the block-causal mask."""
+    torch.manual_seed(11 + Lq)
+    ends = list(np.cumsum([p * p for p in PATCH_NUMS]))
+    n_seq, H, Lmax = 9, 7, 680
+    q = torch.nn.functional.normalize(torch.randn(n_seq, H, Lq, 64, device=DEV), dim=-1) * 8.0
+    k = torch.nn.functional.normalize(torch.randn(n_seq, H, Lmax, 64, device=DEV), dim=-1)
+    v = torch.randn(n_seq, H, Lmax, 64, device=DEV)
+    v[:, :, 64:] = float("nan")  # keys no row of this call may touch
+    qb = (q * math.log2(math.e)).bfloat16() if q_log2 else q.bfloat16()
+    kb, vb = k.bfloat16(), v.bfloat16()
+    out = torch.full((n_seq, Lq, H * 64), float("nan"), device=DEV, dtype=torch.bfloat16)
+    arr = (C.c_int * 10)(*[int(e) for e in ends])
+    L.check(L.load().var_b200_attention(qb.data_ptr(), kb.data_ptr(), vb.data_ptr(), out.data_ptr(), n_seq, H, Lq, Lmax, 0, 10,
+                                        arr, 8.0 if q_log2 else 0.0, q_log2, L.current_stream()), "attention")
+    torch.cuda.synchronize()
+    vref = vb.clone()
+    vref[:, :, 64:] = 0
+    ref = _attn_ref(qb.float() / math.log2(math.e) if q_log2 else qb, kb, vref, 0, ends)
     err = (out.float() - ref).abs().max().item()
     assert torch.isfinite(out.float()).all() and err < 3e-2, f"max err {err}"
 

@@ -20,5 +20,9 @@ struct AttnArgs {
 };
 
 int attn_launch(const AttnArgs& a, cudaStream_t st);
+// Warp-per-item kernel for the first KV-cached scales (attn_small.cu): at most 32 queries and 64 visible keys per
+// (sequence, head). kv_vis = keys visible to the last query row of the call.
+bool attn_small_applies(const AttnArgs& a, int kv_vis);
+int attn_small_launch(const AttnArgs& a, int kv_vis, cudaStream_t st);
 
 }  // namespace vb

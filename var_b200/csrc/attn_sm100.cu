@@ -725,6 +725,11 @@ int attn_launch(const AttnArgs& a, cudaStream_t st) {
   AttnLevels lv;
   lv.n = a.n_scales;
   for (int i = 0; i < VB_MAX_SCALES; ++i) lv.end[i] = i < a.n_scales ? a.level_end[i] : a.level_end[a.n_scales - 1];
+  int kv_vis = lv.end[VB_MAX_SCALES - 1];  // keys visible to the last query row = the most any row of this call sees
+  for (int sc = VB_MAX_SCALES - 2; sc >= 0; --sc) kv_vis = (a.q_pos0 + a.Lq - 1 < lv.end[sc]) ? lv.end[sc] : kv_vis;
+  // VAR_B200_ATTN_SMALL=0 keeps the tcgen05 kernel for every shape (A/B runs)
+  static const bool small_on = [] { const char* e = getenv("VAR_B200_ATTN_SMALL"); return e ? atoi(e) != 0 : true; }();
+  if (small_on && attn_small_applies(a, kv_vis)) return attn_small_launch(a, kv_vis, st);
   CUtensorMap tmQ, tmK, tmV;
   const uint64_t nbh = (uint64_t)a.n_seq * a.H;
   {
@@ -735,7 +740,10 @@ int attn_launch(const AttnArgs& a, cudaStream_t st) {
     if (r) return r;
   }
   {
-    uint64_t dims[3] = {64, (uint64_t)a.Lmax, nbh};
+    // Keys no query of this call can see are declared out of bounds: TMA zero-fills them without touching memory
+    // (the KV-cached steps of the small scales would otherwise read a full 64-row box of K and of V per item - 16 KB for
+    // 1..55 visible keys; zero K rows are masked by the level limit anyway, zero V rows contribute nothing).
+    uint64_t dims[3] = {64, (uint64_t)(kv_vis < a.Lmax ? kv_vis : a.Lmax), nbh};
     uint64_t str[2] = {128, (uint64_t)a.Lmax * 128};
     uint32_t box[3] = {64, ATT_BN, 1};
     int r = make_tmap_bf16_sw128(&tmK, a.k, 3, dims, str, box);
