@@ -170,21 +170,25 @@ int expand_shared_aln(const float* shared, int shared_ld, const float* gss, floa
 // ------------------------------------------------------------------------------------------------
 constexpr int EMB_ROWS = 32;  // rows per CTA
 
-// CTA = 256 channels x EMB_ROWS rows. Each thread keeps its channel's 32 word_embed weights in registers (w_word is
-// stored transposed [Cvae, C] so the load is coalesced) and walks the rows; x_in rows are staged in shared memory.
+// CTA = 256 channels x EMB_ROWS token positions of ONE input sequence. The n_seq output sequences share n_x input
+// sequences (sequence s reads input s % n_x: the cond / uncond halves of a CFG batch share the sampled tokens, the 1000
+// class hypotheses of likelihood scoring all share the image's tokens), so word_embed(x) + position / level embedding
+// is computed once per (input sequence, token, channel) and stored to every output sequence that uses it; only the
+// class-dependent first rows are per sequence. Each thread keeps its channel's 32 word_embed weights in registers
+// (w_word is stored transposed [Cvae, C] so the load is coalesced); x_in rows are staged in shared memory.
 __global__ void __launch_bounds__(256)
 embed_kernel(const float* __restrict__ x_in, int n_x, int l_in, const int* __restrict__ labels,
              const float* __restrict__ class_emb, const float* __restrict__ pos_start,
              const float* __restrict__ lvl_pos, const float* __restrict__ w_word_t, const float* __restrict__ b_word,
-             float* __restrict__ out, int n_rows, int l, int first_rows, int pos0, int C) {
+             float* __restrict__ out, int n_seq, int l, int first_rows, int pos0, int C) {
   __shared__ __align__(16) float xin[EMB_ROWS][32];
   const int c = blockIdx.x * 256 + threadIdx.x;
-  const int r0 = blockIdx.y * EMB_ROWS;
-  const int nr = min(EMB_ROWS, n_rows - r0);
+  const int xs = blockIdx.z;                 // input sequence
+  const int t0 = blockIdx.y * EMB_ROWS;      // first token position of this CTA
+  const int nr = min(EMB_ROWS, l - t0);
   for (int i = threadIdx.x; i < nr * 32; i += 256) {
-    const int r = r0 + (i >> 5), k = i & 31;
-    const int s = r / l, t = r - s * l;
-    xin[i >> 5][k] = (t >= first_rows) ? x_in[((size_t)(s % n_x) * l_in + (t - first_rows)) * 32 + k] : 0.f;
+    const int t = t0 + (i >> 5), k = i & 31;
+    xin[i >> 5][k] = (t >= first_rows) ? x_in[((size_t)xs * l_in + (t - first_rows)) * 32 + k] : 0.f;
   }
   __syncthreads();
   if (c >= C) return;
@@ -193,14 +197,14 @@ embed_kernel(const float* __restrict__ x_in, int n_x, int l_in, const int* __res
   for (int k = 0; k < 32; ++k) w[k] = __ldg(w_word_t + (size_t)k * C + c);
   const float bw = __ldg(b_word + c);
   for (int i = 0; i < nr; ++i) {
-    const int r = r0 + i;
-    const int s = r / l, t = r - s * l;
+    const int t = t0 + i;
     const float lp = __ldg(lvl_pos + (size_t)(pos0 + t) * C + c);
-    float v;
-    if (t < first_rows) {
-      v = (__ldg(class_emb + (size_t)__ldg(labels + s) * C + c) + __ldg(pos_start + (size_t)t * C + c)) + lp;
+    if (t < first_rows) {  // class token rows: per output sequence
+      const float ps = __ldg(pos_start + (size_t)t * C + c);
+      for (int s = xs; s < n_seq; s += n_x)
+        out[((size_t)s * l + t) * C + c] = (__ldg(class_emb + (size_t)__ldg(labels + s) * C + c) + ps) + lp;
     } else {
-      // the row's 32 inputs as eight 16-byte broadcast loads (the scalar version was bound by its 32 LDS per output)
+      // the row's 32 inputs as eight 16-byte broadcast loads
       const float4* xr = reinterpret_cast<const float4*>(xin[i]);
       float acc = 0.f;
 #pragma unroll
@@ -211,9 +215,9 @@ embed_kernel(const float* __restrict__ x_in, int n_x, int l_in, const int* __res
         acc = fmaf(xv.z, w[4 * k + 2], acc);
         acc = fmaf(xv.w, w[4 * k + 3], acc);
       }
-      v = (acc + bw) + lp;
+      const float v = (acc + bw) + lp;
+      for (int s = xs; s < n_seq; s += n_x) out[((size_t)s * l + t) * C + c] = v;
     }
-    out[(size_t)r * C + c] = v;
   }
 }
 
@@ -224,12 +228,13 @@ int embed_tokens(const float* x_in, int n_x, int l_in, const int* labels, const 
   VB_REQUIRE(Cv == 32, "embed: Cvae=%d unsupported (kernel is specialised for 32)", Cv);
   VB_REQUIRE(n_seq > 0 && l > 0, "embed: bad shape n_seq=%d l=%d", n_seq, l);
   VB_REQUIRE(first_rows >= l || (x_in && n_x > 0), "embed: x_in required");
-  const int n_rows = n_seq * l;
-  dim3 grid((C + 255) / 256, (n_rows + EMB_ROWS - 1) / EMB_ROWS);
-  VB_REQUIRE(grid.y <= 65535, "embed: too many rows (%d)", n_rows);
+  // without token input (only class rows) every output sequence is its own "input sequence"
+  const int nx = (x_in && n_x > 0 && n_x <= n_seq) ? n_x : n_seq;
+  dim3 grid((C + 255) / 256, (l + EMB_ROWS - 1) / EMB_ROWS, nx);
+  VB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "embed: too many rows / sequences (l=%d, n_x=%d)", l, nx);
   vb::ProfScope prof_scope(vb::PK_EMBED, st);
-  embed_kernel<<<grid, 256, 0, st>>>(x_in, n_x > 0 ? n_x : 1, l_in, labels, class_emb, pos_start, lvl_pos, w_word_t, b_word,
-                                     out, n_rows, l, first_rows, pos0, C);
+  embed_kernel<<<grid, 256, 0, st>>>(x_in, nx, l_in, labels, class_emb, pos_start, lvl_pos, w_word_t, b_word, out, n_seq, l,
+                                     first_rows, pos0, C);
   VB_CUDA_CHECK(cudaGetLastError());
   vb::count_launch();
   return VB_OK;
