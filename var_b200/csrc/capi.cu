@@ -191,6 +191,8 @@ extern "C" int var_b200_blocks(const var_b200_model_t* m, float* x, const float*
   at.n_seq = n_seq; at.H = m->H; at.Lq = l; at.Lmax = Lmax; at.q_pos0 = pos0; at.n_scales = m->n_scales;
   at.max_score = m->attn_max_score;
   at.q_log2 = m->attn_q_log2;
+  VB_REQUIRE(!m->attn_no_l2norm || (m->attn_max_score == 0.f && !m->attn_q_log2),
+             "blocks: attn_no_l2norm needs attn_max_score = 0 and attn_q_log2 = 0 (unbounded scores: general attention kernel)");
   level_ends(m, at.level_end);
   VB_REQUIRE(pos0 + l <= at.level_end[m->n_scales - 1], "blocks: positions beyond the pyramid");
   // Deferred LayerNorm (gemm_sm100.cuh, LNF): possible when the caller names the class of every sequence and every block
@@ -220,7 +222,7 @@ extern "C" int var_b200_blocks(const var_b200_model_t* m, float* x, const float*
     GemmParams p{};
     p.M = M; p.N = 3 * C; p.K = C; p.bias = bw.b_qkv;
     p.q_out = reinterpret_cast<__nv_bfloat16*>(w.q); p.k_cache = kc; p.v_cache = vc; p.q_scale = bw.q_scale;
-    p.C = C; p.H = m->H; p.pos0 = pos0; p.Lmax = Lmax; p.rows_per_seq = l;
+    p.C = C; p.H = m->H; p.pos0 = pos0; p.Lmax = Lmax; p.rows_per_seq = l; p.no_l2norm = m->attn_no_l2norm;
     if (ln1_deferred) consume(p, bw.u_qkv, bw.v_qkv);
     rc = gemm_launch(w.a, bw.w_qkv, p, EPI_QKV, st);
     if (rc) return rc;

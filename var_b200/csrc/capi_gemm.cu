@@ -20,6 +20,7 @@ extern "C" int var_b200_gemm_bf16(const var_b200_gemm_args_t* a, void* stream) {
   p.v_cache = reinterpret_cast<__nv_bfloat16*>(a->v_cache);
   p.q_scale = a->q_scale;
   p.C = a->C; p.H = a->H; p.pos0 = a->pos0; p.Lmax = a->Lmax;
+  p.no_l2norm = a->no_l2norm;
   p.gt = a->gt;
   p.gt_mod = a->gt_mod > 0 ? a->gt_mod : a->M;
   p.part = reinterpret_cast<float2*>(a->part);

@@ -35,6 +35,7 @@ struct GemmParams {
   __nv_bfloat16* v_cache;  // [n_seq, H, Lmax, 64]
   const float* q_scale;    // [H] = exp(min(scale_mul, ln 100))
   int C, H, pos0, Lmax;
+  int no_l2norm;           // attn_l2_norm=False (basic_var.py:72): q *= q_scale[head] only, k untouched
   // EPI_SCORE
   const int* gt;    // ground-truth token of row m = gt[m % gt_mod]
   int gt_mod;

@@ -322,7 +322,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
           float mul = 1.f;
-          if (which < 2) mul = qs / fmaxf(sqrtf(ss2.x + ss2.y), 1e-12f);  // F.normalize(dim=-1), eps 1e-12
+          if (p.no_l2norm) mul = qs;  // attn_l2_norm=False: softmax scale folded into q, k as it is (qs = 1 for k, v)
+          else if (which < 2) mul = qs / fmaxf(sqrtf(ss2.x + ss2.y), 1e-12f);  // F.normalize(dim=-1), eps 1e-12
           const float2 mul2 = make_float2(mul, mul);
           const size_t head_off = (size_t)head * (which == 0 ? p.rows_per_seq : p.Lmax) * 64;
           __nv_bfloat16* const dst_base = (which == 0 ? p.q_out : (which == 1 ? p.k_cache : p.v_cache)) + head_off;

@@ -30,7 +30,7 @@ class GemmArgs(C.Structure):
         ("bias", C.c_void_p), ("out", C.c_void_p),
         ("resid", C.c_void_p), ("gate", C.c_void_p), ("rows_per_seq", C.c_int), ("gate_ld", C.c_int),
         ("q_out", C.c_void_p), ("k_cache", C.c_void_p), ("v_cache", C.c_void_p), ("q_scale", C.c_void_p),
-        ("C", C.c_int), ("H", C.c_int), ("pos0", C.c_int), ("Lmax", C.c_int),
+        ("C", C.c_int), ("H", C.c_int), ("pos0", C.c_int), ("Lmax", C.c_int), ("no_l2norm", C.c_int),
         ("gt", C.c_void_p), ("gt_mod", C.c_int), ("part", C.c_void_p), ("gt_logit", C.c_void_p),
         ("ln_a_out", C.c_void_p), ("ln_scale", C.c_void_p), ("ln_part_out", C.c_void_p), ("ln_part_in", C.c_void_p),
         ("ln_parts", C.c_int), ("ln_C", C.c_int), ("ln_eps", C.c_float), ("ln_u", C.c_void_p), ("ln_v", C.c_void_p),
@@ -65,7 +65,7 @@ class ModelDesc(C.Structure):
         ("w_ada", C.c_void_p), ("b_ada", C.c_void_p), ("ada_rows", C.c_int), ("ada_gss", C.c_void_p),
         ("w_head", C.c_void_p), ("b_head", C.c_void_p), ("w_word", C.c_void_p), ("b_word", C.c_void_p),
         ("class_emb", C.c_void_p), ("pos_start", C.c_void_p), ("lvl_pos", C.c_void_p),
-        ("attn_max_score", C.c_float), ("attn_q_log2", C.c_int),
+        ("attn_max_score", C.c_float), ("attn_q_log2", C.c_int), ("attn_no_l2norm", C.c_int),
     ]
 
 

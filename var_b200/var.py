@@ -75,9 +75,6 @@ class VAR(nn.Module):
                  fused_if_available=True):
         super().__init__()
         assert embed_dim % num_heads == 0
-        if not attn_l2_norm:
-            raise NotImplementedError("attn_l2_norm=False (basic_var.py:72) is not built: every reference script uses "
-                                      "the build_vae_var default attn_l2_norm=True (models/__init__.py:15)")
         if embed_dim // num_heads != 64:
             raise NotImplementedError("the attention kernel is specialised for head_dim 64 (models/__init__.py:19-20)")
         if mlp_ratio != 4.:
@@ -531,8 +528,12 @@ class PackedModel:
         # |q.k| <= per-head scale exp(min(scale_mul, ln 100)) (basic_var.py:101-105), a model constant: with the largest
         # one <= 43 the attention kernel runs its bounded-score variant, and log2(e) is folded into q_scale so that the
         # scores leave the tensor core as base-2 exponents (one host read at pack time)
-        max_score = float(torch.stack([b.attn.scale_mul_1H11.detach().clamp_max(b.attn.max_scale_mul).exp().max()
-                                       for b in var.blocks]).max().item())
+        l2 = bool(var.blocks[0].attn.attn_l2_norm)
+        if l2:
+            max_score = float(torch.stack([b.attn.scale_mul_1H11.detach().clamp_max(b.attn.max_scale_mul).exp().max()
+                                           for b in var.blocks]).max().item())
+        else:  # attn_l2_norm=False (basic_var.py:72): unnormalised q, k -> unbounded scores, the general attention kernel
+            max_score = 0.0
         q_log2 = 0.0 < max_score <= 43.0
         q_mul = math.log2(math.e) if q_log2 else 1.0
         for i, b in enumerate(var.blocks):
@@ -540,7 +541,8 @@ class PackedModel:
             ts = dict(
                 w_qkv=bf(a.mat_qkv.weight),
                 b_qkv=f32(torch.cat((a.q_bias, torch.zeros_like(a.q_bias), a.v_bias))),
-                q_scale=f32(a.scale_mul_1H11.clamp_max(a.max_scale_mul).exp().reshape(-1) * q_mul),
+                q_scale=(f32(a.scale_mul_1H11.clamp_max(a.max_scale_mul).exp().reshape(-1) * q_mul) if l2 else
+                         torch.full((var.num_heads,), 0.25 / math.sqrt(a.head_dim), dtype=torch.float32, device=p0.device)),
                 w_proj=bf(a.proj.weight), b_proj=f32(a.proj.bias),
                 w_fc1=bf(b.ffn.fc1.weight), b_fc1=f32(b.ffn.fc1.bias),
                 w_fc2=bf(b.ffn.fc2.weight), b_fc2=f32(b.ffn.fc2.bias))
@@ -569,7 +571,7 @@ class PackedModel:
             setattr(m, k, v.data_ptr())
             keep.append(v)
         m.ada_rows = w_ada.shape[0]
-        m.attn_max_score, m.attn_q_log2 = max_score, int(q_log2)
+        m.attn_max_score, m.attn_q_log2, m.attn_no_l2norm = max_score, int(q_log2), int(not l2)
         m.ada_gss = gss.data_ptr() if gss is not None else None
         if gss is not None:
             keep.append(gss)
