@@ -136,6 +136,7 @@ sample_kernel(const float* __restrict__ logits, int B, int l, int V, int use_cfg
   __shared__ int sel_k;
   __shared__ float bval[ST / 32];
   __shared__ int bidx[ST / 32];
+  __shared__ int topp_n;
   const int r = blockIdx.x;  // row = b*l + pos
   const int tid = threadIdx.x;
   const float* lc = logits + (size_t)r * V;
@@ -156,34 +157,71 @@ sample_kernel(const float* __restrict__ logits, int B, int l, int V, int use_cfg
   }
 
   if (top_p > 0.f) {
-    // helpers.py:11-15. Ascending stable sort, softmax over the sorted row, inclusive cumsum (double accumulator as
-    // ATen's CPU cumsum), remove entries with cumsum <= 1-p except the last (largest).
-    for (int i = tid; i < Vpow2; i += ST) {
-      sk[i] = i < V ? xs[i] : INFINITY;
-      sv[i] = i;
+    // helpers.py:11-15: ascending stable sort, softmax over the sorted row, inclusive cumsum (double accumulator as
+    // ATen's CPU cumsum), entries with cumsum <= 1-p removed except the last (largest).
+    // Entries that top-k already removed are -inf: they sort to the front, add exactly 0.0 to every sum and are removed
+    // again - so only the SURVIVORS are compacted, padded to a power of two and sorted (900 of 4096 with the README's
+    // top_k: a 1024-element bitonic network, 55 instead of 78 steps on a quarter of the data). Every value the decision
+    // depends on is computed exactly as on the full sorted row: the softmax denominator adds the survivors in the
+    // per-thread groups their full-row positions would fall into, the probabilities are evaluated in parallel with the
+    // same float operations, and thread 0 only runs the order-preserving double accumulation over them.
+    const int lane = tid & 31;
+    if (tid == 0) topp_n = 0;
+    __syncthreads();
+    for (int v0 = 0; v0 < V; v0 += ST) {
+      const int v = v0 + tid;
+      const float x = v < V ? xs[v] : -INFINITY;
+      const bool keep = x != -INFINITY;
+      const unsigned mask = __ballot_sync(0xffffffffu, keep);
+      int base = 0;
+      if (lane == 0 && mask) base = atomicAdd(&topp_n, __popc(mask));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (keep) {
+        const int pos = base + __popc(mask & ((1u << lane) - 1u));
+        sk[pos] = x;
+        sv[pos] = v;
+      }
     }
     __syncthreads();
-    bitonic_sort(sk, sv, Vpow2);
+    const int ns = topp_n;                    // >= 1: the row maximum always survives top-k
+    int n2 = 1;
+    while (n2 < ns) n2 <<= 1;
+    for (int i2 = ns + tid; i2 < n2; i2 += ST) { sk[i2] = INFINITY; sv[i2] = 0x7fffffff; }
+    __syncthreads();
+    bitonic_sort(sk, sv, n2);
     float m = -INFINITY;
-    for (int i = tid; i < V; i += ST) m = fmaxf(m, sk[i]);
+    for (int i2 = tid; i2 < ns; i2 += ST) m = fmaxf(m, sk[i2]);
     m = block_max(m, red);
+    // survivor j sits at position (V - ns) + j of the full sorted row, which thread ((V - ns) + j) % ST summed
     float ps = 0.f;
-    for (int i = tid; i < V; i += ST) ps += expf(sk[i] - m);
+    for (int j2 = (((tid - (V - ns)) % ST) + ST) % ST; j2 < ns; j2 += ST) ps += expf(sk[j2] - m);
     const float sum = block_sum(ps, red);
-    // Entries already removed by top-k sort to the front as -inf and add exactly 0.0 to the cumulative sum: count them
-    // in parallel and start the (order-preserving, hence serial) double accumulation behind them. With top_k = 900 of
-    // 4096 that skips 78 % of the serial loop without changing a single rounding.
-    int ninf = 0;
-    for (int i = tid; i < V; i += ST) ninf += (sk[i] == -INFINITY) ? 1 : 0;
-    const int i0 = (int)(block_sum((float)ninf, red) + 0.5f);  // <= 4096 per thread: exact in fp32
+    for (int i2 = tid; i2 < ns; i2 += ST) sk[i2] = expf(sk[i2] - m) / sum;  // sorted probabilities, in place
+    __syncthreads();
     if (tid == 0) {
       double c = 0.0;
       const float lim = p_lim;
-      for (int i = i0; i < V - 1; ++i) {
-        c += (double)(expf(sk[i] - m) / sum);
-        if ((float)c <= lim) xs[sv[i]] = -INFINITY; else break;  // cumsum is monotone: nothing later is removed
+      int stop = 0;
+      // The running sum is monotone (probabilities >= 0, rounding is monotone): if it is still <= lim after eight more
+      // terms it was so after each of them. Eight independent loads / conversions per test keep the dependent chain to
+      // the eight double additions; the block in which the limit is crossed is walked term by term.
+      while (stop + 8 <= ns - 1) {
+        double c8 = c;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) c8 += (double)sk[stop + u];
+        if (!((float)c8 <= lim)) break;
+        c = c8;
+        stop += 8;
       }
+      for (; stop < ns - 1; ++stop) {  // nothing behind the first kept entry is removed
+        c += (double)sk[stop];
+        if (!((float)c <= lim)) break;
+      }
+      topp_n = stop;  // entries [0, stop) of the sorted survivors are removed
     }
+    __syncthreads();
+    const int stop = topp_n;
+    for (int i2 = tid; i2 < stop; i2 += ST) xs[sv[i2]] = -INFINITY;
     __syncthreads();
   }
 
