@@ -32,6 +32,26 @@ def test_capi_exports_every_declared_symbol():
     assert lib.var_b200_gemm_tile_n(1920) == 192 and lib.var_b200_gemm_tile_n(4096) == 256
 
 
+def test_binding_declares_the_signature_of_every_entry_point():
+    """Every function include/var_b200.h declares has its ctypes signature declared by var_b200/lib.py with as many
+    arguments as the header's prototype (a C entry point bound without argtypes would truncate 64-bit pointers /
+    sizes silently)."""
+    import re
+    from pathlib import Path
+    from var_b200 import lib as L
+    lib = L.load()
+    hdr = (Path(__file__).resolve().parent.parent / "include" / "var_b200.h").read_text()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = dict(re.findall(r"VAR_B200_API[^;(]*?\b(var_b200_\w+)\s*\(([^;]*?)\)\s*;", hdr, flags=re.S))
+    assert set(protos) == set(L.exported_symbols())
+    for name, args in protos.items():
+        args = args.strip()
+        n_args = 0 if args in ("", "void") else len(args.split(","))
+        fn = getattr(lib, name)
+        assert fn.argtypes is not None, f"{name}: no argtypes declared in var_b200/lib.py"
+        assert len(fn.argtypes) == n_args, f"{name}: header has {n_args} arguments, the binding {len(fn.argtypes)}"
+
+
 def test_custom_op_layer_registers_cuda_only_ops():
     """var_b200/ops.py: every C entry point of the path is a `var_b200::` torch.library op with a CUDA kernel only;
     CPU tensors are refused by the dispatcher (no fallback)."""
